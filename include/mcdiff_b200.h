@@ -1,0 +1,164 @@
+/* mcdiff_b200 -- C ABI of the B200 Monte-Carlo likelihood engine.
+ *
+ * Drop-in boundary for the two seams of annekegh/mcdiff's hot path.  The
+ * reference has no FFI: both seams are plain Python calls, so each entry point below names
+ * the reference function it replaces.
+ *
+ *   mcd_loglike_batch  <->  mcdiff.utils.log_like_lag            (lib/utils.py:355-368)
+ *                           as called by MCState.init_log_like   (lib/MCState.py:101-137)
+ *                           (+ scipy.linalg.expm propagators,     lib/utils.py:313)
+ *   mcd_mc_run         <->  mcdiff.mc.do_mc_cycles                (lib/mc.py:20-51)
+ *                           = MCState.mcmove_potential / mcmove_diffusion / mcmove_timezero /
+ *                             update_movewidth / update_temp      (lib/MCState.py:205-304,371-393)
+ *                           + Logger.log sampling                 (lib/log.py:35-58)
+ *   mcd_rad_loglike_batch <-> mcdiff.twod.rad_log_like_lag        (lib/twod.py:13-32)
+ *
+ * Conventions
+ *   - plain C, no exceptions, no stdout; every function returns 0 on success, a negative
+ *     MCD_E_* code for argument errors, or a positive cudaError_t value.
+ *   - every array argument is a DEVICE pointer owned by the caller (row-major, contiguous)
+ *     unless the name ends in _host.  The library keeps private copies of the problem
+ *     description (mcd_problem) and never frees caller memory.
+ *   - all calls are asynchronous on the cudaStream_t passed as `stream` (0 = default
+ *     stream); the caller synchronises.  One handle per device per host thread.
+ *   - counts[l][i][j] = number of observed transitions j -> i at lag l   (lib/tools/extract.py:86-87)
+ *     w[i] lives between bin i and i+1 (pbc: w[n-1] couples bin n-1 and bin 0)  (lib/utils.py:96-97)
+ */
+#ifndef MCDIFF_B200_H
+#define MCDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCD_VERSION 100
+
+enum {
+  MCD_OK = 0,
+  MCD_E_ARG = -1,        /* bad argument (null pointer, size out of range) */
+  MCD_E_UNSUPPORTED = -2,/* e.g. --pull (non-symmetrisable generator), n too large */
+  MCD_E_NOMEM = -3,
+  MCD_E_NODEVICE = -4
+};
+
+/* per-profile / per-chain status bits */
+enum {
+  MCD_ST_EIG_NOCONV = 1, /* in-kernel eigensolver did not converge (non-finite input) */
+  MCD_ST_NAN_TRIAL = 2   /* a trial log-likelihood was NaN; the move was skipped like
+                            lib/MCState.py:251 does */
+};
+
+typedef struct mcd_handle mcd_handle;
+typedef struct mcd_problem mcd_problem;
+
+/* Static description of one inference problem: what Transitions + Model hold in the
+ * reference (lib/transitions.py:22-70, lib/model.py:29-149). */
+typedef struct {
+  int32_t n;        /* number of bins = dim_v = dim_trans */
+  int32_t pbc;      /* 1: periodic (dim_w = n), 0: reflecting ends (dim_w = n-1) */
+  int32_t nlag;     /* number of lag times / count matrices (<= 64) */
+  int32_t ncosF;    /* 0: per-bin F moves, >0: v = v_basis . v_coeff  (<= 64) */
+  int32_t ncosD;    /* 0: per-bin ln D moves, >0: w = w_basis . w_coeff (<= 64) */
+  int32_t reserved;
+  const double* lagtimes;  /* [nlag]                       device */
+  const int32_t* counts;   /* [nlag][n][n]                 device */
+  const double* v_basis;   /* [n][ncosF] or NULL           device (lib/model.py:93-96) */
+  const double* w_basis;   /* [dim_w][ncosD] or NULL       device (lib/model.py:98-102) */
+  const double* string_vecs; /* [dim_w][dim_w] or NULL     device (lib/utils.py:294-305) */
+  double spring_k;         /* -k option; <= 0 disables     (lib/MCState.py:121-124,287-289) */
+  double clip;             /* lower bound of P before log: 1e-10 (lib/utils.py:317) */
+} mcd_problem_desc;
+
+/* Monte-Carlo schedule: what MCState.set_MC_params holds (lib/MCState.py:29-61). */
+typedef struct {
+  double num_mc_update;  /* --nmc_update (float in the reference CLI); 0 = never adapt */
+  double dtemp;          /* (Tend - T)/(nmc/nmc_update - 1), lib/MCState.py:46-51 */
+  double min_lt;         /* smallest lag time, lib/transitions.py:39 */
+  int32_t move_timezero; /* --t0 */
+  int32_t sample_every;  /* Logger.freq = 100, lib/log.py:9; 0 = no samples */
+  int32_t refresh_every; /* cold eigen re-solve period (0 = never); 512 is a good default */
+  int32_t use_tape;      /* 1: proposals and uniforms come from tape_u / tape_idx */
+  uint64_t seed;         /* Philox4x32-10 key */
+  int64_t chain_offset;  /* global index of chain 0 (chains shard over GPUs) */
+  int64_t tape_stride;   /* 0: one tape for all chains, else per-chain stride (in steps) */
+  int64_t nsamples_cap;  /* rows per chain in `samples` */
+} mcd_mc_params;
+
+#define MCD_NSCAL 8   /* scal[c] = {log_like, timezero, dv, dw, dtimezero, temp, -, -} */
+#define MCD_NCOUNT 8  /* counters[c] = {naccv, naccw, nacctimezero, naccv_update, naccw_update,
+                                        step (imc), status bits, eigen sweeps} */
+
+/* Per-chain state (structure of arrays, C = number of chains), all device pointers. */
+typedef struct {
+  double* v;            /* [C][n] */
+  double* w;            /* [C][dim_w] */
+  double* vcoef;        /* [C][ncosF]  (ignored when ncosF == 0) */
+  double* wcoef;        /* [C][ncosD]  (ignored when ncosD == 0) */
+  double* scal;         /* [C][MCD_NSCAL] */
+  int64_t* counters;    /* [C][MCD_NCOUNT] */
+  int64_t* naccv_coeff; /* [C][max(ncosF,1)]  lib/MCState.py:130-133 */
+  int64_t* naccw_coeff; /* [C][max(ncosD,1)] */
+  double* basis;        /* [C][basis_elems] warm-start eigenvectors kept between launches, or NULL */
+  int32_t* basis_valid; /* [C] */
+  const double* tape_u;   /* [nsteps][5] = u_choice,u_delta,u_accept,u_t0_delta,u_t0_accept (use_tape) */
+  const int32_t* tape_idx;/* [nsteps]    = bin / coefficient index of the move           (use_tape) */
+  uint8_t* decisions;   /* [C][nsteps] or NULL: bit0 move accepted, bit1 t0 accepted, bits2-3 move
+                           type (1 potential, 2 diffusion) */
+  double* ll_try;       /* [C][nsteps] or NULL: trial log-likelihood of the main move */
+  double* samples;      /* [C][nsamples_cap][sample_dim] or NULL; row = {log_like, timezero, dv, dw,
+                           dtimezero, temp, v|v_coeff..., w|w_coeff...}  (lib/log.py:35-58) */
+} mcd_chain_io;
+
+int mcd_version(void);
+const char* mcd_error_string(int code);
+
+int mcd_create(int device, mcd_handle** out);
+int mcd_destroy(mcd_handle* h);
+
+/* Copies the description into library-owned device memory (counts are re-packed to a padded
+ * int32 layout).  `--pull` is not representable (non-symmetrisable): use the host reference. */
+int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* desc, void* stream, mcd_problem** out);
+int mcd_problem_destroy(mcd_problem* p);
+/* np: padded bin count, basis_elems: doubles per chain in mcd_chain_io.basis,
+ * sample_dim: doubles per sample row, in_smem: 1 when the n x n work matrices fit in shared memory */
+int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, int32_t* sample_dim,
+                     int32_t* in_smem);
+
+/* log L of B profiles: out_ll[b] = sum_l sum_ij counts[l,i,j] log(max(P_l[i,j], clip)) with
+ * P_l = expm(lag_l R(v_b, w_b)).  lagtimes == NULL uses the problem's lag times, otherwise
+ * [B][nlag] per-profile lag times (time-offset moves).  out_P (optional) receives
+ * [B][nlag][n][n] propagators, status (optional) [B] status bits.
+ * Replaces log_like_lag, lib/utils.py:355-368. */
+int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
+                      const double* lagtimes, double* out_ll, double* out_P, int32_t* status, void* stream);
+
+/* Advance every chain by nsteps Monte-Carlo steps (one CTA per chain).
+ * Replaces the loop body of do_mc_cycles, lib/mc.py:27-51. */
+int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params, const mcd_chain_io* io,
+               int32_t nchains, int32_t nsteps, void* stream);
+
+/* Radial (2-D) likelihood, lib/twod.py:13-32,89-130: for each of B radial profiles
+ * out_ll[b] = sum_l sum_{k,i,j} counts[l,k,i,j] log(max(P_l[k,i,j], clip)),
+ * P_l[k] = sum_m bessels[m,k] expm(lag_l (R(v,w) - diag(exp(wrad_b) b0zeros[m]^2 / dim_rad^2))).
+ * v [n], w [dim_w] are shared by all profiles (frozen in radial mode, lib/mc.py:29-30),
+ * wrad [B][n], counts [nlag][dim_rad][n][n] (double, as lib/reading.py:129),
+ * bessels [lmax][dim_rad], b0zeros [lmax]. out_P optional [B][nlag][dim_rad][n][n]. */
+int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
+                          const double* v, const double* w, const double* lagtimes, const double* counts,
+                          const double* bessels, const double* b0zeros, double clip, int32_t B,
+                          const double* wrad, double* out_ll, double* out_P, int32_t* status, void* stream);
+
+/* FP64 FMA micro-benchmark: fills *tflops with the measured dense DFMA rate of the device
+ * (the roofline denominator bench.py reports against).  Synchronous. */
+int mcd_fp64_peak(mcd_handle* h, double* tflops);
+
+/* Number of kernels this library has launched through the handle (bench.py's gpu_launches). */
+int64_t mcd_launch_count(const mcd_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCDIFF_B200_H */

@@ -1,0 +1,823 @@
+// One Monte-Carlo chain = one CTA.  Everything a chain touches per step lives in shared
+// memory: the eigenvector matrix XT (row k = k-th eigenvector of the symmetrised rate
+// matrix), a second n x n work matrix B2 (S.X / rotated matrix / scaled eigenvectors), and
+// the profile vectors.  Count matrices are identical for all chains and stay L2 resident.
+//
+// Path restated here (reference file:line, /root/reference):
+//   rate matrix                 lib/utils.py:77-131     -> build_S (symmetrised form)
+//   P = expm(lag R), log L      lib/utils.py:307-368    -> jacobi + loglike
+//   moves / Metropolis          lib/MCState.py:205-304  -> mc_step
+//   width / temperature update  lib/MCState.py:371-393  -> mc_step (tail)
+//   step order, sampling        lib/mc.py:27-51, lib/log.py:35-58
+//
+// Math: with Pi = diag(exp(-v)), S = Pi^-1/2 R Pi^1/2 is symmetric, S[i,i+1] = exp(w_i),
+// S[i,i] = R[i,i]; P = Pi^1/2 V exp(t Lambda) V^T Pi^-1/2, one eigendecomposition serves
+// every lag time.
+#pragma once
+#include "mcd_exec.cuh"
+
+namespace mcd {
+
+constexpr int kMaxLag = 64;
+constexpr int kMaxCoef = 64;
+constexpr int kMaxSweeps = 60;
+
+struct Problem {
+  int n, np, ld, dim_w, pbc, nlag;
+  int ncosF, ncosD;
+  const double* lagtimes;  // [nlag]
+  const int* counts;       // [nlag][np][np]  (padded, counts[l][i][j] = # transitions j -> i)
+  const double* v_basis;   // [n][ncosF]      (null when ncosF == 0)
+  const double* w_basis;   // [dim_w][ncosD]  (null when ncosD == 0)
+  const double* svecs;     // [dim_w][dim_w]  Laplacian eigenvectors (null when spring_k <= 0)
+  double spring_k;
+  double clip;
+};
+
+struct McParams {
+  double num_mc_update;  // lib/MCState.py:382 (parsed as float by the CLI)
+  double dtemp;          // lib/MCState.py:46-51
+  double min_lt;         // lib/MCState.py:207
+  int move_timezero;
+  int sample_every;      // lib/log.py:9  (100)
+  int refresh_every;     // cold re-solve period (bounds orthogonality drift of the warm start)
+  int use_tape;          // 1: proposals/uniforms from the host tape, 0: Philox4x32-10
+  unsigned long long seed;
+  long long chain_offset;  // global id of chain 0 of this launch (multi-GPU sharding)
+  long long tape_stride;   // 0: all chains share one tape, else per-chain stride in steps
+  long long nsamples_cap;  // rows available per chain in the sample buffer
+};
+
+// scal[] slots
+enum { S_LL = 0, S_T0, S_DV, S_DW, S_DT0, S_TEMP, S_NSCAL = 8 };
+// counters[] slots
+enum { C_NACCV = 0, C_NACCW, C_NACCT0, C_NACCV_UPD, C_NACCW_UPD, C_STEP, C_STATUS, C_SWEEPS, C_NCOUNT = 8 };
+// status bits
+enum { ST_JACOBI_NOCONV = 1, ST_NAN_TRIAL = 2 };
+
+struct ChainIO {
+  double* v;        // [C][n]
+  double* w;        // [C][dim_w]
+  double* vcoef;    // [C][ncosF]
+  double* wcoef;    // [C][ncosD]
+  double* scal;     // [C][S_NSCAL]
+  long long* counters;     // [C][C_NCOUNT]
+  long long* naccv_coeff;  // [C][max(ncosF,1)]
+  long long* naccw_coeff;  // [C][max(ncosD,1)]
+  double* basis;    // [C][np*ld] warm-start eigenvectors (may be null)
+  int* basis_valid; // [C]
+  // optional per-step records
+  const double* tape_u;   // [steps][5]
+  const int* tape_idx;    // [steps]
+  unsigned char* decisions;  // [C][nsteps]  bit0 accepted, bit1 t0 accepted, bits 2-3 move type
+  double* ll_try;            // [C][nsteps]
+  double* samples;           // [C][nsamples_cap][sample_dim]
+};
+
+MCD_HOSTDEV int sample_dim(const Problem& P) {
+  return 6 + (P.ncosF > 0 ? P.ncosF : P.n) + (P.ncosD > 0 ? P.ncosD : P.dim_w);
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (step_lo, step_hi, chain, stream)
+// ---------------------------------------------------------------------------------------
+MCD_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+MCD_HD double u53(uint32_t hi, uint32_t lo) {
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ---------------------------------------------------------------------------------------
+struct Scalars {
+  double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring;
+  long long naccv, naccw, nacct0, naccv_upd, naccw_upd, step, status, sweeps;
+  int move, idx, accepted, accepted_t0, nsamp, basis_is_trial, do_t0, pad;
+};
+
+struct Smem {
+  double* XT;
+  double* B2;
+  double *a, *b, *ea, *eb, *lam, *el;
+  double *v, *w, *vt, *wt;
+  double *vc, *wc, *ct;
+  double *lag, *lag_try;
+  double *rc, *rs;
+  double* red;
+  int *rp, *rq;
+  unsigned char* tiles;    // 2 bytes per tile (ib, jb), ib <= jb
+  unsigned char* jblocks;  // 2 bytes per Jacobi block (ka, kb), ka < kb
+  Scalars* sc;
+  int ntiles, nblk;
+};
+
+MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
+  size_t d = (size_t)np * 10 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32;
+  size_t nb = np / 4, h = np / 2;
+  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + sizeof(Scalars) + 64;
+  return (bytes + 15) & ~(size_t)15;
+}
+MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
+
+// mat: storage for XT and B2 (2*np*ld doubles; shared or global), vec: shared storage.
+MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
+  Smem s;
+  const int np = P.np;
+  s.XT = mat;
+  s.B2 = mat + (size_t)np * P.ld;
+  double* d = reinterpret_cast<double*>(vec);
+  s.a = d; d += np;
+  s.b = d; d += np;
+  s.ea = d; d += np;
+  s.eb = d; d += np;
+  s.lam = d; d += np;
+  s.el = d; d += np;
+  s.v = d; d += np;
+  s.w = d; d += np;
+  s.vt = d; d += np;
+  s.wt = d; d += np;
+  s.vc = d; d += kMaxCoef;
+  s.wc = d; d += kMaxCoef;
+  s.ct = d; d += kMaxCoef;
+  s.lag = d; d += kMaxLag;
+  s.lag_try = d; d += kMaxLag;
+  s.rc = d; d += np / 2;
+  s.rs = d; d += np / 2;
+  s.red = d; d += 32;
+  s.sc = reinterpret_cast<Scalars*>(d);
+  d += (sizeof(Scalars) + 7) / 8;
+  int* ip = reinterpret_cast<int*>(d);
+  s.rp = ip; ip += np / 2;
+  s.rq = ip; ip += np / 2;
+  unsigned char* c = reinterpret_cast<unsigned char*>(ip);
+  const int nb = np / 4, h = np / 2;
+  s.ntiles = nb * (nb + 1) / 2;
+  s.nblk = h * (h - 1) / 2;
+  s.tiles = c; c += 2 * s.ntiles;
+  s.jblocks = c;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+template <class Exec>
+struct Chain {
+  Exec& ex;
+  const Problem& P;
+  Smem s;
+
+  MCD_HD Chain(Exec& e, const Problem& p, const Smem& sm) : ex(e), P(p), s(sm) {}
+
+  // Tile list: the upper triangle of the (np/4)^2 tile grid, enumerated patch by patch
+  // (4 x 8 tiles) so that the 32 lanes of a warp share operand rows (shared-memory
+  // broadcast).  Jacobi block list: all pair-slot pairs ka < kb.
+  MCD_HD void build_tables() {
+    ex.single([&]() {
+      const int nb = P.np / 4;
+      int t = 0;
+      for (int pi = 0; pi < nb; pi += 4)
+        for (int pj = (pi / 8) * 8; pj < nb; pj += 8)
+          for (int ib = pi; ib < pi + 4 && ib < nb; ++ib)
+            for (int jb = pj; jb < pj + 8 && jb < nb; ++jb)
+              if (ib <= jb) {
+                s.tiles[2 * t] = (unsigned char)ib;
+                s.tiles[2 * t + 1] = (unsigned char)jb;
+                ++t;
+              }
+      const int h = P.np / 2;
+      int q = 0;
+      for (int ka = 0; ka < h; ++ka)
+        for (int kb = ka + 1; kb < h; ++kb) {
+          s.jblocks[2 * q] = (unsigned char)ka;
+          s.jblocks[2 * q + 1] = (unsigned char)kb;
+          ++q;
+        }
+    });
+  }
+
+  // Symmetrised generator of lib/utils.py:77-131: diagonal a (= R[i,i]), coupling
+  // b[i] = exp(w_i) between bin i and i+1 (b[n-1] = periodic corner), and the similarity
+  // scalings ea = exp(-v/2), eb = exp(+v/2).
+  MCD_HD void build_S(const double* v, const double* w) {
+    const int n = P.n, np = P.np, pbc = P.pbc, dim_w = P.dim_w;
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += Exec::nthr()) {
+        if (i < n) {
+          const double vi = v[i];
+          double ru = 0.0, rd = 0.0;
+          if (i < n - 1) ru = exp(w[i] - 0.5 * (v[i + 1] - vi));
+          else if (pbc) ru = exp(w[n - 1] - 0.5 * (v[0] - vi));
+          if (i > 0) rd = exp(w[i - 1] + 0.5 * (vi - v[i - 1]));
+          else if (pbc) rd = exp(w[n - 1] + 0.5 * (vi - v[n - 1]));
+          s.a[i] = -rd - ru;
+          s.b[i] = (i < dim_w) ? exp(w[i]) : 0.0;
+          s.ea[i] = exp(-0.5 * vi);
+          s.eb[i] = exp(0.5 * vi);
+        } else {
+          s.a[i] = 0.0; s.b[i] = 0.0; s.ea[i] = 0.0; s.eb[i] = 0.0;
+        }
+      }
+    });
+    double sc = ex.max([&](int tid) {
+      double m = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, fabs(s.a[i]));
+      return m;
+    });
+    ex.single([&]() { s.sc->scale = sc; });
+  }
+
+  // Cold start: XT = identity, B2 = dense S.
+  MCD_HD void cold_init() {
+    const int n = P.n, np = P.np, ld = P.ld;
+    ex.par([&](int tid) {
+      for (int e = tid; e < np * np; e += Exec::nthr()) {
+        const int i = e / np, j = e - i * np;
+        s.XT[i * ld + j] = (i == j) ? 1.0 : 0.0;
+        double val = 0.0;
+        if (i < n && j < n) {
+          if (i == j) val = s.a[i];
+          else if (j == i + 1) val = s.b[i];
+          else if (i == j + 1) val = s.b[j];
+          else if (P.pbc && ((i == 0 && j == n - 1) || (j == 0 && i == n - 1))) val = s.b[n - 1];
+        }
+        s.B2[i * ld + j] = val;
+      }
+    });
+  }
+
+  // Warm start: B2 <- XT S XT^T with the eigenvectors of the previous trial matrix.
+  MCD_HD void warm_form() {
+    const int n = P.n, np = P.np, ld = P.ld, nb = np / 4;
+    // (1) B2[j][r] = (S x_j)[r]
+    ex.par([&](int tid) {
+      for (int e = tid; e < np * np; e += Exec::nthr()) {
+        const int j = e / np, r = e - j * np;
+        double val = 0.0;
+        if (r < n) {
+          const double* x = s.XT + j * ld;
+          const int rm = (r == 0) ? n - 1 : r - 1;
+          const int rp = (r == n - 1) ? 0 : r + 1;
+          val = s.a[r] * x[r] + s.b[rm] * x[rm] + s.b[r] * x[rp];
+        }
+        s.B2[j * ld + r] = val;
+      }
+    });
+    // (2) A'_ij = sum_r XT[i][r] B2[j][r] for tile rows {ib + nb a} x {jb + nb b}
+    ex.par([&](int tid) {
+      double* acc = ex.regs(tid);
+      if (tid < s.ntiles) {
+        const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
+        double c[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) c[a][b] = 0.0;
+        const double* x0 = s.XT + ib * ld;
+        const double* y0 = s.B2 + jb * ld;
+        const int sx = nb * ld;
+        for (int r = 0; r < np; r += 2) {
+          d2 xa[4], yb[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) xa[a] = ld2(x0 + a * sx + r);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) yb[b] = ld2(y0 + b * sx + r);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              c[a][b] = fma(xa[a].x, yb[b].x, c[a][b]);
+              c[a][b] = fma(xa[a].y, yb[b].y, c[a][b]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a * 4 + b] = c[a][b];
+      }
+    });
+    // (3) mirror-store (symmetric by construction)
+    ex.par([&](int tid) {
+      const double* acc = ex.regs(tid);
+      if (tid < s.ntiles) {
+        const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) {
+            const int i = ib + nb * a, j = jb + nb * b;
+            if (ib == jb && a > b) continue;  // keep one representative inside diagonal tiles
+            const double val = acc[a * 4 + b];
+            s.B2[i * ld + j] = val;
+            s.B2[j * ld + i] = val;
+          }
+      }
+    });
+  }
+
+  // Parallel cyclic Jacobi (round-robin ordering) on the symmetric matrix in B2,
+  // accumulating the rotations into the rows of XT.  Returns the number of sweeps, or -1
+  // when the off-diagonal part did not vanish (NaN input or kMaxSweeps exceeded).
+  MCD_HD int jacobi() {
+    const int np = P.np, ld = P.ld, h = np / 2, m = np - 1;
+    const double scale = s.sc->scale;
+    const double tol = 2.0e-15 * scale;
+    const double skip = 1.0e-18 * scale;
+    int sweeps = 0;
+    for (;;) {
+      double off = ex.max([&](int tid) {
+        double mx = 0.0;
+        for (int e = tid; e < np * np; e += Exec::nthr()) {
+          const int i = e / np, j = e - i * np;
+          if (j > i) {
+            const double t = fabs(s.B2[i * ld + j]);
+            mx = (t > mx || t != t) ? t : mx;  // propagate NaN
+          }
+        }
+        return mx;
+      });
+      if (off != off) { sweeps = -1; break; }
+      if (off <= tol) break;
+      if (sweeps >= kMaxSweeps) { sweeps = -1; break; }
+      for (int t = 0; t < m; ++t) {
+        // J1: rotation of every pair of this round, from the 2x2 diagonal blocks
+        ex.par([&](int tid) {
+          if (tid < h) {
+            int p, q;
+            if (tid == 0) { p = m; q = t; }
+            else { p = (t + tid) % m; q = (t - tid + m) % m; }
+            const double apq = s.B2[p * ld + q];
+            double c = 1.0, sn = 0.0;
+            if (fabs(apq) > skip) {
+              const double app = s.B2[p * ld + p], aqq = s.B2[q * ld + q];
+              const double theta = (aqq - app) / (2.0 * apq);
+              const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+              c = 1.0 / sqrt(tt * tt + 1.0);
+              sn = tt * c;
+              s.B2[p * ld + p] = app - tt * apq;
+              s.B2[q * ld + q] = aqq + tt * apq;
+              s.B2[p * ld + q] = 0.0;
+              s.B2[q * ld + p] = 0.0;
+            }
+            s.rc[tid] = c; s.rs[tid] = sn; s.rp[tid] = p; s.rq[tid] = q;
+          }
+        });
+        // J2: two-sided update of every off-diagonal 2x2 block + rotation of the XT rows
+        ex.par([&](int tid) {
+          for (int e = tid; e < s.nblk; e += Exec::nthr()) {
+            const int ka = s.jblocks[2 * e], kb = s.jblocks[2 * e + 1];
+            const double sa = s.rs[ka], sb = s.rs[kb];
+            if (sa == 0.0 && sb == 0.0) continue;
+            const double ca = s.rc[ka], cb = s.rc[kb];
+            const int pa = s.rp[ka], qa = s.rq[ka], pb = s.rp[kb], qb = s.rq[kb];
+            const double m00 = s.B2[pa * ld + pb], m01 = s.B2[pa * ld + qb];
+            const double m10 = s.B2[qa * ld + pb], m11 = s.B2[qa * ld + qb];
+            const double r00 = ca * m00 - sa * m10, r01 = ca * m01 - sa * m11;
+            const double r10 = sa * m00 + ca * m10, r11 = sa * m01 + ca * m11;
+            const double n00 = cb * r00 - sb * r01, n01 = sb * r00 + cb * r01;
+            const double n10 = cb * r10 - sb * r11, n11 = sb * r10 + cb * r11;
+            s.B2[pa * ld + pb] = n00; s.B2[pb * ld + pa] = n00;
+            s.B2[pa * ld + qb] = n01; s.B2[qb * ld + pa] = n01;
+            s.B2[qa * ld + pb] = n10; s.B2[pb * ld + qa] = n10;
+            s.B2[qa * ld + qb] = n11; s.B2[qb * ld + qa] = n11;
+          }
+          const int half = np / 2;  // XT rows in chunks of 2 columns
+          for (int e = tid; e < h * half; e += Exec::nthr()) {
+            const int k = e / half, r = (e - k * half) * 2;
+            const double sn = s.rs[k];
+            if (sn == 0.0) continue;
+            const double c = s.rc[k];
+            double* xp = s.XT + s.rp[k] * ld + r;
+            double* xq = s.XT + s.rq[k] * ld + r;
+            const d2 x = ld2(xp), y = ld2(xq);
+            st2(xp, c * x.x - sn * y.x, c * x.y - sn * y.y);
+            st2(xq, sn * x.x + c * y.x, sn * x.y + c * y.y);
+          }
+        });
+      }
+      ++sweeps;
+    }
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += Exec::nthr()) s.lam[i] = s.B2[i * ld + i];
+    });
+    return sweeps;
+  }
+
+  // log L = sum_lag sum_ij N[lag,i,j] log(max(P_ij, clip)),  P = Pi^1/2 XT^T e^{t lam} XT Pi^-1/2
+  // (lib/utils.py:307-368).  B2 is overwritten with the scaled eigenvectors of each lag.
+  // When Pout != nullptr the propagators are also written ([nlag][n][n], row-major).
+  MCD_HD double loglike(const double* lagt, double* Pout) {
+    const int n = P.n, np = P.np, ld = P.ld;
+    ex.par([&](int tid) { ex.regs(tid)[0] = 0.0; });
+    for (int l = 0; l < P.nlag; ++l) {
+      const double t = lagt[l];
+      ex.par([&](int tid) {
+        for (int k = tid; k < np; k += Exec::nthr()) s.el[k] = exp(t * s.lam[k]);
+      });
+      ex.par([&](int tid) {
+        const int half = np / 2;
+        for (int e = tid; e < np * half; e += Exec::nthr()) {
+          const int k = e / half, r = (e - k * half) * 2;
+          const d2 x = ld2(s.XT + k * ld + r);
+          const double f = s.el[k];
+          st2(s.B2 + k * ld + r, x.x * f, x.y * f);
+        }
+      });
+      const int* cnt = P.counts + (size_t)l * np * np;
+      double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
+      ex.par([&](int tid) {
+        double part = 0.0;
+        for (int tt = tid; tt < s.ntiles; tt += Exec::nthr()) {
+          const int ib = s.tiles[2 * tt], jb = s.tiles[2 * tt + 1];
+          const int i0 = ib * 4, j0 = jb * 4;
+          // counts of the tile and of its mirror, fetched before the k loop (L2 latency)
+          i4 nij[4], nji[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            nij[a] = ld4i(cnt + (size_t)(i0 + a) * np + j0);
+            nji[a] = ld4i(cnt + (size_t)(j0 + a) * np + i0);
+          }
+          double c[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) c[a][b] = 0.0;
+          const double* xi = s.XT + i0;
+          const double* wj = s.B2 + j0;
+#pragma unroll 2
+          for (int k = 0; k < np; ++k) {
+            const d2 x01 = ld2(xi + k * ld), x23 = ld2(xi + k * ld + 2);
+            const d2 w01 = ld2(wj + k * ld), w23 = ld2(wj + k * ld + 2);
+            const double xa[4] = {x01.x, x01.y, x23.x, x23.y};
+            const double wb[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) c[a][b] = fma(xa[a], wb[b], c[a][b]);
+          }
+          const double clip = P.clip;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int i = i0 + a;
+            const int nrow[4] = {nij[a].x, nij[a].y, nij[a].z, nij[a].w};
+            const double eai = s.ea[i], ebi = s.eb[i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int j = j0 + b;
+              const double g = c[a][b];
+              const double pij = eai * g * s.eb[j];
+              if (nrow[b] != 0) part += (double)nrow[b] * log(fmax(pij, clip));
+              if (Pl && i < n && j < n) Pl[(size_t)i * n + j] = pij;
+              if (ib != jb) {
+                const int nm = (a == 0) ? nji[b].x : (a == 1) ? nji[b].y : (a == 2) ? nji[b].z : nji[b].w;
+                const double pji = s.ea[j] * g * ebi;
+                if (nm != 0) part += (double)nm * log(fmax(pji, clip));
+                if (Pl && i < n && j < n) Pl[(size_t)j * n + i] = pji;
+              }
+            }
+          }
+        }
+        ex.regs(tid)[0] += part;
+      });
+    }
+    return ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+  }
+
+  // Full likelihood of the profile (v, w) at lag times lagt.
+  // mode 0: warm start from the eigenvectors in XT, 1: cold start, 2: reuse XT/lam as they are
+  // (same v, w as the last solve; only the lag times changed).
+  MCD_HD double evaluate(const double* v, const double* w, const double* lagt, int mode, double* Pout,
+                         int* sweeps_out) {
+    int sw = 0;
+    if (mode != 2) {
+      int cold = mode || (s.ntiles > Exec::nthr());  // warm product keeps one tile per thread
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        build_S(v, w);
+        if (cold) cold_init();
+        else warm_form();
+        sw = jacobi();
+        if (sw >= 0 || cold) break;
+        cold = 1;  // robust fallback: restart from the identity
+      }
+    }
+    if (sweeps_out) *sweeps_out = sw;
+    if (sw < 0) {
+      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      return nan("");
+    }
+    return loglike(lagt, Pout);
+  }
+
+  MCD_HD double string_energy(const double* w) {
+    // k/2 sum (dw)^2 (+ periodic wrap)   lib/utils.py:283-292
+    const int dim_w = P.dim_w;
+    double e = ex.sum([&](int tid) {
+      double acc = 0.0;
+      for (int i = tid; i < dim_w - 1; i += Exec::nthr()) {
+        const double d = w[i + 1] - w[i];
+        acc += d * d;
+      }
+      if (tid == 0 && P.pbc) {
+        const double d = w[0] - w[dim_w - 1];
+        acc += d * d;
+      }
+      return acc;
+    });
+    return 0.5 * P.spring_k * e;
+  }
+
+  // ------------------------------------------------------------------------------------
+  // The MC loop of lib/mc.py:27-51 for one chain.
+  // ------------------------------------------------------------------------------------
+  MCD_HD void run(const McParams& mp, const ChainIO& io, long long chain, int nsteps) {
+    const int n = P.n, np = P.np, ld = P.ld, dim_w = P.dim_w;
+    const int ncosF = P.ncosF, ncosD = P.ncosD;
+    const int sdim = sample_dim(P);
+    Scalars* sc = s.sc;
+    build_tables();
+    // ---- load chain state ----
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += Exec::nthr()) {
+        s.v[i] = (i < n) ? io.v[chain * n + i] : 0.0;
+        s.w[i] = (i < dim_w) ? io.w[chain * dim_w + i] : 0.0;
+      }
+      for (int i = tid; i < ncosF; i += Exec::nthr()) s.vc[i] = io.vcoef[chain * ncosF + i];
+      for (int i = tid; i < ncosD; i += Exec::nthr()) s.wc[i] = io.wcoef[chain * ncosD + i];
+      if (tid == 0) {
+        const double* q = io.scal + chain * S_NSCAL;
+        sc->ll_cur = q[S_LL]; sc->timezero = q[S_T0]; sc->dv = q[S_DV]; sc->dw = q[S_DW];
+        sc->dt0 = q[S_DT0]; sc->temp = q[S_TEMP];
+        const long long* c = io.counters + chain * C_NCOUNT;
+        sc->naccv = c[C_NACCV]; sc->naccw = c[C_NACCW]; sc->nacct0 = c[C_NACCT0];
+        sc->naccv_upd = c[C_NACCV_UPD]; sc->naccw_upd = c[C_NACCW_UPD];
+        sc->step = c[C_STEP]; sc->status = c[C_STATUS]; sc->sweeps = c[C_SWEEPS];
+        sc->nsamp = 0; sc->e_spring = 0.0;
+      }
+    });
+    ex.par([&](int tid) {
+      for (int l = tid; l < P.nlag; l += Exec::nthr()) s.lag[l] = P.lagtimes[l] + sc->timezero;
+    });
+    int have_basis = 0;
+    if (io.basis && io.basis_valid[chain]) {
+      const double* src = io.basis + (size_t)chain * np * ld;
+      ex.par([&](int tid) {
+        for (int e = tid; e < np * ld; e += Exec::nthr()) s.XT[e] = src[e];
+      });
+      have_basis = 1;
+    }
+    long long since_refresh = 0;
+
+    for (int it = 0; it < nsteps; ++it) {
+      // Two phases per step with ONE inlined likelihood evaluation site:
+      // phase 0 = potential/diffusion move (lib/mc.py:33-39), phase 1 = time-offset move
+      // (lib/mc.py:40-42).
+      int move = 0;
+      for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1 && !(mp.move_timezero && sc->dt0 > 0.0)) break;
+        // ---- proposal (thread 0): lib/MCState.py:235-245, 269-280, 206-208 ----
+        ex.single([&]() {
+          const long long imc = sc->step;
+          const long long ts = (long long)it + mp.tape_stride * chain;
+          const uint64_t cid = (uint64_t)(chain + mp.chain_offset);
+          if (phase == 0) {
+            double u_choice, u_delta;
+            uint32_t r1[4] = {0, 0, 0, 0};
+            if (mp.use_tape) {
+              u_choice = io.tape_u[ts * 5 + 0];
+              u_delta = io.tape_u[ts * 5 + 1];
+            } else {
+              uint32_t r0[4];
+              philox4x32_10((uint32_t)imc, (uint32_t)((uint64_t)imc >> 32), (uint32_t)cid, 0u, (uint32_t)mp.seed,
+                            (uint32_t)(mp.seed >> 32), r0);
+              philox4x32_10((uint32_t)imc, (uint32_t)((uint64_t)imc >> 32), (uint32_t)cid, 1u, (uint32_t)mp.seed,
+                            (uint32_t)(mp.seed >> 32), r1);
+              u_choice = u53(r0[0], r0[1]);
+              u_delta = u53(r0[2], r0[3]);
+            }
+            int mv = 0, lo = 0, range = 1;
+            if (u_choice < 0.5 && ncosF != 1 && sc->dv > 0.0) {
+              mv = 1;
+              if (ncosF <= 0) { lo = 0; range = n; } else { lo = 1; range = ncosF - 1; }
+            } else if (sc->dw > 0.0) {
+              mv = 2;
+              if (ncosD <= 0) { lo = 0; range = dim_w; } else { lo = 0; range = ncosD; }
+            }
+            sc->move = mv;
+            sc->idx = mp.use_tape ? io.tape_idx[ts] : lo + (int)(((uint64_t)r1[0] * (uint64_t)range) >> 32);
+            sc->delta = (mv == 1 ? sc->dv : sc->dw) * (u_delta - 0.5);
+            sc->accepted = 0;
+            sc->accepted_t0 = 0;
+            sc->do_t0 = 0;
+          } else {
+            double u_d;
+            if (mp.use_tape) {
+              u_d = io.tape_u[ts * 5 + 3];
+            } else {
+              uint32_t r2[4];
+              philox4x32_10((uint32_t)imc, (uint32_t)((uint64_t)imc >> 32), (uint32_t)cid, 2u, (uint32_t)mp.seed,
+                            (uint32_t)(mp.seed >> 32), r2);
+              u_d = u53(r2[0], r2[1]);
+            }
+            sc->t0_try = sc->timezero + sc->dt0 * (u_d - 0.5);
+            sc->do_t0 = (sc->t0_try > -0.5 * mp.min_lt) ? 1 : 0;  // lib/MCState.py:207
+          }
+        });
+        if (phase == 0) move = sc->move;
+        if (phase == 0 && move == 0) continue;
+        if (phase == 1 && !sc->do_t0) break;
+
+        // ---- trial profile / trial lag times ----
+        const double* vtry = s.v;
+        const double* wtry = s.w;
+        const double* lagp = s.lag;
+        int mode;
+        if (phase == 0) {
+          const int idx = sc->idx;
+          const double delta = sc->delta;
+          ex.par([&](int tid) {
+            if (move == 1) {
+              if (ncosF <= 0) {
+                for (int i = tid; i < np; i += Exec::nthr()) s.vt[i] = s.v[i] + (i == idx ? delta : 0.0);
+              } else {
+                for (int c = tid; c < ncosF; c += Exec::nthr()) s.ct[c] = s.vc[c] + (c == idx ? delta : 0.0);
+              }
+            } else {
+              if (ncosD <= 0) {
+                if (P.spring_k > 0.0) {  // move along a Laplacian eigenvector, lib/MCState.py:269-271
+                  for (int i = tid; i < np; i += Exec::nthr())
+                    s.wt[i] = (i < dim_w) ? s.w[i] + delta * P.svecs[(size_t)i * dim_w + idx] : 0.0;
+                } else {
+                  for (int i = tid; i < np; i += Exec::nthr()) s.wt[i] = s.w[i] + (i == idx ? delta : 0.0);
+                }
+              } else {
+                for (int c = tid; c < ncosD; c += Exec::nthr()) s.ct[c] = s.wc[c] + (c == idx ? delta : 0.0);
+              }
+            }
+          });
+          if ((move == 1 && ncosF > 0) || (move == 2 && ncosD > 0)) {
+            ex.par([&](int tid) {  // profile = sum_k coeff_k basis[:,k], lib/model.py:128-130
+              const int nc = (move == 1) ? ncosF : ncosD;
+              const int lim = (move == 1) ? n : dim_w;
+              const double* basis = (move == 1) ? P.v_basis : P.w_basis;
+              double* dst = (move == 1) ? s.vt : s.wt;
+              for (int i = tid; i < np; i += Exec::nthr()) {
+                double acc = 0.0;
+                if (i < lim)
+                  for (int c = 0; c < nc; ++c) acc += s.ct[c] * basis[(size_t)i * nc + c];
+                dst[i] = acc;
+              }
+            });
+          }
+          if (move == 1) vtry = s.vt; else wtry = s.wt;
+          const int cold = (!have_basis) || (mp.refresh_every > 0 && since_refresh >= mp.refresh_every);
+          if (cold) since_refresh = 0;
+          ++since_refresh;
+          mode = cold ? 1 : 0;
+        } else {
+          const double t0 = sc->t0_try;
+          ex.par([&](int tid) {
+            for (int l = tid; l < P.nlag; l += Exec::nthr()) s.lag_try[l] = P.lagtimes[l] + t0;
+          });
+          lagp = s.lag_try;
+          // XT holds the eigenvectors of the last TRIAL matrix: reusable as they are only when
+          // that trial was accepted (it then is the current state)
+          mode = (move != 0 && sc->accepted && have_basis) ? 2 : (have_basis ? 0 : 1);
+        }
+
+        int sw = 0;
+        const double ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
+        have_basis = (sw >= 0);
+        double e_try = 0.0;
+        if (phase == 0 && move == 2 && P.spring_k > 0.0) e_try = string_energy(s.wt);  // lib/MCState.py:287-289
+
+        // ---- Metropolis (thread 0): lib/MCState.py:251-261, 285-301, 213-221 ----
+        ex.single([&]() {
+          sc->sweeps += (sw > 0 ? sw : 0);
+          double lt = ll_new;
+          if (lt == lt) {
+            lt -= e_try;
+            const long long imc = sc->step;
+            const long long ts = (long long)it + mp.tape_stride * chain;
+            double u_acc;
+            if (mp.use_tape) {
+              u_acc = io.tape_u[ts * 5 + (phase == 0 ? 2 : 4)];
+            } else {
+              uint32_t rr[4];
+              const uint64_t cid = (uint64_t)(chain + mp.chain_offset);
+              philox4x32_10((uint32_t)imc, (uint32_t)((uint64_t)imc >> 32), (uint32_t)cid, phase == 0 ? 1u : 2u,
+                            (uint32_t)mp.seed, (uint32_t)(mp.seed >> 32), rr);
+              u_acc = u53(rr[2], rr[3]);
+            }
+            const double dlog = lt - sc->ll_cur;
+            if (u_acc < exp(dlog / sc->temp)) {
+              sc->ll_cur = lt;
+              if (phase == 0) {
+                sc->accepted = 1;
+                if (move == 1) { sc->naccv += 1; sc->naccv_upd += 1; }
+                else { sc->naccw += 1; sc->naccw_upd += 1; }
+              } else {
+                sc->accepted_t0 = 1;
+                sc->timezero = sc->t0_try;
+                sc->nacct0 += 1;
+              }
+            }
+          } else {
+            sc->status |= ST_NAN_TRIAL;
+          }
+          if (phase == 0) sc->ll_try = lt;
+        });
+        // ---- commit ----
+        if (phase == 0 && sc->accepted) {
+          const int idx = sc->idx;
+          ex.par([&](int tid) {
+            if (move == 1) {
+              for (int i = tid; i < np; i += Exec::nthr()) s.v[i] = s.vt[i];
+              if (ncosF > 0) {
+                for (int c = tid; c < ncosF; c += Exec::nthr()) s.vc[c] = s.ct[c];
+                if (tid == 0) io.naccv_coeff[chain * ncosF + idx] += 1;
+              }
+            } else {
+              for (int i = tid; i < np; i += Exec::nthr()) s.w[i] = s.wt[i];
+              if (ncosD > 0) {
+                for (int c = tid; c < ncosD; c += Exec::nthr()) s.wc[c] = s.ct[c];
+                if (tid == 0) io.naccw_coeff[chain * ncosD + idx] += 1;
+              }
+            }
+          });
+        } else if (phase == 1 && sc->accepted_t0) {
+          ex.par([&](int tid) {
+            for (int l = tid; l < P.nlag; l += Exec::nthr()) s.lag[l] = s.lag_try[l];
+          });
+        }
+      }
+      // ---- per-step records, sampling (lib/log.py:35-58), adaptation (lib/MCState.py:371-393) ----
+      ex.par([&](int tid) {
+        const long long j = sc->step + 1;
+        if (tid == 0) {
+          if (io.decisions)
+            io.decisions[(size_t)chain * nsteps + it] =
+                (unsigned char)((sc->accepted ? 1 : 0) | (sc->accepted_t0 ? 2 : 0) | (move << 2));
+          if (io.ll_try) io.ll_try[(size_t)chain * nsteps + it] = (move != 0) ? sc->ll_try : nan("");
+        }
+        if (io.samples && mp.sample_every > 0 && (j % mp.sample_every) == 0 && sc->nsamp < mp.nsamples_cap) {
+          double* row = io.samples + ((size_t)chain * mp.nsamples_cap + sc->nsamp) * sdim;
+          if (tid == 0) {
+            row[0] = sc->ll_cur; row[1] = sc->timezero; row[2] = sc->dv; row[3] = sc->dw;
+            row[4] = sc->dt0; row[5] = sc->temp;
+          }
+          const int nv = ncosF > 0 ? ncosF : n, nw = ncosD > 0 ? ncosD : dim_w;
+          const double* pv = ncosF > 0 ? s.vc : s.v;
+          const double* pw = ncosD > 0 ? s.wc : s.w;
+          for (int i = tid; i < nv; i += Exec::nthr()) row[6 + i] = pv[i];
+          for (int i = tid; i < nw; i += Exec::nthr()) row[6 + nv + i] = pw[i];
+        }
+      });
+      ex.single([&]() {
+        const long long j = sc->step + 1;
+        if (io.samples && mp.sample_every > 0 && (j % mp.sample_every) == 0 && sc->nsamp < mp.nsamples_cap)
+          sc->nsamp += 1;
+        if (mp.num_mc_update > 0.0 && fmod((double)j, mp.num_mc_update) == 0.0) {
+          if (ncosF != 1) sc->dv *= exp(0.1 * ((double)sc->naccv_upd / mp.num_mc_update - 0.3));
+          sc->dw *= exp(0.1 * ((double)sc->naccw_upd / mp.num_mc_update - 0.3));
+          sc->naccv_upd = 0;
+          sc->naccw_upd = 0;
+          if (mp.dtemp != 0.0) sc->temp += mp.dtemp;
+        }
+        sc->step = j;
+      });
+    }
+    // ---- store chain state ----
+    ex.par([&](int tid) {
+      for (int i = tid; i < n; i += Exec::nthr()) io.v[chain * n + i] = s.v[i];
+      for (int i = tid; i < dim_w; i += Exec::nthr()) io.w[chain * dim_w + i] = s.w[i];
+      for (int i = tid; i < ncosF; i += Exec::nthr()) io.vcoef[chain * ncosF + i] = s.vc[i];
+      for (int i = tid; i < ncosD; i += Exec::nthr()) io.wcoef[chain * ncosD + i] = s.wc[i];
+      if (tid == 0) {
+        double* q = io.scal + chain * S_NSCAL;
+        q[S_LL] = sc->ll_cur; q[S_T0] = sc->timezero; q[S_DV] = sc->dv; q[S_DW] = sc->dw;
+        q[S_DT0] = sc->dt0; q[S_TEMP] = sc->temp;
+        long long* c = io.counters + chain * C_NCOUNT;
+        c[C_NACCV] = sc->naccv; c[C_NACCW] = sc->naccw; c[C_NACCT0] = sc->nacct0;
+        c[C_NACCV_UPD] = sc->naccv_upd; c[C_NACCW_UPD] = sc->naccw_upd;
+        c[C_STEP] = sc->step; c[C_STATUS] = sc->status; c[C_SWEEPS] = sc->sweeps;
+      }
+      if (io.basis && have_basis) {
+        double* dst = io.basis + (size_t)chain * np * ld;
+        for (int e = tid; e < np * ld; e += Exec::nthr()) dst[e] = s.XT[e];
+        if (tid == 0) io.basis_valid[chain] = 1;
+      }
+    });
+  }
+};
+
+}  // namespace mcd

@@ -1,0 +1,375 @@
+// C ABI + kernels of libmcdiff_b200.so (see include/mcdiff_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/mcdiff_b200.h"
+#include "mcd_chain.cuh"
+#include "mcd_radial.cuh"
+
+using namespace mcd;
+
+static_assert(sizeof(mcd_mc_params) == sizeof(McParams), "mcd_mc_params layout");
+static_assert(sizeof(mcd_chain_io) == sizeof(ChainIO), "mcd_chain_io layout");
+static_assert(MCD_NSCAL == S_NSCAL && MCD_NCOUNT == C_NCOUNT, "slot counts");
+static_assert(MCD_ST_EIG_NOCONV == ST_JACOBI_NOCONV && MCD_ST_NAN_TRIAL == ST_NAN_TRIAL, "status bits");
+
+struct mcd_handle {
+  int device;
+  int sm_count;
+  int max_smem_optin;
+  long long launches;
+  double* gws;       // global work matrices for problems that do not fit in shared memory
+  size_t gws_bytes;
+};
+
+struct mcd_problem {
+  mcd_handle* h;
+  Problem P;       // device pointers below are owned by this object
+  void* blob;      // one allocation holding all private copies
+  int in_smem;
+  size_t smem_bytes;
+};
+
+#define CUDA_TRY(x)                          \
+  do {                                       \
+    cudaError_t e_ = (x);                    \
+    if (e_ != cudaSuccess) return (int)e_;   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+template <bool kSmemMat>
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  double* mat = kSmemMat ? reinterpret_cast<double*>(smem_raw)
+                         : gws + (size_t)blockIdx.x * (mat_bytes / sizeof(double));
+  unsigned char* vec = kSmemMat ? smem_raw + mat_bytes : smem_raw;
+  Smem s = carve(P, mat, vec);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec> ch(ex, P, s);
+  ch.run(mp, io, (long long)blockIdx.x, nsteps);
+}
+
+template <bool kSmemMat>
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_loglike_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
+                   const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
+                   int* __restrict__ status, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  double* mat = kSmemMat ? reinterpret_cast<double*>(smem_raw)
+                         : gws + (size_t)blockIdx.x * (mat_bytes / sizeof(double));
+  unsigned char* vec = kSmemMat ? smem_raw + mat_bytes : smem_raw;
+  Smem s = carve(P, mat, vec);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec> ch(ex, P, s);
+  ch.build_tables();
+  const int n = P.n, np = P.np, dim_w = P.dim_w;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += kThreads) {
+        s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
+        s.w[i] = (i < dim_w) ? w[(size_t)b * dim_w + i] : 0.0;
+      }
+      for (int l = tid; l < P.nlag; l += kThreads)
+        s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
+      if (tid == 0) s.sc->status = 0;
+    });
+    int sw = 0;
+    double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
+    const double ll = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    ex.par([&](int tid) {
+      if (tid == 0) {
+        out_ll[b] = ll;
+        if (status) status[b] = (int)s.sc->status;
+      }
+    });
+  }
+}
+
+// counts [L][n][n] -> padded [L][np][np]
+__global__ void mcd_pack_counts_kernel(const int* __restrict__ src, int* __restrict__ dst, int L, int n, int np) {
+  const size_t total = (size_t)L * np * np;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % np);
+    const int i = (int)((e / np) % np);
+    const int l = (int)(e / ((size_t)np * np));
+    dst[e] = (i < n && j < n) ? src[((size_t)l * n + i) * n + j] : 0;
+  }
+}
+
+// dense DFMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) mcd_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int mcd_version(void) { return MCD_VERSION; }
+
+const char* mcd_error_string(int code) {
+  switch (code) {
+    case MCD_OK: return "ok";
+    case MCD_E_ARG: return "invalid argument";
+    case MCD_E_UNSUPPORTED: return "unsupported configuration";
+    case MCD_E_NOMEM: return "out of memory";
+    case MCD_E_NODEVICE: return "no CUDA device";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int mcd_create(int device, mcd_handle** out) {
+  if (!out) return MCD_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MCD_E_NODEVICE;
+  if (device < 0 || device >= ndev) return MCD_E_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  mcd_handle* h = new (std::nothrow) mcd_handle();
+  if (!h) return MCD_E_NOMEM;
+  h->device = device;
+  h->launches = 0;
+  h->gws = nullptr;
+  h->gws_bytes = 0;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  *out = h;
+  return MCD_OK;
+}
+
+int mcd_destroy(mcd_handle* h) {
+  if (!h) return MCD_OK;
+  cudaSetDevice(h->device);
+  if (h->gws) cudaFree(h->gws);
+  delete h;
+  return MCD_OK;
+}
+
+int64_t mcd_launch_count(const mcd_handle* h) { return h ? h->launches : 0; }
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, mcd_problem** out) {
+  if (!h || !d || !out) return MCD_E_ARG;
+  if (d->n < 3 || d->n > 508 || d->nlag < 1 || d->nlag > kMaxLag) return MCD_E_ARG;
+  if (d->ncosF < 0 || d->ncosF > kMaxCoef || d->ncosD < 0 || d->ncosD > kMaxCoef) return MCD_E_ARG;
+  if (!d->lagtimes || !d->counts) return MCD_E_ARG;
+  if ((d->ncosF > 0 && !d->v_basis) || (d->ncosD > 0 && !d->w_basis)) return MCD_E_ARG;
+  if (d->spring_k > 0.0 && !d->string_vecs) return MCD_E_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = d->n, dim_w = d->pbc ? n : n - 1;
+  const int np = (n + 3) & ~3, ld = np + 2;
+
+  mcd_problem* p = new (std::nothrow) mcd_problem();
+  if (!p) return MCD_E_NOMEM;
+  p->h = h;
+  const size_t b_lag = align256((size_t)d->nlag * 8);
+  const size_t b_cnt = align256((size_t)d->nlag * np * np * 4);
+  const size_t b_vb = align256((size_t)n * d->ncosF * 8);
+  const size_t b_wb = align256((size_t)dim_w * d->ncosD * 8);
+  const size_t b_sv = d->spring_k > 0.0 ? align256((size_t)dim_w * dim_w * 8) : 0;
+  unsigned char* blob = nullptr;
+  cudaError_t e = cudaMalloc(&blob, b_lag + b_cnt + b_vb + b_wb + b_sv + 256);
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  p->blob = blob;
+  unsigned char* q = blob;
+  double* lag = (double*)q; q += b_lag;
+  int* cnt = (int*)q; q += b_cnt;
+  double* vb = (double*)q; q += b_vb;
+  double* wb = (double*)q; q += b_wb;
+  double* sv = (double*)q;
+  cudaMemcpyAsync(lag, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToDevice, st);
+  mcd_pack_counts_kernel<<<h->sm_count, 256, 0, st>>>(d->counts, cnt, d->nlag, n, np);
+  h->launches++;
+  if (d->ncosF > 0) cudaMemcpyAsync(vb, d->v_basis, (size_t)n * d->ncosF * 8, cudaMemcpyDeviceToDevice, st);
+  if (d->ncosD > 0) cudaMemcpyAsync(wb, d->w_basis, (size_t)dim_w * d->ncosD * 8, cudaMemcpyDeviceToDevice, st);
+  if (d->spring_k > 0.0)
+    cudaMemcpyAsync(sv, d->string_vecs, (size_t)dim_w * dim_w * 8, cudaMemcpyDeviceToDevice, st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
+
+  Problem& P = p->P;
+  P.n = n; P.np = np; P.ld = ld; P.dim_w = dim_w; P.pbc = d->pbc ? 1 : 0; P.nlag = d->nlag;
+  P.ncosF = d->ncosF; P.ncosD = d->ncosD;
+  P.lagtimes = lag; P.counts = cnt;
+  P.v_basis = d->ncosF > 0 ? vb : nullptr;
+  P.w_basis = d->ncosD > 0 ? wb : nullptr;
+  P.svecs = d->spring_k > 0.0 ? sv : nullptr;
+  P.spring_k = d->spring_k;
+  P.clip = d->clip;
+  const size_t full = smem_matrix_bytes(np, ld) + smem_vectors_bytes(np);
+  // the warm-start tile GEMM keeps one 4x4 tile per thread
+  const int ntiles = (np / 4) * (np / 4 + 1) / 2;
+  p->in_smem = (full <= (size_t)h->max_smem_optin && ntiles <= kThreads) ? 1 : 0;
+  p->smem_bytes = p->in_smem ? full : smem_vectors_bytes(np);
+  if (!p->in_smem && ntiles > kThreads) {
+    // the generic (global work matrices) path loops over tiles in the likelihood but the
+    // warm-start product needs one tile per thread: those problems always solve cold.
+  }
+  *out = p;
+  return MCD_OK;
+}
+
+int mcd_problem_destroy(mcd_problem* p) {
+  if (!p) return MCD_OK;
+  cudaSetDevice(p->h->device);
+  cudaFree(p->blob);
+  delete p;
+  return MCD_OK;
+}
+
+int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, int32_t* sdim, int32_t* in_smem) {
+  if (!p) return MCD_E_ARG;
+  if (np) *np = p->P.np;
+  if (basis_elems) *basis_elems = (int64_t)p->P.np * p->P.ld;
+  if (sdim) *sdim = sample_dim(p->P);
+  if (in_smem) *in_smem = p->in_smem;
+  return MCD_OK;
+}
+
+static int ensure_gws(mcd_handle* h, size_t bytes) {
+  if (h->gws_bytes >= bytes) return MCD_OK;
+  if (h->gws) { cudaDeviceSynchronize(); cudaFree(h->gws); h->gws = nullptr; h->gws_bytes = 0; }
+  cudaError_t e = cudaMalloc(&h->gws, bytes);
+  if (e != cudaSuccess) return (int)e;
+  h->gws_bytes = bytes;
+  return MCD_OK;
+}
+
+int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
+                      const double* lagtimes, double* out_ll, double* out_P, int32_t* status, void* stream) {
+  if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
+  if (B == 0) return MCD_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Problem& P = p->P;
+  if (p->in_smem) {
+    const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
+    CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
+                                                                     nullptr);
+  } else {
+    const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+    int rc = ensure_gws(h, (size_t)grid * smem_matrix_bytes(P.np, P.ld));
+    if (rc != MCD_OK) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
+                                                                      h->gws);
+  }
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params, const mcd_chain_io* io,
+               int32_t nchains, int32_t nsteps, void* stream) {
+  if (!h || !p || !params || !io || nchains < 0 || nsteps < 0) return MCD_E_ARG;
+  if (!io->v || !io->w || !io->scal || !io->counters) return MCD_E_ARG;
+  const Problem& P = p->P;
+  if (P.ncosF > 0 && (!io->vcoef || !io->naccv_coeff)) return MCD_E_ARG;
+  if (P.ncosD > 0 && (!io->wcoef || !io->naccw_coeff)) return MCD_E_ARG;
+  if (params->use_tape && (!io->tape_u || !io->tape_idx)) return MCD_E_ARG;
+  if (io->basis && !io->basis_valid) return MCD_E_ARG;
+  if (nchains == 0 || nsteps == 0) return MCD_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  McParams mp;
+  ChainIO cio;
+  std::memcpy(&mp, params, sizeof(mp));
+  std::memcpy(&cio, io, sizeof(cio));
+  if (p->in_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, nullptr);
+  } else {
+    const int ntiles = (P.np / 4) * (P.np / 4 + 1) / 2;
+    if (ntiles > kThreads) mp.refresh_every = 1;  // always cold: warm product needs one tile per thread
+    int rc = ensure_gws(h, (size_t)nchains * smem_matrix_bytes(P.np, P.ld));
+    if (rc != MCD_OK) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_mc_run_kernel<false><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+  }
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
+                          const double* v, const double* w, const double* lagtimes, const double* counts,
+                          const double* bessels, const double* b0zeros, double clip, int32_t B,
+                          const double* wrad, double* out_ll, double* out_P, int32_t* status, void* stream) {
+  if (!h || !v || !w || !lagtimes || !counts || !bessels || !b0zeros || !wrad || !out_ll) return MCD_E_ARG;
+  if (n < 3 || n > 256 || nlag < 1 || nlag > kMaxLag || dim_rad < 1 || lmax < 1 || lmax > kMaxBessel || B < 0)
+    return MCD_E_ARG;
+  if (B == 0) return MCD_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RadProblem R;
+  R.n = n; R.np = (n + 3) & ~3; R.ld = R.np + 2; R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
+  R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
+  R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
+  R.clip = clip;
+  const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+  const size_t per_cta = rad_workspace_doubles(R) * sizeof(double);
+  int rc = ensure_gws(h, (size_t)grid * per_cta);
+  if (rc != MCD_OK) return rc;
+  const size_t smem = rad_smem_bytes(R);
+  if (smem > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcd_rad_loglike_kernel<<<grid, kThreads, smem, st>>>(R, B, wrad, out_ll, out_P, status, h->gws);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+int mcd_fp64_peak(mcd_handle* h, double* tflops) {
+  if (!h || !tflops) return MCD_E_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mcd_dfma_kernel<<<blocks, threads>>>(out, 256);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    mcd_dfma_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  h->launches += 6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// CPU emulation of the CUDA chain body -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles mcdiff_b200/csrc/mcd_chain.cuh with g++ under the HostExec policy: the same
+// source the GPU runs as one CTA is executed by looping the thread index between barriers.
+// This validates tile maps, the Jacobi schedule, the Metropolis logic and the state layout
+// in the GPU-less build container.  It is never part of libmcdiff_b200.so and never a
+// fallback for it.
+//
+// Build: g++ -O2 -std=c++17 -shared -fPIC tests/emul/emul.cpp -o tests/emul/libmcd_emul.so
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mcdiff_b200.h"
+#include "../../mcdiff_b200/csrc/mcd_chain.cuh"
+
+using namespace mcd;
+
+namespace {
+struct HostProblem {
+  Problem P;
+  std::vector<int> counts;
+};
+
+void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
+  Problem& P = hp.P;
+  const int n = d->n, np = (n + 3) & ~3;
+  P.n = n; P.np = np; P.ld = np + 2; P.pbc = d->pbc ? 1 : 0; P.dim_w = d->pbc ? n : n - 1;
+  P.nlag = d->nlag; P.ncosF = d->ncosF; P.ncosD = d->ncosD;
+  hp.counts.assign((size_t)d->nlag * np * np, 0);
+  for (int l = 0; l < d->nlag; ++l)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) hp.counts[((size_t)l * np + i) * np + j] = d->counts[((size_t)l * n + i) * n + j];
+  P.lagtimes = d->lagtimes;
+  P.counts = hp.counts.data();
+  P.v_basis = d->v_basis;
+  P.w_basis = d->w_basis;
+  P.svecs = d->string_vecs;
+  P.spring_k = d->spring_k;
+  P.clip = d->clip;
+}
+}  // namespace
+
+extern "C" {
+
+int emul_loglike_batch(const mcd_problem_desc* d, int B, const double* v, const double* w, const double* lagtimes,
+                       double* out_ll, double* out_P, int* status, int* sweeps) {
+  HostProblem hp;
+  make_problem(d, hp);
+  const Problem& P = hp.P;
+  std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
+  std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
+  std::vector<double> store((size_t)kThreads * kMaxRegs);
+  Smem s = carve(P, mat.data(), vec.data());
+  HostExec ex(store.data());
+  Chain<HostExec> ch(ex, P, s);
+  ch.build_tables();
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < P.np; ++i) {
+      s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
+      s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
+    }
+    for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
+    s.sc->status = 0;
+    int sw = 0;
+    out_ll[b] = ch.evaluate(s.v, s.w, s.lag, 1, out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr, &sw);
+    if (status) status[b] = (int)s.sc->status;
+    if (sweeps) sweeps[b] = sw;
+  }
+  return 0;
+}
+
+int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mcd_chain_io* io, int nchains,
+                int nsteps) {
+  HostProblem hp;
+  make_problem(d, hp);
+  const Problem& P = hp.P;
+  McParams mp;
+  ChainIO cio;
+  static_assert(sizeof(mp) == sizeof(*params), "params layout");
+  static_assert(sizeof(cio) == sizeof(*io), "io layout");
+  std::memcpy(&mp, params, sizeof(mp));
+  std::memcpy(&cio, io, sizeof(cio));
+  std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
+  std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
+  std::vector<double> store((size_t)kThreads * kMaxRegs);
+  for (int c = 0; c < nchains; ++c) {
+    Smem s = carve(P, mat.data(), vec.data());
+    HostExec ex(store.data());
+    Chain<HostExec> ch(ex, P, s);
+    ch.run(mp, cio, c, nsteps);
+  }
+  return 0;
+}
+
+void emul_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+  philox4x32_10(c0, c1, c2, c3, k0, k1, out);
+}
+
+}  // extern "C"
