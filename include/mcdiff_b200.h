@@ -51,6 +51,14 @@ enum {
                             lib/MCState.py:251 does */
 };
 
+/* Propagator engines.  Both produce P_l = expm(lag_l R) (lib/utils.py:313):
+ *  EIGEN    : in-CTA parallel Jacobi eigendecomposition of the detailed-balance-symmetrised
+ *             generator, P = Pi^1/2 V exp(lag Lambda) V^T Pi^-1/2; any lag times, time-offset moves.
+ *  SQUARING : symmetric scaling-and-squaring, all products as register-tiled FP64 GEMMs in shared
+ *             memory; needs lag times in arithmetic progression lag_l = (l+1) lag_0, no time-offset
+ *             move and n <= 108 (work matrices in shared memory). */
+enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2 };
+
 typedef struct mcd_handle mcd_handle;
 typedef struct mcd_problem mcd_problem;
 
@@ -81,6 +89,8 @@ typedef struct {
   int32_t sample_every;  /* Logger.freq = 100, lib/log.py:9; 0 = no samples */
   int32_t refresh_every; /* cold eigen re-solve period (0 = never); 512 is a good default */
   int32_t use_tape;      /* 1: proposals and uniforms come from tape_u / tape_idx */
+  int32_t method;        /* MCD_METHOD_*: propagator engine (AUTO picks SQUARING when it applies) */
+  int32_t taylor_m;      /* Taylor order of the squaring engine, 0 = default (20) */
   uint64_t seed;         /* Philox4x32-10 key */
   int64_t chain_offset;  /* global index of chain 0 (chains shard over GPUs) */
   int64_t tape_stride;   /* 0: one tape for all chains, else per-chain stride (in steps) */
@@ -123,17 +133,20 @@ int mcd_destroy(mcd_handle* h);
 int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* desc, void* stream, mcd_problem** out);
 int mcd_problem_destroy(mcd_problem* p);
 /* np: padded bin count, basis_elems: doubles per chain in mcd_chain_io.basis,
- * sample_dim: doubles per sample row, in_smem: 1 when the n x n work matrices fit in shared memory */
+ * sample_dim: doubles per sample row, in_smem: 1 when the n x n work matrices fit in shared memory,
+ * squaring_ok: 1 when MCD_METHOD_SQUARING applies to this problem (see above) */
 int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, int32_t* sample_dim,
-                     int32_t* in_smem);
+                     int32_t* in_smem, int32_t* squaring_ok);
 
 /* log L of B profiles: out_ll[b] = sum_l sum_ij counts[l,i,j] log(max(P_l[i,j], clip)) with
  * P_l = expm(lag_l R(v_b, w_b)).  lagtimes == NULL uses the problem's lag times, otherwise
  * [B][nlag] per-profile lag times (time-offset moves).  out_P (optional) receives
- * [B][nlag][n][n] propagators, status (optional) [B] status bits.
+ * [B][nlag][n][n] propagators, status (optional) [B] status bits.  method: MCD_METHOD_AUTO = EIGEN here
+ * (the batched call is also the independent cross-check of the squaring engine).
  * Replaces log_like_lag, lib/utils.py:355-368. */
-int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
-                      const double* lagtimes, double* out_ll, double* out_P, int32_t* status, void* stream);
+int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
+                      const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
+                      void* stream);
 
 /* Advance every chain by nsteps Monte-Carlo steps (one CTA per chain).
  * Replaces the loop body of do_mc_cycles, lib/mc.py:27-51. */

@@ -16,6 +16,7 @@ MCD_NCOUNT = 8
 S_LL, S_T0, S_DV, S_DW, S_DT0, S_TEMP = range(6)
 C_NACCV, C_NACCW, C_NACCT0, C_NACCV_UPD, C_NACCW_UPD, C_STEP, C_STATUS, C_SWEEPS = range(8)
 ST_EIG_NOCONV, ST_NAN_TRIAL = 1, 2
+METHOD_AUTO, METHOD_EIGEN, METHOD_SQUARING = 0, 1, 2
 
 c_dp = C.c_void_p  # device (or, for the test emulator, host) pointers are passed as integers
 
@@ -33,7 +34,8 @@ class McParams(C.Structure):
     _fields_ = [
         ("num_mc_update", C.c_double), ("dtemp", C.c_double), ("min_lt", C.c_double),
         ("move_timezero", C.c_int32), ("sample_every", C.c_int32), ("refresh_every", C.c_int32),
-        ("use_tape", C.c_int32), ("seed", C.c_uint64), ("chain_offset", C.c_int64),
+        ("use_tape", C.c_int32), ("method", C.c_int32), ("taylor_m", C.c_int32),
+        ("seed", C.c_uint64), ("chain_offset", C.c_int64),
         ("tape_stride", C.c_int64), ("nsamples_cap", C.c_int64),
     ]
 
@@ -78,8 +80,8 @@ def load():
     lib.mcd_problem_create.argtypes = [C.c_void_p, C.POINTER(ProblemDesc), C.c_void_p, C.POINTER(C.c_void_p)]
     lib.mcd_problem_destroy.argtypes = [C.c_void_p]
     lib.mcd_problem_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64),
-                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-    lib.mcd_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.mcd_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                       C.c_void_p]
     lib.mcd_mc_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(McParams), C.POINTER(ChainIO), C.c_int32,
                                C.c_int32, C.c_void_p]

@@ -42,6 +42,8 @@ struct McParams {
   int sample_every;      // lib/log.py:9  (100)
   int refresh_every;     // cold re-solve period (bounds orthogonality drift of the warm start)
   int use_tape;          // 1: proposals/uniforms from the host tape, 0: Philox4x32-10
+  int method;            // 1: Jacobi eigendecomposition, 2: symmetric scaling-and-squaring
+  int taylor_m;          // Taylor order of the squaring engine (0 = default 20)
   unsigned long long seed;
   long long chain_offset;  // global id of chain 0 of this launch (multi-GPU sharding)
   long long tape_stride;   // 0: all chains share one tape, else per-chain stride in steps
@@ -118,6 +120,7 @@ struct Smem {
   double *lag, *lag_try;
   double *rc, *rs;
   double* red;
+  double* part;  // per-thread likelihood partial sums (squaring engine)
   int *rp, *rq;
   unsigned char* tiles;    // 2 bytes per tile (ib, jb), ib <= jb
   unsigned char* jblocks;  // 2 bytes per Jacobi block (ka, kb), ka < kb
@@ -126,7 +129,7 @@ struct Smem {
 };
 
 MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
-  size_t d = (size_t)np * 10 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32;
+  size_t d = (size_t)np * 10 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
   size_t nb = np / 4, h = np / 2;
   size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + sizeof(Scalars) + 64;
   return (bytes + 15) & ~(size_t)15;
@@ -158,6 +161,7 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
   s.rc = d; d += np / 2;
   s.rs = d; d += np / 2;
   s.red = d; d += 32;
+  s.part = d; d += kThreads;
   s.sc = reinterpret_cast<Scalars*>(d);
   d += (sizeof(Scalars) + 7) / 8;
   int* ip = reinterpret_cast<int*>(d);
@@ -413,6 +417,69 @@ struct Chain {
     return sweeps;
   }
 
+  // c = tile (ib, jb) of X^T Y for row-major n x n operands (leading dimension ld); with
+  // symmetric X this is the tile of X Y.  Register-blocked 4x4, operands read as 128-bit rows.
+  MCD_HD void tile_product(const double* X, const double* Y, int ib, int jb, double (&c)[4][4]) {
+    const int np = P.np, ld = P.ld;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) c[a][b] = 0.0;
+    const double* xi = X + ib * 4;
+    const double* yj = Y + jb * 4;
+#pragma unroll 2
+    for (int k = 0; k < np; ++k) {
+      const d2 x01 = ld2(xi + k * ld), x23 = ld2(xi + k * ld + 2);
+      const d2 y01 = ld2(yj + k * ld), y23 = ld2(yj + k * ld + 2);
+      const double xa[4] = {x01.x, x01.y, x23.x, x23.y};
+      const double yb[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[a][b] = fma(xa[a], yb[b], c[a][b]);
+    }
+  }
+
+  // Likelihood contribution of one 4x4 tile of the symmetric kernel G (and of its mirror):
+  // P_ij = exp(-v_i/2) G_ij exp(+v_j/2);  sum N_ij log(max(P_ij, clip))   (lib/utils.py:317-321)
+  MCD_HD double tile_loglike(const double (&c)[4][4], int ib, int jb, const i4 (&nij)[4], const i4 (&nji)[4],
+                             double* Pl) {
+    const int n = P.n;
+    const int i0 = ib * 4, j0 = jb * 4;
+    const double clip = P.clip;
+    double part = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + a;
+      const int nrow[4] = {nij[a].x, nij[a].y, nij[a].z, nij[a].w};
+      const double eai = s.ea[i], ebi = s.eb[i];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = j0 + b;
+        const double g = c[a][b];
+        const double pij = eai * g * s.eb[j];
+        if (nrow[b] != 0) part += (double)nrow[b] * log(fmax(pij, clip));
+        if (Pl && i < n && j < n) Pl[(size_t)i * n + j] = pij;
+        if (ib != jb) {
+          const int nm = (a == 0) ? nji[b].x : (a == 1) ? nji[b].y : (a == 2) ? nji[b].z : nji[b].w;
+          const double pji = s.ea[j] * g * ebi;
+          if (nm != 0) part += (double)nm * log(fmax(pji, clip));
+          if (Pl && i < n && j < n) Pl[(size_t)j * n + i] = pji;
+        }
+      }
+    }
+    return part;
+  }
+
+  MCD_HD void load_counts(const int* cnt, int ib, int jb, i4 (&nij)[4], i4 (&nji)[4]) {
+    const int np = P.np;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      nij[a] = ld4i(cnt + (size_t)(ib * 4 + a) * np + jb * 4);
+      nji[a] = ld4i(cnt + (size_t)(jb * 4 + a) * np + ib * 4);
+    }
+  }
+
   // log L = sum_lag sum_ij N[lag,i,j] log(max(P_ij, clip)),  P = Pi^1/2 XT^T e^{t lam} XT Pi^-1/2
   // (lib/utils.py:307-368).  B2 is overwritten with the scaled eigenvectors of each lag.
   // When Pout != nullptr the propagators are also written ([nlag][n][n], row-major).
@@ -439,58 +506,160 @@ struct Chain {
         double part = 0.0;
         for (int tt = tid; tt < s.ntiles; tt += Exec::nthr()) {
           const int ib = s.tiles[2 * tt], jb = s.tiles[2 * tt + 1];
-          const int i0 = ib * 4, j0 = jb * 4;
-          // counts of the tile and of its mirror, fetched before the k loop (L2 latency)
           i4 nij[4], nji[4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            nij[a] = ld4i(cnt + (size_t)(i0 + a) * np + j0);
-            nji[a] = ld4i(cnt + (size_t)(j0 + a) * np + i0);
-          }
+          load_counts(cnt, ib, jb, nij, nji);  // before the k loop: hides the L2 latency
           double c[4][4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) c[a][b] = 0.0;
-          const double* xi = s.XT + i0;
-          const double* wj = s.B2 + j0;
-#pragma unroll 2
-          for (int k = 0; k < np; ++k) {
-            const d2 x01 = ld2(xi + k * ld), x23 = ld2(xi + k * ld + 2);
-            const d2 w01 = ld2(wj + k * ld), w23 = ld2(wj + k * ld + 2);
-            const double xa[4] = {x01.x, x01.y, x23.x, x23.y};
-            const double wb[4] = {w01.x, w01.y, w23.x, w23.y};
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int b = 0; b < 4; ++b) c[a][b] = fma(xa[a], wb[b], c[a][b]);
-          }
-          const double clip = P.clip;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int i = i0 + a;
-            const int nrow[4] = {nij[a].x, nij[a].y, nij[a].z, nij[a].w};
-            const double eai = s.ea[i], ebi = s.eb[i];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int j = j0 + b;
-              const double g = c[a][b];
-              const double pij = eai * g * s.eb[j];
-              if (nrow[b] != 0) part += (double)nrow[b] * log(fmax(pij, clip));
-              if (Pl && i < n && j < n) Pl[(size_t)i * n + j] = pij;
-              if (ib != jb) {
-                const int nm = (a == 0) ? nji[b].x : (a == 1) ? nji[b].y : (a == 2) ? nji[b].z : nji[b].w;
-                const double pji = s.ea[j] * g * ebi;
-                if (nm != 0) part += (double)nm * log(fmax(pji, clip));
-                if (Pl && i < n && j < n) Pl[(size_t)j * n + i] = pji;
-              }
-            }
-          }
+          tile_product(s.XT, s.B2, ib, jb, c);
+          part += tile_loglike(c, ib, jb, nij, nji, Pl);
         }
         ex.regs(tid)[0] += part;
       });
     }
     return ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+  }
+
+  // ------------------------------------------------------------------------------------
+  // Propagators without an eigensolver: symmetric scaling-and-squaring.
+  //   G(t0) = exp(t0 S) = (T_m(h S))^(2^s),  h = t0 / 2^s,  ||h S||_inf <= 1,
+  //   G((l+1) t0) = G(l t0) G(t0)            (lag times in arithmetic progression)
+  // exp(hS) >= 0 entrywise (S is a symmetrised generator), so every product is a sum of
+  // non-negative terms and keeps componentwise relative accuracy.  All products are
+  // symmetric: only the upper-triangular tiles are computed, register-staged and written
+  // back in place (with their mirror) after a barrier -- two n x n buffers suffice.
+  // Same quantity as lib/utils.py:313 (scipy.linalg.expm is also scaling-and-squaring).
+  // ------------------------------------------------------------------------------------
+  MCD_HD void store_tile_mirror(double* D, int ib, int jb, const double* r) {
+    const int ld = P.ld;
+    const int i0 = ib * 4, j0 = jb * 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      st2(D + (i0 + a) * ld + j0, r[a * 4 + 0], r[a * 4 + 1]);
+      st2(D + (i0 + a) * ld + j0 + 2, r[a * 4 + 2], r[a * 4 + 3]);
+    }
+    if (ib != jb) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        st2(D + (j0 + b) * ld + i0, r[0 * 4 + b], r[1 * 4 + b]);
+        st2(D + (j0 + b) * ld + i0 + 2, r[2 * 4 + b], r[3 * 4 + b]);
+      }
+    }
+  }
+
+  // D <- X Y (symmetric, commuting operands; D may alias X or Y).  If cnt != nullptr the
+  // product is the kernel of a lag time and its likelihood terms are added to regs[0]... the
+  // partial sum lives in `part_acc` (per-thread, caller-owned).
+  MCD_HD void sym_product(const double* X, const double* Y, double* D, const int* cnt, double* Pl, bool store,
+                          double* part_acc_slot) {
+    (void)part_acc_slot;
+    ex.par([&](int tid) {
+      double* r = ex.regs(tid);
+      if (tid < s.ntiles) {
+        const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
+        i4 nij[4], nji[4];
+        if (cnt) load_counts(cnt, ib, jb, nij, nji);
+        double c[4][4];
+        tile_product(X, Y, ib, jb, c);
+        if (cnt) s.part[tid] += tile_loglike(c, ib, jb, nij, nji, Pl);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) r[a * 4 + b] = c[a][b];
+      }
+    });
+    if (store) {
+      ex.par([&](int tid) {
+        if (tid < s.ntiles) store_tile_mirror(D, s.tiles[2 * tid], s.tiles[2 * tid + 1], ex.regs(tid));
+      });
+    }
+  }
+
+  // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
+  MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, int taylor_m, double* Pout,
+                            int* squarings_out) {
+    const int n = P.n, np = P.np, ld = P.ld;
+    build_S(v, w);
+    // Gershgorin bound of ||S||
+    const double gersh = ex.max([&](int tid) {
+      double m = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) {
+        const int im = (i == 0) ? n - 1 : i - 1;
+        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+        m = (r > m || r != r) ? r : m;
+      }
+      return m;
+    });
+    const double t0 = lagt[0];
+    const double rho = t0 * gersh;
+    if (!(rho < 1.0e9) || !(t0 > 0.0)) {  // non-finite profile or absurd scale
+      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      if (squarings_out) *squarings_out = -1;
+      return nan("");
+    }
+    int nsq = 0;
+    for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
+    const double h = ldexp(t0, -nsq);
+    const int m = taylor_m > 0 ? taylor_m : 20;
+    double* A = s.XT;
+    double* B = s.B2;
+    // ---- T_m(hS) by Horner, band-limited: H <- I + (hS H)/k, k = m..1, ping-pong A/B ----
+    ex.par([&](int tid) {
+      for (int e = tid; e < np * ld; e += Exec::nthr()) { A[e] = 0.0; B[e] = 0.0; }
+      if (tid < s.ntiles) s.part[tid] = 0.0;
+    });
+    double* src = (m & 1) ? B : A;   // after m steps the result sits in A
+    double* dst = (m & 1) ? A : B;
+    ex.par([&](int tid) {
+      for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
+    });
+    for (int t = 1; t <= m; ++t) {
+      const double f = h / (double)(m - t + 1);
+      const int width = (2 * t + 1 < n) ? 2 * t + 1 : n;
+      const bool full = (width == n);
+      ex.par([&](int tid) {
+        for (int e = tid; e < n * width; e += Exec::nthr()) {
+          const int i = e / width, dd = e - i * width;
+          int j;
+          if (full) j = dd;
+          else {
+            j = i - t + dd;
+            if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
+            else if (j < 0 || j >= n) continue;
+          }
+          const int im = (i == 0) ? n - 1 : i - 1;
+          const int ip = (i == n - 1) ? 0 : i + 1;
+          const double val = s.a[i] * src[i * ld + j] + s.b[im] * src[im * ld + j] + s.b[i] * src[ip * ld + j];
+          dst[i * ld + j] = ((i == j) ? 1.0 : 0.0) + f * val;
+        }
+      });
+      double* tmp = src; src = dst; dst = tmp;
+    }
+    // ---- G(t0) = T^(2^s) ----
+    for (int q = 0; q < nsq; ++q) sym_product(A, A, A, nullptr, nullptr, true, nullptr);
+    // ---- likelihood of lag 0 straight from A, then the progression G((l+1) t0) = G(l t0) G(t0) ----
+    {
+      const int* cnt = P.counts;
+      ex.par([&](int tid) {
+        if (tid < s.ntiles) {
+          const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
+          i4 nij[4], nji[4];
+          load_counts(cnt, ib, jb, nij, nji);
+          double c[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const d2 g01 = ld2(A + (ib * 4 + a) * ld + jb * 4), g23 = ld2(A + (ib * 4 + a) * ld + jb * 4 + 2);
+            c[a][0] = g01.x; c[a][1] = g01.y; c[a][2] = g23.x; c[a][3] = g23.y;
+          }
+          s.part[tid] += tile_loglike(c, ib, jb, nij, nji, Pout);
+        }
+      });
+    }
+    for (int l = 1; l < P.nlag; ++l) {
+      const int* cnt = P.counts + (size_t)l * np * np;
+      double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
+      sym_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag, nullptr);
+    }
+    if (squarings_out) *squarings_out = nsq;
+    return ex.sum([&](int tid) { return (tid < s.ntiles) ? s.part[tid] : 0.0; });
   }
 
   // Full likelihood of the profile (v, w) at lag times lagt.
@@ -695,8 +864,13 @@ struct Chain {
         }
 
         int sw = 0;
-        const double ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
-        have_basis = (sw >= 0);
+        double ll_new;
+        if (mp.method == 2) {
+          ll_new = evaluate_sq(vtry, wtry, lagp, mp.taylor_m, nullptr, &sw);
+        } else {
+          ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
+          have_basis = (sw >= 0);
+        }
         double e_try = 0.0;
         if (phase == 0 && move == 2 && P.spring_k > 0.0) e_try = string_energy(s.wt);  // lib/MCState.py:287-289
 

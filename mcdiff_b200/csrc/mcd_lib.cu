@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -31,6 +32,7 @@ struct mcd_problem {
   Problem P;       // device pointers below are owned by this object
   void* blob;      // one allocation holding all private copies
   int in_smem;
+  int squaring_ok;  // lag times in arithmetic progression, work matrices in shared memory
   size_t smem_bytes;
 };
 
@@ -59,7 +61,7 @@ mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
 
 template <bool kSmemMat>
 __global__ void __launch_bounds__(kThreads, 1)
-mcd_loglike_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
+mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, const double* __restrict__ w,
                    const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
                    int* __restrict__ status, double* gws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,7 +86,8 @@ mcd_loglike_kernel(Problem P, int B, const double* __restrict__ v, const double*
     });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    const double ll = (kSmemMat && method == MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, Pb, &sw)
+                                                                  : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -221,6 +224,15 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   // the warm-start tile GEMM keeps one 4x4 tile per thread
   const int ntiles = (np / 4) * (np / 4 + 1) / 2;
   p->in_smem = (full <= (size_t)h->max_smem_optin && ntiles <= kThreads) ? 1 : 0;
+  {
+    double hl[kMaxLag];
+    CUDA_TRY(cudaMemcpyAsync(hl, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int ok = p->in_smem && hl[0] > 0.0;
+    for (int l = 1; l < d->nlag && ok; ++l)
+      if (!(fabs(hl[l] - (l + 1) * hl[0]) <= 1e-12 * hl[l])) ok = 0;
+    p->squaring_ok = ok;
+  }
   p->smem_bytes = p->in_smem ? full : smem_vectors_bytes(np);
   if (!p->in_smem && ntiles > kThreads) {
     // the generic (global work matrices) path loops over tiles in the likelihood but the
@@ -238,12 +250,14 @@ int mcd_problem_destroy(mcd_problem* p) {
   return MCD_OK;
 }
 
-int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, int32_t* sdim, int32_t* in_smem) {
+int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, int32_t* sdim, int32_t* in_smem,
+                     int32_t* squaring_ok) {
   if (!p) return MCD_E_ARG;
   if (np) *np = p->P.np;
   if (basis_elems) *basis_elems = (int64_t)p->P.np * p->P.ld;
   if (sdim) *sdim = sample_dim(p->P);
   if (in_smem) *in_smem = p->in_smem;
+  if (squaring_ok) *squaring_ok = p->squaring_ok;
   return MCD_OK;
 }
 
@@ -256,9 +270,13 @@ static int ensure_gws(mcd_handle* h, size_t bytes) {
   return MCD_OK;
 }
 
-int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
-                      const double* lagtimes, double* out_ll, double* out_P, int32_t* status, void* stream) {
+int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
+                      const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
+                      void* stream) {
   if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
+  if (method == MCD_METHOD_AUTO) method = MCD_METHOD_EIGEN;
+  if (method != MCD_METHOD_EIGEN && method != MCD_METHOD_SQUARING) return MCD_E_ARG;
+  if (method == MCD_METHOD_SQUARING && (!p->squaring_ok || lagtimes)) return MCD_E_UNSUPPORTED;
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -267,16 +285,16 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const doub
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
-                                                                     nullptr);
+    mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
+                                                                     status, nullptr);
   } else {
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
     int rc = ensure_gws(h, (size_t)grid * smem_matrix_bytes(P.np, P.ld));
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
-                                                                      h->gws);
+    mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
+                                                                      status, h->gws);
   }
   h->launches++;
   return (int)cudaGetLastError();
@@ -298,6 +316,10 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   ChainIO cio;
   std::memcpy(&mp, params, sizeof(mp));
   std::memcpy(&cio, io, sizeof(cio));
+  const bool sq_ok = p->squaring_ok && !mp.move_timezero;
+  if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
+  if (mp.method == MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
+  if (mp.method != MCD_METHOD_SQUARING && mp.method != MCD_METHOD_EIGEN) return MCD_E_ARG;
   if (p->in_smem) {
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));

@@ -1,0 +1,308 @@
+"""Thin host layer over the C ABI: device buffers are torch tensors, compute is CUDA.
+
+`Engine` owns one library handle per GPU, `DeviceProblem` the device copy of what the
+reference keeps in `Transitions` + `Model` (count matrices, lag times, basis functions), and
+`ChainBatch` the structure-of-arrays state of many independent Monte-Carlo chains.
+
+There is no CPU path: every method ends in a call into libmcdiff_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as K
+
+SAMPLE_HEAD = 6  # log_like, timezero, dv, dw, dtimezero, temp
+
+
+def _dev(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise K.McdError("mcdiff_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = K.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        K.check(self.lib.mcd_create(self.device_index, C.byref(h)), "mcd_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mcd_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, a, dtype):
+        """Host array -> device tensor through pinned memory (async on the current stream)."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.pin_memory().to(self.device, non_blocking=True)
+
+    def fp64_peak_tflops(self) -> float:
+        out = C.c_double()
+        K.check(self.lib.mcd_fp64_peak(self.handle, C.byref(out)), "mcd_fp64_peak")
+        return out.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.mcd_launch_count(self.handle))
+
+
+class DeviceProblem:
+    """Device-resident problem description (counts, lag times, bases)."""
+
+    def __init__(self, eng: Engine, counts, lagtimes, pbc, v_basis=None, w_basis=None, spring_k=-1.0,
+                 string_vecs=None, clip=1e-10):
+        self.eng = eng
+        counts = np.asarray(counts)
+        if counts.ndim != 3 or counts.shape[1] != counts.shape[2]:
+            raise ValueError("counts must be [nlag][n][n]")
+        if np.any(counts < 0) or np.any(counts > np.iinfo(np.int32).max):
+            raise ValueError("counts out of int32 range")
+        self.n = int(counts.shape[1])
+        self.nlag = int(counts.shape[0])
+        self.pbc = bool(pbc)
+        self.dim_w = self.n if self.pbc else self.n - 1
+        self.ncosF = 0 if v_basis is None else int(np.asarray(v_basis).shape[1])
+        self.ncosD = 0 if w_basis is None else int(np.asarray(w_basis).shape[1])
+        self.spring_k = float(spring_k)
+        with torch.cuda.device(eng.device):
+            self.d_counts = eng.to_device(counts.astype(np.int32), torch.int32)
+            self.d_lag = eng.to_device(np.asarray(lagtimes, dtype=np.float64), torch.float64)
+            self.d_vb = None if v_basis is None else eng.to_device(np.asarray(v_basis, dtype=np.float64), torch.float64)
+            self.d_wb = None if w_basis is None else eng.to_device(np.asarray(w_basis, dtype=np.float64), torch.float64)
+            self.d_sv = None
+            if self.spring_k > 0:
+                if string_vecs is None:
+                    raise ValueError("spring_k > 0 needs string_vecs")
+                self.d_sv = eng.to_device(np.asarray(string_vecs, dtype=np.float64), torch.float64)
+            d = K.ProblemDesc()
+            d.n, d.pbc, d.nlag, d.ncosF, d.ncosD = self.n, int(self.pbc), self.nlag, self.ncosF, self.ncosD
+            d.lagtimes = self.d_lag.data_ptr()
+            d.counts = self.d_counts.data_ptr()
+            d.v_basis = None if self.d_vb is None else self.d_vb.data_ptr()
+            d.w_basis = None if self.d_wb is None else self.d_wb.data_ptr()
+            d.string_vecs = None if self.d_sv is None else self.d_sv.data_ptr()
+            d.spring_k, d.clip = self.spring_k, float(clip)
+            p = C.c_void_p()
+            K.check(eng.lib.mcd_problem_create(eng.handle, C.byref(d), eng.stream_ptr(), C.byref(p)),
+                    "mcd_problem_create")
+            self.ptr = p
+            np_, be, sd, ins, sq = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+            K.check(eng.lib.mcd_problem_info(p, C.byref(np_), C.byref(be), C.byref(sd), C.byref(ins), C.byref(sq)))
+            self.np, self.basis_elems, self.sample_dim, self.in_smem = np_.value, be.value, sd.value, bool(ins.value)
+            self.squaring_ok = bool(sq.value)
+        self.lagtimes = np.asarray(lagtimes, dtype=np.float64).copy()
+        self.min_lt = float(np.min(self.lagtimes))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.eng.lib.mcd_problem_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- likelihood seam: mcdiff.utils.log_like_lag (lib/utils.py:355-368) ----
+    def loglike_device(self, d_v, d_w, d_lag=None, want_P=False, method=K.METHOD_AUTO):
+        """Device tensors in, device tensors out (asynchronous)."""
+        eng = self.eng
+        B = d_v.shape[0]
+        out = torch.empty(B, dtype=torch.float64, device=eng.device)
+        status = torch.empty(B, dtype=torch.int32, device=eng.device)
+        P = torch.empty((B, self.nlag, self.n, self.n), dtype=torch.float64, device=eng.device) if want_P else None
+        K.check(eng.lib.mcd_loglike_batch(eng.handle, self.ptr, int(method), B, _dev(d_v), _dev(d_w), _dev(d_lag), _dev(out),
+                                          _dev(P), _dev(status), eng.stream_ptr()), "mcd_loglike_batch")
+        return out, P, status
+
+    def loglike(self, v, w, lagtimes=None, want_P=False, method=K.METHOD_AUTO):
+        """Host arrays in, host arrays out: log L (and optionally the propagators) of B profiles."""
+        eng = self.eng
+        v = np.atleast_2d(np.asarray(v, dtype=np.float64))
+        w = np.atleast_2d(np.asarray(w, dtype=np.float64))
+        if v.shape[1] != self.n or w.shape[1] != self.dim_w or v.shape[0] != w.shape[0]:
+            raise ValueError("profile shapes do not match the problem")
+        with torch.cuda.device(eng.device):
+            d_v = eng.to_device(v, torch.float64)
+            d_w = eng.to_device(w, torch.float64)
+            d_l = None
+            if lagtimes is not None:
+                lt = np.asarray(lagtimes, dtype=np.float64)
+                if lt.shape != (v.shape[0], self.nlag):
+                    raise ValueError("lagtimes must be [B][nlag]")
+                d_l = eng.to_device(lt, torch.float64)
+            out, P, status = self.loglike_device(d_v, d_w, d_l, want_P, method)
+            ll = out.cpu().numpy()
+            st = status.cpu().numpy()
+            Pn = None if P is None else P.cpu().numpy()
+        return ll, Pn, st
+
+
+class ChainBatch:
+    """State of C independent chains on one GPU (what MCState + model hold per chain)."""
+
+    def __init__(self, prob: DeviceProblem, nchains: int, keep_basis: bool = True):
+        self.prob = prob
+        self.eng = prob.eng
+        self.C = int(nchains)
+        dev = self.eng.device
+        f64, i64 = torch.float64, torch.int64
+        with torch.cuda.device(dev):
+            self.v = torch.zeros((self.C, prob.n), dtype=f64, device=dev)
+            self.w = torch.zeros((self.C, prob.dim_w), dtype=f64, device=dev)
+            self.vcoef = torch.zeros((self.C, max(prob.ncosF, 1)), dtype=f64, device=dev)
+            self.wcoef = torch.zeros((self.C, max(prob.ncosD, 1)), dtype=f64, device=dev)
+            self.scal = torch.zeros((self.C, K.MCD_NSCAL), dtype=f64, device=dev)
+            self.counters = torch.zeros((self.C, K.MCD_NCOUNT), dtype=i64, device=dev)
+            self.naccv_coeff = torch.zeros((self.C, max(prob.ncosF, 1)), dtype=i64, device=dev)
+            self.naccw_coeff = torch.zeros((self.C, max(prob.ncosD, 1)), dtype=i64, device=dev)
+            self.basis = None
+            self.basis_valid = None
+            if keep_basis and prob.in_smem:
+                self.basis = torch.empty((self.C, prob.basis_elems), dtype=f64, device=dev)
+                self.basis_valid = torch.zeros(self.C, dtype=torch.int32, device=dev)
+
+    def set_state(self, v, w, vcoef=None, wcoef=None, *, dv, dw, dtimezero=0.1, temp=1.0, timezero=0.0,
+                  log_like=None):
+        """Upload initial profiles ([n] broadcast to all chains, or [C][n]) and MC scalars."""
+        eng, prob = self.eng, self.prob
+
+        def bc(a, width):
+            a = np.asarray(a, dtype=np.float64)
+            if a.ndim == 1:
+                a = np.broadcast_to(a, (self.C, a.shape[0]))
+            if a.shape != (self.C, width):
+                raise ValueError("bad state shape %s, expected %s" % (a.shape, (self.C, width)))
+            return np.ascontiguousarray(a)
+
+        with torch.cuda.device(eng.device):
+            self.v.copy_(eng.to_device(bc(v, prob.n), torch.float64))
+            self.w.copy_(eng.to_device(bc(w, prob.dim_w), torch.float64))
+            if prob.ncosF > 0:
+                self.vcoef.copy_(eng.to_device(bc(vcoef, prob.ncosF), torch.float64))
+            if prob.ncosD > 0:
+                self.wcoef.copy_(eng.to_device(bc(wcoef, prob.ncosD), torch.float64))
+            scal = np.zeros((self.C, K.MCD_NSCAL))
+            scal[:, K.S_T0] = timezero
+            scal[:, K.S_DV] = dv
+            scal[:, K.S_DW] = dw
+            scal[:, K.S_DT0] = dtimezero
+            scal[:, K.S_TEMP] = temp
+            if log_like is not None:
+                scal[:, K.S_LL] = log_like
+            self.scal.copy_(eng.to_device(scal, torch.float64))
+            self.counters.zero_()
+            self.naccv_coeff.zero_()
+            self.naccw_coeff.zero_()
+            if self.basis_valid is not None:
+                self.basis_valid.zero_()
+
+    def init_log_like(self):
+        """First likelihood of every chain (MCState.init_log_like, lib/MCState.py:101-137).
+        Returns the host copy; raises like the reference on a non-finite value."""
+        prob = self.prob
+        with torch.cuda.device(self.eng.device):
+            lag = None
+            t0 = self.scal[:, K.S_T0]
+            if bool((t0 != 0).any()):
+                lag = (prob.d_lag[None, :] + t0[:, None]).contiguous()
+            ll, _, status = prob.loglike_device(self.v, self.w, lag)
+            if prob.spring_k > 0:  # lib/MCState.py:121-124
+                d = self.w[:, 1:] - self.w[:, :-1]
+                e = 0.5 * prob.spring_k * (d * d).sum(dim=1)
+                if prob.pbc:
+                    e = e + 0.5 * prob.spring_k * (self.w[:, 0] - self.w[:, -1]) ** 2
+                ll = ll - e
+            self.scal[:, K.S_LL] = ll
+            host = ll.cpu().numpy()
+        if np.any(np.isnan(host)):
+            raise ValueError("Initial likelihood diverges")  # lib/MCState.py:116-117
+        return host
+
+    def run(self, nsteps, params: K.McParams, tape_u=None, tape_idx=None, record=False, nsamples_cap=0):
+        """Advance all chains by nsteps (asynchronous).  Returns device tensors
+        (decisions, ll_try, samples), each None unless requested."""
+        eng, prob = self.eng, self.prob
+        dev = eng.device
+        with torch.cuda.device(dev):
+            io = K.ChainIO()
+            io.v, io.w = self.v.data_ptr(), self.w.data_ptr()
+            io.vcoef, io.wcoef = self.vcoef.data_ptr(), self.wcoef.data_ptr()
+            io.scal, io.counters = self.scal.data_ptr(), self.counters.data_ptr()
+            io.naccv_coeff, io.naccw_coeff = self.naccv_coeff.data_ptr(), self.naccw_coeff.data_ptr()
+            io.basis = None if self.basis is None else self.basis.data_ptr()
+            io.basis_valid = None if self.basis_valid is None else self.basis_valid.data_ptr()
+            keep = []
+            if params.use_tape:
+                tu = eng.to_device(np.asarray(tape_u, dtype=np.float64), torch.float64)
+                ti = eng.to_device(np.asarray(tape_idx, dtype=np.int32), torch.int32)
+                keep += [tu, ti]
+                io.tape_u, io.tape_idx = tu.data_ptr(), ti.data_ptr()
+            dec = llt = samples = None
+            if record:
+                dec = torch.zeros((self.C, nsteps), dtype=torch.uint8, device=dev)
+                llt = torch.zeros((self.C, nsteps), dtype=torch.float64, device=dev)
+                io.decisions, io.ll_try = dec.data_ptr(), llt.data_ptr()
+            if nsamples_cap > 0:
+                samples = torch.zeros((self.C, nsamples_cap, prob.sample_dim), dtype=torch.float64, device=dev)
+                io.samples = samples.data_ptr()
+            params.nsamples_cap = int(nsamples_cap)
+            K.check(eng.lib.mcd_mc_run(eng.handle, prob.ptr, C.byref(params), C.byref(io), self.C, int(nsteps),
+                                       eng.stream_ptr()), "mcd_mc_run")
+            self._keep = keep
+        return dec, llt, samples
+
+    def host_state(self):
+        """Device -> host copy of the whole chain state (one synchronisation)."""
+        with torch.cuda.device(self.eng.device):
+            out = dict(v=self.v.cpu().numpy(), w=self.w.cpu().numpy(), scal=self.scal.cpu().numpy(),
+                       counters=self.counters.cpu().numpy(),
+                       vcoef=self.vcoef.cpu().numpy() if self.prob.ncosF else None,
+                       wcoef=self.wcoef.cpu().numpy() if self.prob.ncosD else None,
+                       naccv_coeff=self.naccv_coeff.cpu().numpy(), naccw_coeff=self.naccw_coeff.cpu().numpy())
+        return out
+
+
+def rad_loglike(eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad, clip=1e-32, want_P=False):
+    """Radial likelihood seam: mcdiff.twod.rad_log_like_lag (lib/twod.py:13-32)."""
+    v = np.asarray(v, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    counts = np.asarray(counts, dtype=np.float64)
+    wrad = np.atleast_2d(np.asarray(wrad, dtype=np.float64))
+    nlag, dim_rad, n, _ = counts.shape
+    lmax = int(np.asarray(bessels).shape[0])
+    B = wrad.shape[0]
+    with torch.cuda.device(eng.device):
+        f64 = torch.float64
+        d_v, d_w = eng.to_device(v, f64), eng.to_device(w, f64)
+        d_l, d_c = eng.to_device(np.asarray(lagtimes, dtype=np.float64), f64), eng.to_device(counts, f64)
+        d_b, d_z = eng.to_device(np.asarray(bessels, dtype=np.float64), f64), eng.to_device(np.asarray(b0zeros, dtype=np.float64), f64)
+        d_r = eng.to_device(wrad, f64)
+        out = torch.empty(B, dtype=f64, device=eng.device)
+        status = torch.empty(B, dtype=torch.int32, device=eng.device)
+        P = torch.empty((B, nlag, dim_rad, n, n), dtype=f64, device=eng.device) if want_P else None
+        K.check(eng.lib.mcd_rad_loglike_batch(eng.handle, n, int(bool(pbc)), nlag, dim_rad, lmax, _dev(d_v), _dev(d_w),
+                                              _dev(d_l), _dev(d_c), _dev(d_b), _dev(d_z), float(clip), B, _dev(d_r),
+                                              _dev(out), _dev(P), _dev(status), eng.stream_ptr()),
+                "mcd_rad_loglike_batch")
+        return out.cpu().numpy(), (None if P is None else P.cpu().numpy()), status.cpu().numpy()

@@ -43,8 +43,8 @@ void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
 
 extern "C" {
 
-int emul_loglike_batch(const mcd_problem_desc* d, int B, const double* v, const double* w, const double* lagtimes,
-                       double* out_ll, double* out_P, int* status, int* sweeps) {
+int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const double* v, const double* w,
+                       const double* lagtimes, double* out_ll, double* out_P, int* status, int* sweeps) {
   HostProblem hp;
   make_problem(d, hp);
   const Problem& P = hp.P;
@@ -63,7 +63,9 @@ int emul_loglike_batch(const mcd_problem_desc* d, int B, const double* v, const 
     for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
     s.sc->status = 0;
     int sw = 0;
-    out_ll[b] = ch.evaluate(s.v, s.w, s.lag, 1, out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr, &sw);
+    double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
+    out_ll[b] = (method == MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, Pb, &sw)
+                                                : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     if (status) status[b] = (int)s.sc->status;
     if (sweeps) sweeps[b] = sw;
   }

@@ -65,7 +65,7 @@ class HostProblem:
         self.sample_dim = 6 + (self.ncosF or self.n) + (self.ncosD or self.dim_w)
 
 
-def loglike_batch(prob: HostProblem, v, w, lagtimes=None, want_P=False):
+def loglike_batch(prob: HostProblem, v, w, lagtimes=None, want_P=False, method=1):
     v = np.ascontiguousarray(np.atleast_2d(v), dtype=np.float64)
     w = np.ascontiguousarray(np.atleast_2d(w), dtype=np.float64)
     B = v.shape[0]
@@ -74,7 +74,7 @@ def loglike_batch(prob: HostProblem, v, w, lagtimes=None, want_P=False):
     status = np.zeros(B, dtype=np.int32)
     sweeps = np.zeros(B, dtype=np.int32)
     lt = None if lagtimes is None else np.ascontiguousarray(lagtimes, dtype=np.float64)
-    rc = lib().emul_loglike_batch(C.byref(prob.desc), C.c_int(B), C.c_void_p(ptr(v)), C.c_void_p(ptr(w)),
+    rc = lib().emul_loglike_batch(C.byref(prob.desc), C.c_int(method), C.c_int(B), C.c_void_p(ptr(v)), C.c_void_p(ptr(w)),
                                   C.c_void_p(ptr(lt)), C.c_void_p(ptr(out)), C.c_void_p(ptr(P)),
                                   C.c_void_p(ptr(status)), C.c_void_p(ptr(sweeps)))
     assert rc == 0

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden
+fixtures and the CPU oracle.
+
+Tolerances (north star): log-likelihood and propagator within 1e-9 relative of the
+reference's numpy/scipy path in fp64; accept/reject decisions bit-exact for a host-supplied
+tape of proposals and uniforms.
+Propagator entries are compared norm-wise (|dP| <= 1e-9 max|P|) and entry-wise above 1e-6:
+expm itself is only accurate to ~1e-16 absolute, so tiny entries carry no 1e-9 relative
+information in the reference either.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import REPLAY_TAGS, replay_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+METHODS = {"eigen": 1, "squaring": 2}
+
+
+def _params(case, nsteps, use_tape=1, seed=0, refresh=64, chain_offset=0, method=0):
+    from mcdiff_b200 import _capi as K
+    mp = K.McParams()
+    mp.num_mc_update = case["nmc_update"]
+    mp.dtemp = case["dtemp"]
+    mp.min_lt = float(np.min(case["lagtimes"]))
+    mp.move_timezero = int(case["move_timezero"])
+    mp.sample_every = 100
+    mp.refresh_every = refresh
+    mp.use_tape = use_tape
+    mp.seed = seed
+    mp.chain_offset = chain_offset
+    mp.tape_stride = 0
+    mp.method = method
+    return mp
+
+
+def _problem(engine, case):
+    from mcdiff_b200.engine import DeviceProblem
+    return DeviceProblem(engine, case["counts"], case["lagtimes"], case["pbc"], v_basis=case["v_basis"],
+                         w_basis=case["w_basis"], spring_k=case["k"], string_vecs=case["svecs"])
+
+
+@pytest.mark.parametrize("method", ["eigen", "squaring"])
+def test_known_answers_K1_K4(engine, gold_ll, method):
+    """The four archived `initial log-likelihood` values of the reference's example logs."""
+    from mcdiff_b200.engine import DeviceProblem
+    G = gold_ll
+    m = METHODS[method]
+    pA = DeviceProblem(engine, G["A_counts"], G["A_lags"], True)
+    pM = DeviceProblem(engine, G["M_counts"], G["M_lags"], True)
+    assert pA.squaring_ok and pA.in_smem
+    llA, _, stA = pA.loglike(G["K_v"][:2], G["K_w"][:2], method=m)
+    llM, _, stM = pM.loglike(G["K_v"][2:], G["K_w"][2:], method=m)
+    ll = np.concatenate([llA, llM])
+    assert not stA.any() and not stM.any()
+    np.testing.assert_allclose(ll, G["K_ll"], rtol=RTOL)
+    # archived logs print 12 significant digits
+    np.testing.assert_allclose(ll, G["K_archived"], rtol=5e-12)
+
+
+@pytest.mark.parametrize("method", ["eigen", "squaring"])
+def test_propagator_matches_expm(engine, gold_ll, method):
+    from mcdiff_b200.engine import DeviceProblem
+    G = gold_ll
+    m = METHODS[method]
+    pA = DeviceProblem(engine, G["A_counts"], G["A_lags"], True)
+    for v, w, Pref in ((G["K_v"][1], G["K_w"][1], G["K2_P"]), (G["rand_v"][0], G["rand_w"][0], G["rand_P0"])):
+        _, P, st = pA.loglike(v, w, want_P=True, method=m)
+        P = P[0, 0]
+        assert not st.any()
+        assert np.max(np.abs(P - Pref)) <= RTOL * np.max(np.abs(Pref))
+        big = Pref > 1e-6
+        assert np.max(np.abs(P - Pref)[big] / Pref[big]) <= RTOL
+        np.testing.assert_allclose(P.sum(axis=0), 1.0, atol=1e-12)     # column stochastic
+    pC = DeviceProblem(engine, G["C_counts"], G["C_lags"], False)
+    _, P, _ = pC.loglike(G["C_v"][0], G["C_w"][0], want_P=True, method=m)
+    assert np.max(np.abs(P[0, 0] - G["C_P0"])) <= RTOL * np.max(np.abs(G["C_P0"]))
+
+
+def test_random_profiles_all_fixtures(engine, gold_ll):
+    """pbc 1 lag, pbc 4 lags, nopbc cut (n=60), odd size n=37 with 2 lags (padding path)."""
+    from mcdiff_b200.engine import DeviceProblem
+    G = gold_ll
+    cases = [
+        (G["A_counts"], G["A_lags"], True, G["rand_v"], G["rand_w"], G["rand_ll_A"]),
+        (G["P_counts"], G["P_lags"], True, G["rand_v"], G["rand_wP"], G["rand_ll_P"]),
+        (G["C_counts"], G["C_lags"], False, G["C_v"], G["C_w"], G["C_ll"]),
+        (G["S_counts"], G["S_lags"], True, G["S_v"], G["S_w"], G["S_ll"]),
+    ]
+    for counts, lags, pbc, v, w, ref in cases:
+        prob = DeviceProblem(engine, counts, lags, pbc)
+        ll, _, st = prob.loglike(v, w)
+        assert not st.any()
+        np.testing.assert_allclose(ll, ref, rtol=RTOL)
+        if prob.squaring_ok:       # lag times 20 | 10,20,30,40: the squaring engine applies
+            ll2, _, st2 = prob.loglike(v, w, method=METHODS["squaring"])
+            assert not st2.any()
+            np.testing.assert_allclose(ll2, ref, rtol=RTOL)
+        else:                      # 5, 12.5 is no arithmetic progression
+            assert list(lags) == [5.0, 12.5]
+    # flat start of the 4-lag fixture (-23355.373632376784)
+    prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True)
+    ll, _, _ = prob.loglike(np.zeros(100), G["P_flat_w"])
+    np.testing.assert_allclose(ll[0], G["P_flat_ll"], rtol=RTOL)
+
+
+def test_per_profile_lagtimes(engine, gold_ll):
+    """lagtimes argument (time-offset moves evaluate the same profile at shifted lags)."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    G = gold_ll
+    prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True)
+    v, w = G["rand_v"][:3], G["rand_wP"][:3]
+    lt = G["P_lags"][None, :] + np.array([[-1.5], [0.0], [2.25]])
+    ll, _, _ = prob.loglike(v, w, lagtimes=lt)
+    ref = [O.log_like_lag(v[b], w[b], lt[b], G["P_counts"], True) for b in range(3)]
+    np.testing.assert_allclose(ll, ref, rtol=RTOL)
+
+
+def test_nan_profile_reports_status(engine, gold_ll):
+    from mcdiff_b200.engine import DeviceProblem
+    G = gold_ll
+    prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True)
+    v = np.zeros((2, 100))
+    v[1, 7] = np.nan
+    w = np.tile(G["P_flat_w"], (2, 1))
+    ll, _, st = prob.loglike(v, w)
+    assert np.isfinite(ll[0]) and st[0] == 0
+    assert np.isnan(ll[1]) and st[1] != 0
+
+
+@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("tag", REPLAY_TAGS)
+def test_replay_against_reference_trajectories(engine, gold_replay, tag, method):
+    """Tape-driven MC: decisions bit-exact vs the UNMODIFIED reference run on the same tape
+    (Fourier 10/6, per-bin 4 lags, time-offset + annealing, nopbc cut, spring prior)."""
+    from mcdiff_b200.engine import ChainBatch
+    case = replay_case(gold_replay, tag)
+    g = case["g"]
+    if method == "squaring" and case["move_timezero"]:
+        pytest.skip("time-offset moves run on the eigen engine")
+    prob = _problem(engine, case)
+    nch = 3
+    ch = ChainBatch(prob, nch)
+    ch.set_state(g("v0"), g("w0"), g("vc0") if case["ncosF"] else None, g("wc0") if case["ncosD"] else None,
+                 dv=case["dv"], dw=case["dw"], dtimezero=case["dt0"], temp=case["temp"])
+    ll0 = ch.init_log_like()
+    np.testing.assert_allclose(ll0, float(g("ll0")), rtol=RTOL)
+    nmc = case["nmc"]
+    dec, llt, samples = ch.run(nmc, _params(case, nmc, method=METHODS[method]), g("tape_u"), g("tape_idx"),
+                               record=True, nsamples_cap=nmc // 100)
+    dec = dec.cpu().numpy()
+    st = ch.host_state()
+    for c in range(nch):   # all chains share the tape -> identical trajectories
+        assert np.array_equal(dec[c] >> 2, g("move"))
+        assert np.array_equal(dec[c] & 1, g("accepted"))
+        assert np.array_equal((dec[c] >> 1) & 1, g("accepted_t0"))
+    s0 = st["scal"][0]
+    np.testing.assert_allclose(s0[0], float(g("ll")), rtol=RTOL)
+    np.testing.assert_allclose(s0[1], float(g("timezero")), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(s0[2:4], [float(g("dv")), float(g("dw"))], rtol=1e-14)
+    np.testing.assert_allclose(s0[5], float(g("temp")), rtol=1e-14)
+    np.testing.assert_allclose(st["v"][0], g("v"), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(st["w"][0], g("w"), rtol=0, atol=1e-13)
+    assert list(st["counters"][0][:3]) == [int(g("naccv")), int(g("naccw")), int(g("nacct0"))]
+    assert st["counters"][0][6] == 0
+    if case["ncosF"]:
+        assert np.array_equal(st["naccv_coeff"][0], g("naccv_coeff"))
+    if case["ncosD"]:
+        assert np.array_equal(st["naccw_coeff"][0], g("naccw_coeff"))
+    # Logger rows (lib/log.py:35-58): rows 1.. of the reference logger
+    smp = samples.cpu().numpy()[0]
+    np.testing.assert_allclose(smp[:, 0], g("log_ll")[1:], rtol=RTOL)
+    np.testing.assert_allclose(smp[:, 2], g("log_dv")[1:], rtol=1e-14)
+    nv = g("log_pv").shape[1]
+    np.testing.assert_allclose(smp[:, 6:6 + nv], g("log_pv")[1:], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(smp[:, 6 + nv:], g("log_pw")[1:], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("method", ["eigen", "squaring"])
+def test_philox_run_equals_oracle_replay(engine, gold_ll, method):
+    """Production mode (Philox4x32-10 on device): the trajectory of each chain equals the
+    oracle replayed on the tape the host mirror of the RNG derives; chains are split over two
+    launches and over a chain_offset to cover resumption and multi-GPU sharding."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from mcdiff_b200 import philox
+    from oracle import mcdiff_oracle as O
+    G = gold_ll
+    n = 100
+    vb, wb = O.cos_basis_center(n, 6), O.cos_basis_border(n, n, 4)
+    prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True, v_basis=vb, w_basis=wb)
+    nch, nsteps, seed, off = 4, 160, 20240607, 1000
+    wc0 = np.zeros(4)
+    wc0[0] = G["P_flat_w"][0]
+    ch = ChainBatch(prob, nch)
+    ch.set_state(np.zeros(n), wb @ wc0, np.zeros(6), wc0, dv=0.3, dw=0.3)
+    ch.init_log_like()
+    case = dict(nmc_update=50.0, dtemp=0.0, lagtimes=G["P_lags"], move_timezero=False)
+    mp = _params(case, nsteps, use_tape=0, seed=seed, chain_offset=off, method=METHODS[method])
+    d1, _, _ = ch.run(100, mp, record=True)
+    d2, _, _ = ch.run(60, mp, record=True)
+    dec = np.concatenate([d1.cpu().numpy(), d2.cpu().numpy()], axis=1)
+    st = ch.host_state()
+    cfg = O.ChainConfig(G["P_counts"], G["P_lags"], True, v_basis=vb, w_basis=wb, dv=0.3, dw=0.3, temp=1.0,
+                        nmc=nsteps, num_mc_update=50.0)
+    for c in range(nch):
+        tu, ti = philox.chain_tape(seed, off + c, 0, nsteps, n, n, 6, 4)
+        out = O.replay(cfg, np.zeros(n), wb @ wc0, tu, ti, v_coeff0=np.zeros(6), w_coeff0=wc0)
+        assert np.array_equal(dec[c] & 1, out["accepted"]), "chain %d" % c
+        assert np.array_equal(dec[c] >> 2, out["move"])
+        np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
+        np.testing.assert_allclose(st["vcoef"][c], out["v_coeff"], atol=1e-13)
+        np.testing.assert_allclose(st["scal"][c][2:4], [out["dv"], out["dw"]], rtol=1e-13)
+    # different chains really are different streams
+    assert not np.array_equal(dec[0], dec[1])
+
+
+@pytest.mark.parametrize("method", ["eigen", "squaring"])
+def test_full_size_properties(engine, method):
+    """BASELINE shape (100 bins x 4 lags, 1024 chains): size-independent checks.
+    (a) log L of the final state recomputed by the cold batched path equals the running
+    log L each chain carried through warm-started solves; (b) propagators of final states are
+    column-stochastic and satisfy detailed balance P_ij pi_j = P_ji pi_i."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from oracle import mcdiff_oracle as O
+    counts, lags, edges, F, w_true = O.synthetic_counts()
+    n = 100
+    prob = DeviceProblem(engine, counts, lags, True)
+    nch = 1024
+    w0 = np.zeros(n) + np.log(1.0 / 0.25)
+    ch = ChainBatch(prob, nch)
+    ch.set_state(np.zeros(n), w0, dv=0.05, dw=0.05)
+    ll0 = ch.init_log_like()
+    ref0 = O.log_like_lag(np.zeros(n), w0, lags, counts, True)
+    np.testing.assert_allclose(ll0, ref0, rtol=RTOL)
+    case = dict(nmc_update=100.0, dtemp=0.0, lagtimes=lags, move_timezero=False)
+    mp = _params(case, 0, use_tape=0, seed=1, refresh=512, method=METHODS[method])
+    ch.run(300, mp)
+    st = ch.host_state()
+    assert not st["counters"][:, 6].any()
+    ll_cold, _, stat = prob.loglike(st["v"], st["w"])
+    assert not stat.any()
+    np.testing.assert_allclose(st["scal"][:, 0], ll_cold, rtol=1e-11)
+    assert np.all(st["scal"][:, 0] > ll0)          # every chain climbed from the flat start
+    acc = (st["counters"][:, 0] + st["counters"][:, 1]) / 300.0
+    assert 0.02 < acc.mean() < 0.9
+    # oracle on a few final states
+    for c in (0, 511, 1023):
+        np.testing.assert_allclose(st["scal"][c, 0], O.log_like_lag(st["v"][c], st["w"][c], lags, counts, True),
+                                   rtol=RTOL)
+    _, P, _ = prob.loglike(st["v"][:4], st["w"][:4], want_P=True)
+    for c in range(4):
+        pi = np.exp(-st["v"][c])
+        for l in range(4):
+            np.testing.assert_allclose(P[c, l].sum(axis=0), 1.0, atol=1e-12)
+            flux = P[c, l] * pi[None, :]
+            assert np.max(np.abs(flux - flux.T)) <= 1e-12 * np.max(flux)
+
+
+def test_radial_likelihood(engine, gold_radial):
+    from mcdiff_b200.engine import rad_loglike
+    Rd = gold_radial
+    ll, P, st = rad_loglike(engine, Rd["v"], Rd["w"], True, Rd["lags"], Rd["counts"], Rd["table"], Rd["zeros"],
+                            Rd["wrad"], want_P=True)
+    assert not st.any()
+    np.testing.assert_allclose(ll, Rd["ll"], rtol=RTOL)
+    assert np.max(np.abs(P[0, 0] - Rd["P0"])) <= RTOL * np.max(np.abs(Rd["P0"]))
+
+
+def test_large_n_generic_path(engine):
+    """n = 200, 8 lags (BASELINE config 3 shape): the work matrices do not fit in shared
+    memory, the generic global-memory path must give the same numbers."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    lags = (5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0)
+    counts, lags, edges, F, w_true = O.synthetic_counts(n=200, lags=lags, seed=3, total=2.0e5)
+    prob = DeviceProblem(engine, counts, lags, True)
+    assert not prob.in_smem
+    rng = np.random.default_rng(1)
+    v = F[None, :] + rng.normal(0, 0.2, (3, 200))
+    w = w_true[None, :] + rng.normal(0, 0.2, (3, 200))
+    ll, _, st = prob.loglike(v, w)
+    assert not st.any()
+    ref = [O.log_like_lag(v[b], w[b], lags, counts, True) for b in range(3)]
+    np.testing.assert_allclose(ll, ref, rtol=RTOL)
+
+
+def test_engines_agree_step_by_step(engine):
+    """Same Philox streams through both propagator engines: identical decisions for every
+    chain and step (each engine's log L error is orders of magnitude below the margins)."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from oracle import mcdiff_oracle as O
+    counts, lags, edges, F, w_true = O.synthetic_counts()
+    n = 100
+    prob = DeviceProblem(engine, counts, lags, True)
+    w0 = np.zeros(n) + np.log(1.0 / 0.25)
+    out = {}
+    for name, m in METHODS.items():
+        ch = ChainBatch(prob, 64)
+        ch.set_state(np.zeros(n), w0, dv=0.05, dw=0.05)
+        ch.init_log_like()
+        case = dict(nmc_update=100.0, dtemp=0.0, lagtimes=lags, move_timezero=False)
+        dec, llt, _ = ch.run(200, _params(case, 0, use_tape=0, seed=7, method=m), record=True)
+        out[name] = (dec.cpu().numpy(), llt.cpu().numpy(), ch.host_state())
+    assert np.array_equal(out["eigen"][0], out["squaring"][0])
+    np.testing.assert_allclose(out["eigen"][1], out["squaring"][1], rtol=1e-12)
+    np.testing.assert_allclose(out["eigen"][2]["v"], out["squaring"][2]["v"], atol=1e-13)
+
+
+def test_squaring_rejects_unsupported(engine, gold_ll):
+    from mcdiff_b200.engine import DeviceProblem
+    from mcdiff_b200._capi import McdError
+    G = gold_ll
+    prob = DeviceProblem(engine, G["S_counts"], G["S_lags"], True)     # lags 5, 12.5
+    assert not prob.squaring_ok
+    with pytest.raises(McdError):
+        prob.loglike(G["S_v"], G["S_w"], method=METHODS["squaring"])
