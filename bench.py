@@ -182,7 +182,7 @@ def run_gpu(args):
         mp.seed = seed
         mp.chain_offset = rank * nch
         mp.tape_stride = 0
-        mp.method = {"auto": 0, "eigen": 1, "squaring": 2}[args.method]
+        mp.method = {"auto": 0, "eigen": 1, "squaring": 2, "squaring_dfma": 3}[args.method]
         return mp
 
     # ---------------- device-resident arm: inputs already in HBM ----------------
@@ -309,7 +309,7 @@ def run_gpu(args):
             "chains_per_gpu": nch, "mc_steps_per_launch": MC_PER_LAUNCH, "mc_steps_per_bench_step": nch * MC_PER_LAUNCH,
             "l2": "256 MiB buffer rewritten between timed launches; working set (160 KB counts + per-chain state) "
                   "is smem/L2 resident by design, the kernel is FP64/shared-memory bound, not HBM bound",
-            "philox_seed": 1, "propagator_engine": ("squaring" if (args.method != "eigen" and prob.squaring_ok) else "eigen"),
+            "philox_seed": 1, "propagator_engine": ("eigen" if (args.method == "eigen" or not prob.squaring_ok) else ("squaring_dfma" if args.method == "squaring_dfma" else "squaring_dmma")),
             "jacobi_sweeps_or_squarings_per_mc_step": sweeps, "chains_with_status": bad,
             "mean_acceptance": float((summary_all[:, 6] + summary_all[:, 7]).sum() / max(1.0, float(world) * st["counters"][:, 5].sum())),
         },
@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--method", default="auto", choices=["auto", "eigen", "squaring"],
+    ap.add_argument("--method", default="auto", choices=["auto", "eigen", "squaring", "squaring_dfma"],
                     help="propagator engine (auto = symmetric scaling-and-squaring for this workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -54,10 +54,11 @@ enum {
 /* Propagator engines.  Both produce P_l = expm(lag_l R) (lib/utils.py:313):
  *  EIGEN    : in-CTA parallel Jacobi eigendecomposition of the detailed-balance-symmetrised
  *             generator, P = Pi^1/2 V exp(lag Lambda) V^T Pi^-1/2; any lag times, time-offset moves.
- *  SQUARING : symmetric scaling-and-squaring, all products as register-tiled FP64 GEMMs in shared
- *             memory; needs lag times in arithmetic progression lag_l = (l+1) lag_0, no time-offset
+ *  SQUARING : symmetric scaling-and-squaring, all products as FP64 tensor-core (mma.sync m8n8k4)
+ *             GEMMs on shared-memory operands; needs lag times in arithmetic progression lag_l = (l+1) lag_0, no time-offset
  *             move and n <= 108 (work matrices in shared memory). */
-enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2 };
+enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2,
+       MCD_METHOD_SQUARING_DFMA = 3 /* same algorithm, products on the FP64 vector pipe (A/B reference) */ };
 
 typedef struct mcd_handle mcd_handle;
 typedef struct mcd_problem mcd_problem;

@@ -1,0 +1,304 @@
+"""Monte-Carlo state of MANY chains, with the reference's MCState interface.
+
+The reference's MCState (lib/MCState.py:23-491) holds one chain and evaluates one move per
+Python call.  Here the same object fronts `nchains` independent chains that live on the GPU:
+`set_MC_params`, `set_model`, `use_initfile`, `init_log_like` keep their names, arguments and
+error behaviour; the per-move methods are replaced by `advance(nsteps)`, which runs the fused
+CUDA loop (mcd_mc_run) for all chains at once.  Scalar attributes (`dv`, `dw`, `temp`,
+`log_like`, `naccv`, ...) always mirror chain 0, so code written against the reference keeps
+working; the `chain_*` arrays expose every chain.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from . import _capi as K
+from .model import MODELS_1D, Model, RadCosinusModel, RadModel
+from .outreading import read_Dcoeffs, read_Fcoeffs, read_F_D_edges, read_dv_dw
+from .parallel import shard_range
+
+
+def _string_vecs(n, pbc):
+    """Eigenvectors of the 1-D Laplacian: directions of the smoothed moves (lib/utils.py:294-305)."""
+    M = 2.0 * np.eye(n)
+    i = np.arange(n - 1)
+    M[i, i + 1] = -1.0
+    M[i + 1, i] = -1.0
+    if pbc:
+        M[0, n - 1] = M[n - 1, 0] = -1.0
+    else:
+        M[0, 0] = M[n - 1, n - 1] = 1.0
+    return np.linalg.eigh(M)[1]
+
+
+class MCState:
+    def __init__(self, pbc, lmax=-1, nchains=1, device=None, seed=None, rank=0, world=1, method="auto",
+                 jitter=0.0):
+        self.pbc = pbc
+        self.lmax = lmax
+        self.do_radial = lmax > 0
+        self.nchains_total = int(nchains)
+        self.rank, self.world = int(rank), int(world)
+        self.chain_lo, self.chain_hi = shard_range(self.nchains_total, self.rank, self.world)
+        self.nchains = self.chain_hi - self.chain_lo
+        self.device = device
+        self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        self.method = {"auto": K.METHOD_AUTO, "eigen": K.METHOD_EIGEN, "squaring": K.METHOD_SQUARING}[method]
+        self.jitter = float(jitter)
+        self.engine = None
+        self.problem = None
+        self.chains = None
+        self.steps_done = 0
+
+    # ---- lib/MCState.py:29-61 ------------------------------------------------------------
+    def set_MC_params(self, dv, dw, dwrad, D0, dtimezero, temp, nmc, num_MC_update, move_timezero, k, temp_end=None):
+        self.dv, self.dw, self.dwrad, self.D0, self.dtimezero = dv, dw, dwrad, D0, dtimezero
+        self.temp = self.temp_start = temp
+        self.temp_end = temp_end
+        self.nmc = nmc
+        self.num_MC_update = num_MC_update
+        self.move_timezero = move_timezero
+        if self.temp_end is None:
+            self.temp_end = temp
+            self.dtemp = 0.0
+        else:
+            nupdate = self.nmc / self.num_MC_update - 1 if self.num_MC_update else 0
+            self.dtemp = (self.temp_end - self.temp_start) / float(nupdate) if nupdate > 0 else 0.0
+        self.naccv = self.naccw = self.naccwrad = self.nacctimezero = 0
+        self.naccv_update = self.naccw_update = self.naccwrad_update = self.nacctimezero_update = 0
+        self.k = k
+
+    # ---- lib/MCState.py:63-99 ------------------------------------------------------------
+    def set_model(self, model, data, ncosF, ncosD, ncosDrad, pull):
+        self.data = data
+        self.pull = None if pull is None else -pull * self.data.dz
+        if self.pull is not None:
+            raise NotImplementedError(
+                "--pull makes the generator non-symmetrisable (complex spectrum); the CUDA engines of this "
+                "build cover the symmetric cases only. Run the reference for --pull.")
+        if self.do_radial:
+            if model == "RadCosinusModel":
+                self.model = RadCosinusModel(self.data, self.D0, ncosF, ncosD, 0, ncosDrad)
+            elif model == "RadModel":
+                self.model = RadModel(self.data, self.D0, ncosF, ncosD, 0)
+            else:
+                raise ValueError("model %s not found" % model)
+            from scipy import special
+            zeros = special.jn_zeros(0, self.lmax)                       # lib/twod.py:45-59
+            r = np.arange(self.model.dim_rad, dtype=np.float64) + 0.5
+            rmax = np.float64(self.model.dim_rad)
+            self.model.bessel0_zeros = zeros
+            self.model.bessels = np.array([2 * r * special.j0(r / rmax * z) / special.j1(z) ** 2 / rmax ** 2
+                                           for z in zeros])
+        else:
+            if model in MODELS_1D:
+                self.model = MODELS_1D[model](self.data, self.D0, ncosF, ncosD, 0)
+            elif model == "Model":
+                self.model = Model(self.data, self.D0)
+            else:
+                raise ValueError("model %s not found" % model)
+        if self.pbc != self.model.pbc:
+            raise AssertionError("pbc flag and counting method of the transition matrices disagree")
+
+    # ---- lib/MCState.py:139-201 ------------------------------------------------------------
+    def use_initfile(self, initfile, final=True):
+        m = self.model
+        if m.ncosF > 0:
+            c = read_Fcoeffs(initfile, final=True)
+            if len(c) > 0:
+                print("USING initfile for v_coeff", initfile, len(c), "coeffs")
+                k = min(len(c), m.ncosF)
+                m.v_coeff[:k] = c[:k]
+                m.update_v()
+        else:
+            F, D, edges = read_F_D_edges(initfile)
+            if len(F) != len(m.v):
+                raise AssertionError("initfile has %d bins, model has %d" % (len(F), len(m.v)))
+            print("USING initfile for v", initfile, len(F), "values")
+            m.v = F
+        if m.ncosD > 0:
+            c = read_Dcoeffs(initfile, final=True)
+            if len(c) > 0:
+                print("USING initfile for w_coeff", initfile, len(c), "coeffs")
+                k = min(len(c), m.ncosD)
+                m.w_coeff[:k] = c[:k]
+                m.w_coeff[0] -= m.wunit
+                m.update_w()
+        else:
+            F, D, edges = read_F_D_edges(initfile)
+            if len(D) != len(m.w):
+                raise AssertionError("initfile has %d D values, model has %d" % (len(D), len(m.w)))
+            print("USING initfile for w", initfile, len(D), "values")
+            m.w = np.log(D) - m.wunit
+        read_dv_dw(initfile, final=True)      # read but not applied, like lib/MCState.py:199-201
+
+    # ---- device set-up -----------------------------------------------------------------------
+    def _ensure_device(self):
+        if self.chains is not None:
+            return
+        from .engine import ChainBatch, DeviceProblem, Engine
+        if self.do_radial:
+            raise NotImplementedError("radial Monte-Carlo moves are not part of this build; the radial "
+                                      "likelihood is available as engine.rad_loglike")
+        m = self.model
+        self.engine = Engine(self.device)
+        svecs = _string_vecs(m.dim_w, self.pbc) if self.k > 0 else None
+        self.string_vecs = svecs
+        counts = np.asarray(self.data.list_trans)
+        if not np.all(counts == np.round(counts)):
+            raise ValueError("transition counts must be integers")
+        self.problem = DeviceProblem(self.engine, counts.astype(np.int64), self.data.list_lt, self.pbc,
+                                     v_basis=m.v_basis if m.ncosF > 0 else None,
+                                     w_basis=m.w_basis if m.ncosD > 0 else None,
+                                     spring_k=self.k if self.k > 0 else -1.0, string_vecs=svecs)
+        self.chains = ChainBatch(self.problem, self.nchains)
+        v = np.tile(m.v, (self.nchains, 1))
+        w = np.tile(m.w, (self.nchains, 1))
+        vc = np.tile(m.v_coeff, (self.nchains, 1)) if m.ncosF > 0 else None
+        wc = np.tile(m.w_coeff, (self.nchains, 1)) if m.ncosD > 0 else None
+        if self.jitter > 0:     # optional over-dispersed starts; chain 0 of rank 0 keeps the exact start
+            rng = np.random.default_rng(self.seed ^ 0x5DEECE66D)
+            skip = 1 if self.rank == 0 else 0
+            if m.ncosF > 0:
+                vc[skip:, 1:] += self.jitter * rng.standard_normal(vc[skip:, 1:].shape)
+                v = vc @ m.v_basis.T
+            else:
+                v[skip:] += self.jitter * rng.standard_normal(v[skip:].shape)
+            if m.ncosD > 0:
+                wc[skip:] += self.jitter * rng.standard_normal(wc[skip:].shape)
+                w = wc @ m.w_basis.T
+            else:
+                w[skip:] += self.jitter * rng.standard_normal(w[skip:].shape)
+        self.chains.set_state(v, w, vc, wc, dv=self.dv, dw=self.dw, dtimezero=self.dtimezero, temp=self.temp,
+                              timezero=m.timezero)
+
+    # ---- lib/MCState.py:101-137 ----------------------------------------------------------------
+    def init_log_like(self):
+        self._ensure_device()
+        ll = self.chains.init_log_like()          # raises ValueError("Initial likelihood diverges") on NaN
+        self.chain_log_like = ll
+        self.log_like = float(ll[0])
+        print("initial log-likelihood:", self.log_like)
+        m = self.model
+        if m.ncosF > 0:
+            self.naccv_coeff = np.zeros(m.ncosF, int)
+        if m.ncosD > 0:
+            self.naccw_coeff = np.zeros(m.ncosD, int)
+        return ll
+
+    # ---- the hot loop: lib/mc.py:27-51 on the GPU ------------------------------------------------
+    def mc_params(self):
+        mp = K.McParams()
+        mp.num_mc_update = float(self.num_MC_update)
+        mp.dtemp = float(self.dtemp)
+        mp.min_lt = float(self.data.min_lt)
+        mp.move_timezero = int(bool(self.move_timezero))
+        mp.sample_every = 100
+        mp.refresh_every = 512
+        mp.use_tape = 0
+        mp.method = self.method
+        mp.taylor_m = 0
+        mp.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        mp.chain_offset = self.chain_lo
+        mp.tape_stride = 0
+        return mp
+
+    def advance(self, nsteps, want_samples=True):
+        """Run nsteps MC steps on every chain; returns the host sample rows
+        [nchains][k][sample_dim] taken at steps that are multiples of 100."""
+        self._ensure_device()
+        first = self.steps_done
+        nsamp = (first + nsteps) // 100 - first // 100 if want_samples else 0
+        _, _, smp = self.chains.run(nsteps, self.mc_params(), nsamples_cap=nsamp)
+        self.steps_done += nsteps
+        self.sync_from_device()
+        return None if smp is None else smp.cpu().numpy()
+
+    def sync_from_device(self):
+        st = self.chains.host_state()
+        self.chain_v, self.chain_w = st["v"], st["w"]
+        self.chain_v_coeff, self.chain_w_coeff = st["vcoef"], st["wcoef"]
+        sc, ct = st["scal"], st["counters"]
+        self.chain_log_like = sc[:, K.S_LL].copy()
+        self.chain_timezero = sc[:, K.S_T0].copy()
+        self.chain_dv, self.chain_dw = sc[:, K.S_DV].copy(), sc[:, K.S_DW].copy()
+        self.chain_temp = sc[:, K.S_TEMP].copy()
+        self.chain_naccv, self.chain_naccw = ct[:, K.C_NACCV].copy(), ct[:, K.C_NACCW].copy()
+        self.chain_nacctimezero = ct[:, K.C_NACCT0].copy()
+        self.chain_status = ct[:, K.C_STATUS].copy()
+        self.chain_naccv_coeff, self.chain_naccw_coeff = st["naccv_coeff"], st["naccw_coeff"]
+        # chain 0 -> the reference's scalar attributes
+        m = self.model
+        m.v, m.w = st["v"][0].copy(), st["w"][0].copy()
+        if m.ncosF > 0:
+            m.v_coeff = st["vcoef"][0].copy()
+            self.naccv_coeff = st["naccv_coeff"][0].copy()
+        if m.ncosD > 0:
+            m.w_coeff = st["wcoef"][0].copy()
+            self.naccw_coeff = st["naccw_coeff"][0].copy()
+        m.timezero = float(sc[0, K.S_T0])
+        m.list_lt = np.asarray(self.data.list_lt) + m.timezero
+        self.log_like = float(sc[0, K.S_LL])
+        self.dv, self.dw, self.temp = float(sc[0, K.S_DV]), float(sc[0, K.S_DW]), float(sc[0, K.S_TEMP])
+        self.naccv, self.naccw = int(ct[0, K.C_NACCV]), int(ct[0, K.C_NACCW])
+        self.nacctimezero = int(ct[0, K.C_NACCT0])
+
+    # ---- printing (same text as lib/MCState.py:396-491) ----------------------------------------
+    def print_MC_params(self, f=None, final=False):
+        f = f or sys.stdout
+        print("----- final Settings MC -----" if final else "----- Settings MC -----", file=f)
+        print("dv(MC-potential)=", self.dv, file=f)
+        print("dw(MC-logD)=", self.dw, file=f)
+        print("dwrad(MC-logDrad)=", self.dwrad, file=f)
+        print("temp=", self.temp, file=f)
+        print("n(MC)=", self.nmc, file=f)
+        print("n(update)=", self.num_MC_update, file=f)
+        print("k=", self.k, file=f)
+        print("-" * 20, file=f)
+
+    def print_intermediate(self, imc, printfreq=100):
+        step = imc + 1
+        print(imc, self.log_like, float(self.naccv) / step, float(self.naccw) / step, float(self.naccwrad) / step)
+
+    def print_statistics(self, f=None):
+        f = f or sys.stdout
+        print("===== Statistics =====", file=f)
+        print("nmc         ", self.nmc, file=f)
+        print("naccv       ", self.naccv, file=f)
+        print("naccw       ", self.naccw, file=f)
+        print("naccwrad    ", self.naccwrad, file=f)
+        print("nacctimezero", self.nacctimezero, file=f)
+        for name, val in (("accv ratio       ", self.naccv), ("accw ratio       ", self.naccw),
+                          ("accwrad ratio    ", self.naccwrad), ("acctimezero ratio", self.nacctimezero)):
+            print(name, "%5.1f" % (float(val) / self.nmc * 100), "%", file=f)
+        print("=" * 10, file=f)
+        m = self.model
+        for ncos, title, arr in ((m.ncosF, "naccv_coeff", getattr(self, "naccv_coeff", None)),
+                                 (m.ncosD, "naccw_coeff", getattr(self, "naccw_coeff", None))):
+            if ncos > 0:
+                tot = max(1, np.sum(arr))
+                print(title, file=f)
+                for i, val in enumerate(arr):
+                    print("%8d %8d %5.1f %s %5.1f %s" % (i, val, float(val) / tot * 100, "%",
+                                                        float(val) / self.nmc * 100, "%"), file=f)
+        if self.nchains > 1:
+            acc = (self.chain_naccv + self.chain_naccw) / float(max(1, self.nmc))
+            print("===== Statistics over %d chains =====" % self.nchains, file=f)
+            print("acceptance mean/min/max %6.3f %6.3f %6.3f" % (acc.mean(), acc.min(), acc.max()), file=f)
+            print("log-like   mean/min/max", self.chain_log_like.mean(), self.chain_log_like.min(),
+                  self.chain_log_like.max(), file=f)
+
+    def print_coeffs_laststate(self, f, final=False):
+        from .log import print_coeffs
+        m = self.model
+        print_coeffs(f, m, m.v_coeff if m.ncosF > 0 else None, m.w_coeff if m.ncosD > 0 else None, None,
+                     m.timezero if self.move_timezero else None, final=final)
+
+    def print_laststate(self, f, final=False):
+        from .log import print_profiles
+        self.print_MC_params(f, final=final)
+        self.print_coeffs_laststate(f, final=final)
+        print_profiles(f, self.model, self.model.v, self.model.w, wrad=None, final=final)

@@ -16,7 +16,7 @@ MCD_NCOUNT = 8
 S_LL, S_T0, S_DV, S_DW, S_DT0, S_TEMP = range(6)
 C_NACCV, C_NACCW, C_NACCT0, C_NACCV_UPD, C_NACCW_UPD, C_STEP, C_STATUS, C_SWEEPS = range(8)
 ST_EIG_NOCONV, ST_NAN_TRIAL = 1, 2
-METHOD_AUTO, METHOD_EIGEN, METHOD_SQUARING = 0, 1, 2
+METHOD_AUTO, METHOD_EIGEN, METHOD_SQUARING, METHOD_SQUARING_DFMA = 0, 1, 2, 3
 
 c_dp = C.c_void_p  # device (or, for the test emulator, host) pointers are passed as integers
 

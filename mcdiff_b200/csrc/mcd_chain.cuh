@@ -42,7 +42,7 @@ struct McParams {
   int sample_every;      // lib/log.py:9  (100)
   int refresh_every;     // cold re-solve period (bounds orthogonality drift of the warm start)
   int use_tape;          // 1: proposals/uniforms from the host tape, 0: Philox4x32-10
-  int method;            // 1: Jacobi eigendecomposition, 2: symmetric scaling-and-squaring
+  int method;            // 1: Jacobi eigen, 2: scaling-and-squaring on FP64 tensor cores, 3: same with DFMA
   int taylor_m;          // Taylor order of the squaring engine (0 = default 20)
   unsigned long long seed;
   long long chain_offset;  // global id of chain 0 of this launch (multi-GPU sharding)
@@ -76,6 +76,14 @@ struct ChainIO {
   double* samples;           // [C][nsamples_cap][sample_dim]
 };
 
+// Padded bin count (multiple of 8: 8x8 tensor tiles, 4x4 register tiles) and leading dimension.
+// ld = 4 mod 8 doubles: a 64-bit shared load is served per half-warp, and the half-warp of an
+// m8n8k4 fragment load touches 4 consecutive k-rows x 4 doubles; with a row pitch of 32 mod 64
+// bytes those four 32-byte pieces fall into four different bank groups (conflict-free).  Rows stay
+// 16-byte aligned for the 128-bit loads of the vector-pipe kernels.
+MCD_HOSTDEV int padded_bins(int n) { return (n + 7) & ~7; }
+MCD_HOSTDEV int leading_dim(int np) { return np + 4; }
+
 MCD_HOSTDEV int sample_dim(const Problem& P) {
   return 6 + (P.ncosF > 0 ? P.ncosF : P.n) + (P.ncosD > 0 ? P.ncosD : P.dim_w);
 }
@@ -108,7 +116,7 @@ MCD_HD double u53(uint32_t hi, uint32_t lo) {
 struct Scalars {
   double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring;
   long long naccv, naccw, nacct0, naccv_upd, naccw_upd, step, status, sweeps;
-  int move, idx, accepted, accepted_t0, nsamp, basis_is_trial, do_t0, pad;
+  int move, idx, accepted, accepted_t0, nsamp, basis_is_trial, do_t0, mma_tasks;
 };
 
 struct Smem {
@@ -124,6 +132,7 @@ struct Smem {
   int *rp, *rq;
   unsigned char* tiles;    // 2 bytes per tile (ib, jb), ib <= jb
   unsigned char* jblocks;  // 2 bytes per Jacobi block (ka, kb), ka < kb
+  unsigned char* wtab;     // 16 bytes per warp task of the tensor-core product (see build_tables)
   Scalars* sc;
   int ntiles, nblk;
 };
@@ -131,7 +140,7 @@ struct Smem {
 MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
   size_t d = (size_t)np * 10 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
   size_t nb = np / 4, h = np / 2;
-  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + sizeof(Scalars) + 64;
+  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + 16 * (kThreads / 32) + sizeof(Scalars) + 64;
   return (bytes + 15) & ~(size_t)15;
 }
 MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
@@ -172,7 +181,8 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
   s.ntiles = nb * (nb + 1) / 2;
   s.nblk = h * (h - 1) / 2;
   s.tiles = c; c += 2 * s.ntiles;
-  s.jblocks = c;
+  s.jblocks = c; c += 2 * s.nblk;
+  s.wtab = c;
   return s;
 }
 
@@ -201,6 +211,58 @@ struct Chain {
                 s.tiles[2 * t + 1] = (unsigned char)jb;
                 ++t;
               }
+      // Tensor-core warp tasks: the upper triangle of the (np/8)^2 grid of 8x8 tiles is cut into
+      // row segments of at most 8 tiles; a warp owns one full segment or two partial ones
+      // (first-fit decreasing), i.e. at most 8 tiles from at most 2 tile rows, so that one or
+      // two A fragments serve all of its MMAs.  wtab[w] = {nt, na, rowA, rowB, jb[8]}: tiles
+      // t < na belong to rowA, na <= t < nt to rowB, t >= nt are padding (computed, not used).
+      {
+        const int nb8 = P.np / 8, cap = 8, maxw = kThreads / 32;
+        unsigned char sib[64], sjb[64], sln[64], used[64];
+        int nseg = 0;
+        for (int ib = 0; ib < nb8; ++ib)
+          for (int jb = ib; jb < nb8; jb += cap) {
+            sib[nseg] = (unsigned char)ib; sjb[nseg] = (unsigned char)jb;
+            sln[nseg] = (unsigned char)((nb8 - jb < cap) ? nb8 - jb : cap);
+            used[nseg] = 0; ++nseg;
+          }
+        int nw = 0;
+        bool ok = true;
+        auto put = [&](int w, int sg, bool first) {
+          unsigned char* wt = s.wtab + 16 * w;
+          if (first) { wt[0] = 0; wt[1] = sln[sg]; wt[2] = sib[sg]; wt[3] = sib[sg]; }
+          else wt[3] = sib[sg];
+          for (int t = 0; t < sln[sg]; ++t) wt[4 + wt[0] + t] = (unsigned char)(sjb[sg] + t);
+          wt[0] = (unsigned char)(wt[0] + sln[sg]);
+        };
+        for (int sg = 0; sg < nseg; ++sg)
+          if (sln[sg] == cap) {
+            if (nw < maxw) put(nw, sg, true); else ok = false;
+            used[sg] = 1; ++nw;
+          }
+        const int first_partial = nw;
+        int nsegs_in[kThreads / 32];
+        for (int w = 0; w < maxw; ++w) nsegs_in[w] = 0;
+        for (;;) {
+          int best = -1;
+          for (int sg = 0; sg < nseg; ++sg)
+            if (!used[sg] && (best < 0 || sln[sg] > sln[best])) best = sg;
+          if (best < 0) break;
+          used[best] = 1;
+          int w = -1;
+          for (int c = first_partial; c < nw && c < maxw; ++c)
+            if (nsegs_in[c] == 1 && s.wtab[16 * c] + sln[best] <= cap) { w = c; break; }
+          if (w < 0) {
+            w = nw++;
+            if (w < maxw) { put(w, best, true); nsegs_in[w] = 1; } else ok = false;
+          } else { put(w, best, false); nsegs_in[w] = 2; }
+        }
+        for (int w = 0; w < nw && w < maxw; ++w) {
+          unsigned char* wt = s.wtab + 16 * w;
+          for (int t = wt[0]; t < cap; ++t) wt[4 + t] = wt[4];
+        }
+        s.sc->mma_tasks = ok ? nw : 0;
+      }
       const int h = P.np / 2;
       int q = 0;
       for (int ka = 0; ka < h; ++ka)
@@ -573,9 +635,148 @@ struct Chain {
     }
   }
 
+  // ---- FP64 tensor-core variant of sym_product (mma.sync.m8n8k4.f64) ----------------------
+  // ncu on the DFMA version: LSU shared wavefronts 74 % busy, FP64 pipe 29 % -- a 4x4 register
+  // tile needs 0.5 operand doubles per FMA from shared memory.  An m8n8k4 fragment shares its
+  // operands across the 32 lanes: 2 doubles per lane feed 8 FMAs per lane.  Each warp owns up to
+  // 8 consecutive upper-triangular 8x8 tiles (row-major, so the A fragment is mostly reused) and
+  // keeps their 2-doubles-per-lane accumulators in registers; results are register-staged and
+  // written back in place after the barrier, like the DFMA version.
+  static constexpr int kTilesPerWarp = 8;
+  MCD_HD bool dmma_ok() const { return s.sc->mma_tasks > 0; }
+
+#if defined(__CUDA_ARCH__)
+  static __device__ __forceinline__ double lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+  }
+  // k loop of one warp task: NA tiles use the A fragment of rowA, the others that of rowB.
+  template <int NA>
+  static __device__ __forceinline__ void mma_loop(unsigned ax, unsigned ay, int pitch4, int nk4, int offA0, int offA1,
+                                                  const int (&offB)[kTilesPerWarp], double (&c)[kTilesPerWarp][2]) {
+#pragma unroll 2
+    for (int it = 0; it < nk4; ++it) {
+      const double a0 = lds64(ax + offA0);
+      const double a1 = (NA < kTilesPerWarp) ? lds64(ax + offA1) : 0.0;
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) {
+        const double b = lds64(ay + offB[t]);
+        const double a = (t < NA) ? a0 : a1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1])
+                     : "d"(a), "d"(b));
+      }
+      ax += pitch4;
+      ay += pitch4;
+    }
+  }
+#endif
+
+  MCD_HD void dmma_product(const double* X, const double* Y, double* D, const int* cnt, double* Pl, bool store) {
+    const int n = P.n, np = P.np, ld = P.ld;
+    const int ntasks = s.sc->mma_tasks;
+    ex.par([&](int tid) {
+      const int warp = tid >> 5, lane = tid & 31;
+      const unsigned char* wt = s.wtab + 16 * warp;
+      const bool active = warp < ntasks;
+      const int nt = active ? wt[0] : 0, na = active ? wt[1] : 0;
+      const int rowA = wt[2], rowB = wt[3];
+      double c[kTilesPerWarp][2];
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+      const int fr = lane >> 2, fk = lane & 3;   // fragment row (m or n) and k index of this lane
+      if (active) {
+#if defined(__CUDA_ARCH__)
+        int offB[kTilesPerWarp];
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = wt[4 + t] * 64;
+        const unsigned ax = (unsigned)__cvta_generic_to_shared(X) + (unsigned)(fk * ld + fr) * 8u;
+        const unsigned ay = (unsigned)__cvta_generic_to_shared(Y) + (unsigned)(fk * ld + fr) * 8u;
+        const int pitch4 = 4 * ld * 8, nk4 = np / 4;
+        switch (na) {
+          case 1: mma_loop<1>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 2: mma_loop<2>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 3: mma_loop<3>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 4: mma_loop<4>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 5: mma_loop<5>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 6: mma_loop<6>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          case 7: mma_loop<7>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          default: mma_loop<8>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+        }
+#else
+        for (int t = 0; t < nt; ++t) {
+          const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
+          const int i = ib * 8 + fr;
+          for (int e = 0; e < 2; ++e) {
+            const int j = jb * 8 + 2 * fk + e;
+            double acc = 0.0;
+            for (int k = 0; k < np; ++k) acc = fma(X[k * ld + i], Y[k * ld + j], acc);
+            c[t][e] = acc;
+          }
+        }
+#endif
+      }
+      // likelihood epilogue: this lane owns G[i][j], G[i][j+1] (and their mirrors)
+      if (cnt && nt > 0) {
+        double part = 0.0;
+        const double clip = P.clip;
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          if (t < nt) {
+            const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+            const double eai = s.ea[i], ebi = s.eb[i];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int jj = j + e;
+              const double g = c[t][e];
+              const int nij = cnt[(size_t)i * np + jj];
+              const double pij = eai * g * s.eb[jj];
+              if (nij != 0) part += (double)nij * log(fmax(pij, clip));
+              if (Pl && i < n && jj < n) Pl[(size_t)i * n + jj] = pij;
+              if (ib != jb) {
+                const int nji = cnt[(size_t)jj * np + i];
+                const double pji = s.ea[jj] * g * ebi;
+                if (nji != 0) part += (double)nji * log(fmax(pji, clip));
+                if (Pl && i < n && jj < n) Pl[(size_t)jj * n + i] = pji;
+              }
+            }
+          }
+        }
+        s.part[tid] += part;
+      }
+      double* r = ex.regs(tid);
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) { r[2 * t] = c[t][0]; r[2 * t + 1] = c[t][1]; }
+    });
+    if (store) {
+      ex.par([&](int tid) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const unsigned char* wt = s.wtab + 16 * warp;
+        const int nt = (warp < ntasks) ? wt[0] : 0, na = wt[1];
+        const int fr = lane >> 2, fk = lane & 3;
+        const double* r = ex.regs(tid);
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          if (t < nt) {
+            const int ib = (t < na) ? wt[2] : wt[3], jb = wt[4 + t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+            st2(D + i * ld + j, r[2 * t], r[2 * t + 1]);
+            if (ib != jb) {
+              D[j * ld + i] = r[2 * t];
+              D[(j + 1) * ld + i] = r[2 * t + 1];
+            }
+          }
+        }
+      });
+    }
+  }
+
   // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
-  MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, int taylor_m, double* Pout,
-                            int* squarings_out) {
+  MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, int taylor_m, bool tensor,
+                            double* Pout, int* squarings_out) {
+    const bool use_mma = tensor && dmma_ok();
     const int n = P.n, np = P.np, ld = P.ld;
     build_S(v, w);
     // Gershgorin bound of ||S||
@@ -604,7 +805,7 @@ struct Chain {
     // ---- T_m(hS) by Horner, band-limited: H <- I + (hS H)/k, k = m..1, ping-pong A/B ----
     ex.par([&](int tid) {
       for (int e = tid; e < np * ld; e += Exec::nthr()) { A[e] = 0.0; B[e] = 0.0; }
-      if (tid < s.ntiles) s.part[tid] = 0.0;
+      s.part[tid] = 0.0;
     });
     double* src = (m & 1) ? B : A;   // after m steps the result sits in A
     double* dst = (m & 1) ? A : B;
@@ -634,7 +835,10 @@ struct Chain {
       double* tmp = src; src = dst; dst = tmp;
     }
     // ---- G(t0) = T^(2^s) ----
-    for (int q = 0; q < nsq; ++q) sym_product(A, A, A, nullptr, nullptr, true, nullptr);
+    for (int q = 0; q < nsq; ++q) {
+      if (use_mma) dmma_product(A, A, A, nullptr, nullptr, true);
+      else sym_product(A, A, A, nullptr, nullptr, true, nullptr);
+    }
     // ---- likelihood of lag 0 straight from A, then the progression G((l+1) t0) = G(l t0) G(t0) ----
     {
       const int* cnt = P.counts;
@@ -656,10 +860,11 @@ struct Chain {
     for (int l = 1; l < P.nlag; ++l) {
       const int* cnt = P.counts + (size_t)l * np * np;
       double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
-      sym_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag, nullptr);
+      if (use_mma) dmma_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag);
+      else sym_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag, nullptr);
     }
     if (squarings_out) *squarings_out = nsq;
-    return ex.sum([&](int tid) { return (tid < s.ntiles) ? s.part[tid] : 0.0; });
+    return ex.sum([&](int tid) { return s.part[tid]; });
   }
 
   // Full likelihood of the profile (v, w) at lag times lagt.
@@ -865,8 +1070,8 @@ struct Chain {
 
         int sw = 0;
         double ll_new;
-        if (mp.method == 2) {
-          ll_new = evaluate_sq(vtry, wtry, lagp, mp.taylor_m, nullptr, &sw);
+        if (mp.method >= 2) {
+          ll_new = evaluate_sq(vtry, wtry, lagp, mp.taylor_m, mp.method == 2, nullptr, &sw);
         } else {
           ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
           have_basis = (sw >= 0);

@@ -30,6 +30,9 @@ struct i4 {
   int x, y, z, w;
 };
 
+// max that propagates NaN (fmax would drop it): non-finite profiles must surface as NaN
+MCD_HD double nanmax(double a, double b) { return (a != a || a > b) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
 MCD_HD d2 ld2(const double* p) {
 #if defined(__CUDA_ARCH__)
   double2 t = *reinterpret_cast<const double2*>(p);
@@ -94,12 +97,12 @@ struct DeviceExec {
   __device__ __forceinline__ double max(F f) {
     double v = f(tid);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     double t = red[0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) t = fmax(t, red[w]);
+    for (int w = 1; w < kThreads / 32; ++w) t = nanmax(t, red[w]);
     __syncthreads();
     return t;
   }
@@ -141,7 +144,7 @@ struct HostExec {
   template <class F>
   double max(F f) {
     double m = f(0);
-    for (int t = 1; t < kThreads; ++t) m = std::fmax(m, f(t));
+    for (int t = 1; t < kThreads; ++t) m = nanmax(m, f(t));
     return m;
   }
 };

@@ -86,7 +86,7 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
     });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = (kSmemMat && method == MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, Pb, &sw)
+    const double ll = (kSmemMat && method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, method == MCD_METHOD_SQUARING, Pb, &sw)
                                                                   : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
@@ -181,7 +181,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int n = d->n, dim_w = d->pbc ? n : n - 1;
-  const int np = (n + 3) & ~3, ld = np + 2;
+  const int np = padded_bins(n), ld = leading_dim(np);
 
   mcd_problem* p = new (std::nothrow) mcd_problem();
   if (!p) return MCD_E_NOMEM;
@@ -275,8 +275,8 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
                       void* stream) {
   if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
   if (method == MCD_METHOD_AUTO) method = MCD_METHOD_EIGEN;
-  if (method != MCD_METHOD_EIGEN && method != MCD_METHOD_SQUARING) return MCD_E_ARG;
-  if (method == MCD_METHOD_SQUARING && (!p->squaring_ok || lagtimes)) return MCD_E_UNSUPPORTED;
+  if (method < MCD_METHOD_EIGEN || method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
+  if (method >= MCD_METHOD_SQUARING && (!p->squaring_ok || lagtimes)) return MCD_E_UNSUPPORTED;
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -318,8 +318,8 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   std::memcpy(&cio, io, sizeof(cio));
   const bool sq_ok = p->squaring_ok && !mp.move_timezero;
   if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
-  if (mp.method == MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
-  if (mp.method != MCD_METHOD_SQUARING && mp.method != MCD_METHOD_EIGEN) return MCD_E_ARG;
+  if (mp.method < MCD_METHOD_EIGEN || mp.method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
+  if (mp.method >= MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
   if (p->in_smem) {
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
@@ -348,7 +348,7 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   RadProblem R;
-  R.n = n; R.np = (n + 3) & ~3; R.ld = R.np + 2; R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
+  R.n = n; R.np = padded_bins(n); R.ld = leading_dim(R.np); R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
   R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
   R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
   R.clip = clip;

@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing: chains shard over ranks, nothing is exchanged while sampling.
+
+One process per GPU (torchrun / torch.distributed, backend "nccl" on GPUs, "gloo" in the CPU
+tests).  Every rank owns a contiguous block of the global chain index (the Philox stream of a
+chain is keyed by its GLOBAL index, so the trajectories do not depend on the number of GPUs),
+and ONE collective at the end collects the per-chain posterior summaries and acceptance
+statistics on every rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(nchains: int, rank: int, world: int):
+    """Block partition [lo, hi) of the global chain index for `rank` (remainder to the first ranks)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(nchains), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def dist_info():
+    """(rank, world, initialised) from torch.distributed, (0, 1, False) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), True
+    except Exception:
+        pass
+    return 0, 1, False
+
+
+def all_gather_rows(local_rows: np.ndarray, nchains_total: int, device=None) -> np.ndarray:
+    """Gather per-chain rows [n_local][k] of every rank into [nchains_total][k], chain order =
+    global chain index.  Uses all_gather_into_tensor on equal-sized padded blocks."""
+    import torch
+    import torch.distributed as dist
+    rank, world, on = dist_info()
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
+    if not on or world == 1:
+        return local_rows
+    k = local_rows.shape[1]
+    sizes = [shard_range(nchains_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    buf = torch.zeros((width, k), dtype=torch.float64, device=device)
+    buf[: local_rows.shape[0]] = torch.from_numpy(local_rows).to(device)
+    out = torch.empty((world * width, k), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, buf)
+    out = out.cpu().numpy().reshape(world, width, k)
+    return np.concatenate([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], axis=0)
+
+
+def reduce_max(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+    rank, world, on = dist_info()
+    if not on or world == 1:
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

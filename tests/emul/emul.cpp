@@ -24,8 +24,8 @@ struct HostProblem {
 
 void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
   Problem& P = hp.P;
-  const int n = d->n, np = (n + 3) & ~3;
-  P.n = n; P.np = np; P.ld = np + 2; P.pbc = d->pbc ? 1 : 0; P.dim_w = d->pbc ? n : n - 1;
+  const int n = d->n, np = padded_bins(n);
+  P.n = n; P.np = np; P.ld = leading_dim(np); P.pbc = d->pbc ? 1 : 0; P.dim_w = d->pbc ? n : n - 1;
   P.nlag = d->nlag; P.ncosF = d->ncosF; P.ncosD = d->ncosD;
   hp.counts.assign((size_t)d->nlag * np * np, 0);
   for (int l = 0; l < d->nlag; ++l)
@@ -64,7 +64,7 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     s.sc->status = 0;
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
-    out_ll[b] = (method == MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, Pb, &sw)
+    out_ll[b] = (method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, method == MCD_METHOD_SQUARING, Pb, &sw)
                                                 : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     if (status) status[b] = (int)s.sc->status;
     if (sweeps) sweeps[b] = sw;

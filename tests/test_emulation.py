@@ -1,0 +1,98 @@
+"""CPU emulation of the CUDA chain body (same source, HostExec policy) against the
+reference fixtures.  This exercises, without a GPU, everything but the hardware: tile maps,
+the Jacobi schedule, the scaling-and-squaring chain, Metropolis, adaptation, sampling."""
+import numpy as np
+import pytest
+
+from mcdiff_b200 import _capi as K
+from tests.emul import harness as H
+from tests.helpers import replay_case
+
+EIGEN, SQUARING, SQUARING_DFMA = 1, 2, 3
+
+
+@pytest.mark.parametrize("method", [EIGEN, SQUARING, SQUARING_DFMA])
+def test_loglike_and_propagator(gold_ll, method):
+    G = gold_ll
+    pA = H.HostProblem(G["A_counts"], G["A_lags"], True)
+    ll, P, st, _ = H.loglike_batch(pA, G["K_v"][:2], G["K_w"][:2], want_P=True, method=method)
+    assert not st.any()
+    np.testing.assert_allclose(ll, G["K_ll"][:2], rtol=1e-12)
+    assert np.max(np.abs(P[1, 0] - G["K2_P"])) < 1e-13
+    np.testing.assert_allclose(P[1, 0].sum(axis=0), 1.0, atol=1e-12)
+    pP = H.HostProblem(G["P_counts"], G["P_lags"], True)
+    ll, _, st, _ = H.loglike_batch(pP, G["rand_v"][:3], G["rand_wP"][:3], method=method)
+    np.testing.assert_allclose(ll, G["rand_ll_P"][:3], rtol=1e-12)
+    pC = H.HostProblem(G["C_counts"], G["C_lags"], False)
+    ll, P, st, _ = H.loglike_batch(pC, G["C_v"][:2], G["C_w"][:2], want_P=True, method=method)
+    np.testing.assert_allclose(ll, G["C_ll"][:2], rtol=1e-12)
+    assert np.max(np.abs(P[0, 0] - G["C_P0"])) < 1e-12
+
+
+def test_padding_path_odd_size(gold_ll):
+    G = gold_ll
+    pS = H.HostProblem(G["S_counts"], G["S_lags"], True)            # n = 37 -> padded to 40
+    ll, _, st, _ = H.loglike_batch(pS, G["S_v"], G["S_w"], method=EIGEN)
+    assert not st.any()
+    np.testing.assert_allclose(ll, G["S_ll"], rtol=1e-12)
+
+
+def test_nan_input_is_flagged(gold_ll):
+    G = gold_ll
+    pP = H.HostProblem(G["P_counts"], G["P_lags"], True)
+    v = np.zeros((1, 100))
+    v[0, 3] = np.nan
+    for method in (EIGEN, SQUARING):
+        ll, _, st, _ = H.loglike_batch(pP, v, G["P_flat_w"][None, :], method=method)
+        assert np.isnan(ll[0]) and st[0] != 0
+
+
+def _run_case(gold_replay, tag, method, nsteps):
+    case = replay_case(gold_replay, tag)
+    g = case["g"]
+    prob = H.HostProblem(case["counts"], case["lagtimes"], case["pbc"], v_basis=case["v_basis"],
+                         w_basis=case["w_basis"], spring_k=case["k"], string_vecs=case["svecs"])
+    ch = H.HostChains(prob, 1, g("v0"), g("w0"), g("vc0"), g("wc0"), ll0=float(g("ll0")), dv=case["dv"],
+                      dw=case["dw"], dt0=case["dt0"], temp=case["temp"])
+    mp = K.McParams()
+    mp.num_mc_update = case["nmc_update"]
+    mp.dtemp = case["dtemp"]
+    mp.min_lt = float(np.min(case["lagtimes"]))
+    mp.move_timezero = int(case["move_timezero"])
+    mp.sample_every = 100
+    mp.refresh_every = 16
+    mp.use_tape = 1
+    mp.method = method
+    dec, llt, smp = ch.run(nsteps, mp, g("tape_u"), g("tape_idx"), nsamples_cap=max(1, nsteps // 100))
+    return case, g, ch, dec, llt, smp
+
+
+@pytest.mark.parametrize("tag,method,nsteps", [("cosA", EIGEN, 40), ("cosA", SQUARING, 110), ("binP4", SQUARING_DFMA, 40),
+                                               ("cosP4t0", EIGEN, 40), ("binCut", SQUARING, 110),
+                                               ("springP4", EIGEN, 30)])
+def test_replay_prefix_matches_reference(gold_replay, tag, method, nsteps):
+    case, g, ch, dec, llt, smp = _run_case(gold_replay, tag, method, nsteps)
+    assert np.array_equal(dec[0] >> 2, g("move")[:nsteps])
+    assert np.array_equal(dec[0] & 1, g("accepted")[:nsteps])
+    assert np.array_equal((dec[0] >> 1) & 1, g("accepted_t0")[:nsteps])
+    np.testing.assert_allclose(ch.scal[0, K.S_LL], g("ll_after")[nsteps - 1], rtol=1e-11)
+    assert ch.counters[0, K.C_STATUS] == 0 and ch.counters[0, K.C_STEP] == nsteps
+    if nsteps >= 100:
+        np.testing.assert_allclose(smp[0, 0, 0], g("log_ll")[1], rtol=1e-11)
+        w_ref = g("widths")
+        np.testing.assert_allclose(ch.scal[0, K.S_DV:K.S_DW + 1], w_ref[0, 1:], rtol=1e-13)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10, device code vs the host mirror."""
+    import ctypes as C
+    from mcdiff_b200 import philox
+    out = (C.c_uint * 4)()
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        H.lib().emul_philox(*ctr, *key, out)
+        assert tuple(out) == want
+        assert philox.philox4x32_10(*ctr, *key) == want

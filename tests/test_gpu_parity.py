@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-METHODS = {"eigen": 1, "squaring": 2}
+METHODS = {"eigen": 1, "squaring": 2, "squaring_dfma": 3}
 
 
 def _params(case, nsteps, use_tape=1, seed=0, refresh=64, chain_offset=0, method=0):
@@ -44,7 +44,7 @@ def _problem(engine, case):
                          w_basis=case["w_basis"], spring_k=case["k"], string_vecs=case["svecs"])
 
 
-@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("method", ["eigen", "squaring", "squaring_dfma"])
 def test_known_answers_K1_K4(engine, gold_ll, method):
     """The four archived `initial log-likelihood` values of the reference's example logs."""
     from mcdiff_b200.engine import DeviceProblem
@@ -62,7 +62,7 @@ def test_known_answers_K1_K4(engine, gold_ll, method):
     np.testing.assert_allclose(ll, G["K_archived"], rtol=5e-12)
 
 
-@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("method", ["eigen", "squaring", "squaring_dfma"])
 def test_propagator_matches_expm(engine, gold_ll, method):
     from mcdiff_b200.engine import DeviceProblem
     G = gold_ll
@@ -133,7 +133,7 @@ def test_nan_profile_reports_status(engine, gold_ll):
     assert np.isnan(ll[1]) and st[1] != 0
 
 
-@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("method", ["eigen", "squaring", "squaring_dfma"])
 @pytest.mark.parametrize("tag", REPLAY_TAGS)
 def test_replay_against_reference_trajectories(engine, gold_replay, tag, method):
     """Tape-driven MC: decisions bit-exact vs the UNMODIFIED reference run on the same tape
@@ -141,7 +141,7 @@ def test_replay_against_reference_trajectories(engine, gold_replay, tag, method)
     from mcdiff_b200.engine import ChainBatch
     case = replay_case(gold_replay, tag)
     g = case["g"]
-    if method == "squaring" and case["move_timezero"]:
+    if method != "eigen" and case["move_timezero"]:
         pytest.skip("time-offset moves run on the eigen engine")
     prob = _problem(engine, case)
     nch = 3
@@ -181,7 +181,7 @@ def test_replay_against_reference_trajectories(engine, gold_replay, tag, method)
     np.testing.assert_allclose(smp[:, 6 + nv:], g("log_pw")[1:], rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("method", ["eigen", "squaring", "squaring_dfma"])
 def test_philox_run_equals_oracle_replay(engine, gold_ll, method):
     """Production mode (Philox4x32-10 on device): the trajectory of each chain equals the
     oracle replayed on the tape the host mirror of the RNG derives; chains are split over two
@@ -219,7 +219,7 @@ def test_philox_run_equals_oracle_replay(engine, gold_ll, method):
     assert not np.array_equal(dec[0], dec[1])
 
 
-@pytest.mark.parametrize("method", ["eigen", "squaring"])
+@pytest.mark.parametrize("method", ["eigen", "squaring", "squaring_dfma"])
 def test_full_size_properties(engine, method):
     """BASELINE shape (100 bins x 4 lags, 1024 chains): size-independent checks.
     (a) log L of the final state recomputed by the cold batched path equals the running
@@ -306,9 +306,10 @@ def test_engines_agree_step_by_step(engine):
         case = dict(nmc_update=100.0, dtemp=0.0, lagtimes=lags, move_timezero=False)
         dec, llt, _ = ch.run(200, _params(case, 0, use_tape=0, seed=7, method=m), record=True)
         out[name] = (dec.cpu().numpy(), llt.cpu().numpy(), ch.host_state())
-    assert np.array_equal(out["eigen"][0], out["squaring"][0])
-    np.testing.assert_allclose(out["eigen"][1], out["squaring"][1], rtol=1e-12)
-    np.testing.assert_allclose(out["eigen"][2]["v"], out["squaring"][2]["v"], atol=1e-13)
+    for other in ("squaring", "squaring_dfma"):
+        assert np.array_equal(out["eigen"][0], out[other][0])
+        np.testing.assert_allclose(out["eigen"][1], out[other][1], rtol=1e-12)
+        np.testing.assert_allclose(out["eigen"][2]["v"], out[other][2]["v"], atol=1e-13)
 
 
 def test_squaring_rejects_unsupported(engine, gold_ll):
