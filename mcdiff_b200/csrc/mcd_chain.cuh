@@ -14,6 +14,8 @@
 // S[i,i] = R[i,i]; P = Pi^1/2 V exp(t Lambda) V^T Pi^-1/2, one eigendecomposition serves
 // every lag time.
 #pragma once
+#include <cstring>
+
 #include "mcd_exec.cuh"
 
 namespace mcd {
@@ -27,6 +29,8 @@ struct Problem {
   int ncosF, ncosD;
   const double* lagtimes;  // [nlag]
   const int* counts;       // [nlag][np][np]  (padded, counts[l][i][j] = # transitions j -> i)
+  const int* nsym;         // [nlag][np][np]  N_ij + N_ji (i != j), N_ii on the diagonal
+  const double* rvec;      // [np]  sum_lag (column sum - row sum) of the counts: the part of log L linear in v
   const double* v_basis;   // [n][ncosF]      (null when ncosF == 0)
   const double* w_basis;   // [dim_w][ncosD]  (null when ncosD == 0)
   const double* svecs;     // [dim_w][dim_w]  Laplacian eigenvectors (null when spring_k <= 0)
@@ -114,7 +118,7 @@ MCD_HD double u53(uint32_t hi, uint32_t lo) {
 // shared-memory carve-up
 // ---------------------------------------------------------------------------------------
 struct Scalars {
-  double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring;
+  double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring, gmin, lin;
   long long naccv, naccw, nacct0, naccv_upd, naccw_upd, step, status, sweeps;
   int move, idx, accepted, accepted_t0, nsamp, basis_is_trial, do_t0, mma_tasks;
 };
@@ -122,7 +126,8 @@ struct Scalars {
 struct Smem {
   double* XT;
   double* B2;
-  double *a, *b, *ea, *eb, *lam, *el;
+  double *a, *b, *ea, *eb, *hv, *lam, *el;
+  double *lgc, *lgl;   // log tables: c_k ~ 1/(1+(k+1/2)/128), -log(c_k)
   double *v, *w, *vt, *wt;
   double *vc, *wc, *ct;
   double *lag, *lag_try;
@@ -138,7 +143,7 @@ struct Smem {
 };
 
 MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
-  size_t d = (size_t)np * 10 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
+  size_t d = (size_t)np * 11 + 256 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
   size_t nb = np / 4, h = np / 2;
   size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + 16 * (kThreads / 32) + sizeof(Scalars) + 64;
   return (bytes + 15) & ~(size_t)15;
@@ -156,6 +161,9 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
   s.b = d; d += np;
   s.ea = d; d += np;
   s.eb = d; d += np;
+  s.hv = d; d += np;
+  s.lgc = d; d += 128;
+  s.lgl = d; d += 128;
   s.lam = d; d += np;
   s.el = d; d += np;
   s.v = d; d += np;
@@ -199,6 +207,13 @@ struct Chain {
   // (4 x 8 tiles) so that the 32 lanes of a warp share operand rows (shared-memory
   // broadcast).  Jacobi block list: all pair-slot pairs ka < kb.
   MCD_HD void build_tables() {
+    ex.par([&](int tid) {
+      if (tid < 128) {
+        const double c = 1.0 / (1.0 + ((double)tid + 0.5) / 128.0);
+        s.lgc[tid] = c;
+        s.lgl[tid] = -log(c);
+      }
+    });
     ex.single([&]() {
       const int nb = P.np / 4;
       int t = 0;
@@ -292,8 +307,9 @@ struct Chain {
           s.b[i] = (i < dim_w) ? exp(w[i]) : 0.0;
           s.ea[i] = exp(-0.5 * vi);
           s.eb[i] = exp(0.5 * vi);
+          s.hv[i] = 0.5 * vi;
         } else {
-          s.a[i] = 0.0; s.b[i] = 0.0; s.ea[i] = 0.0; s.eb[i] = 0.0;
+          s.a[i] = 0.0; s.b[i] = 0.0; s.ea[i] = 0.0; s.eb[i] = 0.0; s.hv[i] = 0.0;
         }
       }
     });
@@ -302,7 +318,28 @@ struct Chain {
       for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, fabs(s.a[i]));
       return m;
     });
-    ex.single([&]() { s.sc->scale = sc; });
+    // g >= gmin guarantees P_ij = exp(-v_i/2) g exp(v_j/2) >= clip for every pair (i, j)
+    const double hmax = ex.max([&](int tid) {
+      double m = -1.0e308;
+      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, s.hv[i]);
+      return m;
+    });
+    const double hmin = -ex.max([&](int tid) {
+      double m = -1.0e308;
+      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, -s.hv[i]);
+      return m;
+    });
+    // sum_ij N_ij (v_j - v_i)/2 = sum_k (v_k/2) (colsum_k - rowsum_k)
+    const double lin = P.rvec ? ex.sum([&](int tid) {
+      double acc = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) acc += s.hv[i] * P.rvec[i];
+      return acc;
+    }) : 0.0;
+    ex.single([&]() {
+      s.sc->scale = sc;
+      s.sc->gmin = P.clip * exp(hmax - hmin);
+      s.sc->lin = lin;
+    });
   }
 
   // Cold start: XT = identity, B2 = dense S.
@@ -401,6 +438,7 @@ struct Chain {
     const double skip = 1.0e-18 * scale;
     int sweeps = 0;
     for (;;) {
+      if (!(scale < 1.0e300)) { sweeps = -1; break; }  // non-finite profile (exp overflow / NaN)
       double off = ex.max([&](int tid) {
         double mx = 0.0;
         for (int e = tid; e < np * np; e += Exec::nthr()) {
@@ -502,44 +540,83 @@ struct Chain {
     }
   }
 
-  // Likelihood contribution of one 4x4 tile of the symmetric kernel G (and of its mirror):
-  // P_ij = exp(-v_i/2) G_ij exp(+v_j/2);  sum N_ij log(max(P_ij, clip))   (lib/utils.py:317-321)
-  MCD_HD double tile_loglike(const double (&c)[4][4], int ib, int jb, const i4 (&nij)[4], const i4 (&nji)[4],
-                             double* Pl) {
+  // Natural logarithm for positive, finite, normal arguments (the likelihood epilogue only calls it
+  // with g >= gmin >= clip > 0).  Branch-free: g = 2^e m, m in [1,2); table of 128 reciprocals c_k
+  // brings r = m c_k - 1 into |r| < 2^-8; log g = e ln2 - log c_k + (r - r^2/2 + ... - r^6/6).
+  // Absolute error < 4e-16 + 1.6e-16 |log g| (checked against libm in tests/test_emulation.py).
+  MCD_HD double fast_log(double g) const {
+#if defined(__CUDA_ARCH__)
+    const long long bits = __double_as_longlong(g);
+#else
+    long long bits;
+    std::memcpy(&bits, &g, 8);
+#endif
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    const int k = (int)((bits >> 45) & 127);
+    const long long mb = (bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+#if defined(__CUDA_ARCH__)
+    const double m = __longlong_as_double(mb);
+#else
+    double m;
+    std::memcpy(&m, &mb, 8);
+#endif
+    const double r = fma(m, s.lgc[k], -1.0);
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r * r, p, r);
+    return fma((double)e, 0.6931471805599453094, s.lgl[k] + p);
+  }
+
+  // Likelihood terms of the unordered pair {i, j} of the symmetric kernel entry g = G_ij:
+  //   N_ij log P_ij + N_ji log P_ji,   P_ij = exp(-v_i/2) g exp(+v_j/2),  P_ji = exp(-v_j/2) g exp(+v_i/2)
+  // = (N_ij + N_ji) log g + (N_ij - N_ji)(v_j - v_i)/2.
+  // The second part is linear in v and summed once per evaluation from the precomputed row/column
+  // sums (build_S: sc->lin), so the pair costs ONE logarithm weighted by nsym = N_ij + N_ji.
+  // Entries that fall below the clip of lib/utils.py:317 take the exact per-entry route.
+  MCD_HD double pair_term(double g, int ns, int i, int j, const int* cnt) const {
+    if (ns == 0) return 0.0;
+    if (g >= s.sc->gmin) return (double)ns * fast_log(g);
+    const int np = P.np;
+    const double clip = P.clip;
+    if (i == j) return (double)ns * log(fmax(g, clip));
+    const int nij = cnt[(size_t)i * np + j], nji = cnt[(size_t)j * np + i];
+    const double pij = s.ea[i] * g * s.eb[j], pji = s.ea[j] * g * s.eb[i];
+    double part = -(double)(nij - nji) * (s.hv[j] - s.hv[i]);   // undo this pair's share of sc->lin
+    if (nij != 0) part += (double)nij * log(fmax(pij, clip));
+    if (nji != 0) part += (double)nji * log(fmax(pji, clip));
+    return part;
+  }
+
+  // Likelihood contribution of one 4x4 tile of the symmetric kernel G (upper triangle of the tile
+  // grid; inside diagonal tiles only i <= j).
+  MCD_HD double tile_loglike(const double (&c)[4][4], int ib, int jb, const i4 (&ns)[4], const int* cnt, double* Pl) {
     const int n = P.n;
     const int i0 = ib * 4, j0 = jb * 4;
-    const double clip = P.clip;
     double part = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int i = i0 + a;
-      const int nrow[4] = {nij[a].x, nij[a].y, nij[a].z, nij[a].w};
-      const double eai = s.ea[i], ebi = s.eb[i];
+      const int nrow[4] = {ns[a].x, ns[a].y, ns[a].z, ns[a].w};
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int j = j0 + b;
-        const double g = c[a][b];
-        const double pij = eai * g * s.eb[j];
-        if (nrow[b] != 0) part += (double)nrow[b] * log(fmax(pij, clip));
-        if (Pl && i < n && j < n) Pl[(size_t)i * n + j] = pij;
-        if (ib != jb) {
-          const int nm = (a == 0) ? nji[b].x : (a == 1) ? nji[b].y : (a == 2) ? nji[b].z : nji[b].w;
-          const double pji = s.ea[j] * g * ebi;
-          if (nm != 0) part += (double)nm * log(fmax(pji, clip));
-          if (Pl && i < n && j < n) Pl[(size_t)j * n + i] = pji;
+        if (ib == jb && j < i) continue;
+        part += pair_term(c[a][b], nrow[b], i, j, cnt);
+        if (Pl && i < n && j < n) {
+          Pl[(size_t)i * n + j] = s.ea[i] * c[a][b] * s.eb[j];
+          Pl[(size_t)j * n + i] = s.ea[j] * c[a][b] * s.eb[i];
         }
       }
     }
     return part;
   }
 
-  MCD_HD void load_counts(const int* cnt, int ib, int jb, i4 (&nij)[4], i4 (&nji)[4]) {
+  MCD_HD void load_counts(const int* nsym, int ib, int jb, i4 (&ns)[4]) {
     const int np = P.np;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      nij[a] = ld4i(cnt + (size_t)(ib * 4 + a) * np + jb * 4);
-      nji[a] = ld4i(cnt + (size_t)(jb * 4 + a) * np + ib * 4);
-    }
+    for (int a = 0; a < 4; ++a) ns[a] = ld4i(nsym + (size_t)(ib * 4 + a) * np + jb * 4);
   }
 
   // log L = sum_lag sum_ij N[lag,i,j] log(max(P_ij, clip)),  P = Pi^1/2 XT^T e^{t lam} XT Pi^-1/2
@@ -563,21 +640,22 @@ struct Chain {
         }
       });
       const int* cnt = P.counts + (size_t)l * np * np;
+      const int* nsy = P.nsym + (size_t)l * np * np;
       double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
       ex.par([&](int tid) {
         double part = 0.0;
         for (int tt = tid; tt < s.ntiles; tt += Exec::nthr()) {
           const int ib = s.tiles[2 * tt], jb = s.tiles[2 * tt + 1];
-          i4 nij[4], nji[4];
-          load_counts(cnt, ib, jb, nij, nji);  // before the k loop: hides the L2 latency
+          i4 ns[4];
+          load_counts(nsy, ib, jb, ns);  // before the k loop: hides the L2 latency
           double c[4][4];
           tile_product(s.XT, s.B2, ib, jb, c);
-          part += tile_loglike(c, ib, jb, nij, nji, Pl);
+          part += tile_loglike(c, ib, jb, ns, cnt, Pl);
         }
         ex.regs(tid)[0] += part;
       });
     }
-    return ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+    return s.sc->lin + ex.sum([&](int tid) { return ex.regs(tid)[0]; });
   }
 
   // ------------------------------------------------------------------------------------
@@ -610,25 +688,27 @@ struct Chain {
   // D <- X Y (symmetric, commuting operands; D may alias X or Y).  If cnt != nullptr the
   // product is the kernel of a lag time and its likelihood terms are added to regs[0]... the
   // partial sum lives in `part_acc` (per-thread, caller-owned).
-  MCD_HD void sym_product(const double* X, const double* Y, double* D, const int* cnt, double* Pl, bool store,
-                          double* part_acc_slot) {
-    (void)part_acc_slot;
+  // store: 0 = result not kept, 1 = D is a third buffer (direct store, no extra barrier phase),
+  //        2 = D aliases an operand (register-staged, written after the barrier)
+  MCD_HD void sym_product(const double* X, const double* Y, double* D, const int* cnt, const int* nsy, double* Pl,
+                          int store) {
     ex.par([&](int tid) {
       double* r = ex.regs(tid);
       if (tid < s.ntiles) {
         const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
-        i4 nij[4], nji[4];
-        if (cnt) load_counts(cnt, ib, jb, nij, nji);
+        i4 ns[4];
+        if (cnt) load_counts(nsy, ib, jb, ns);
         double c[4][4];
         tile_product(X, Y, ib, jb, c);
-        if (cnt) s.part[tid] += tile_loglike(c, ib, jb, nij, nji, Pl);
+        if (cnt) s.part[tid] += tile_loglike(c, ib, jb, ns, cnt, Pl);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) r[a * 4 + b] = c[a][b];
+        if (store == 1) store_tile_mirror(D, ib, jb, r);
       }
     });
-    if (store) {
+    if (store == 2) {
       ex.par([&](int tid) {
         if (tid < s.ntiles) store_tile_mirror(D, s.tiles[2 * tid], s.tiles[2 * tid + 1], ex.regs(tid));
       });
@@ -673,7 +753,27 @@ struct Chain {
   }
 #endif
 
-  MCD_HD void dmma_product(const double* X, const double* Y, double* D, const int* cnt, double* Pl, bool store) {
+  MCD_HD void dmma_store(double* D, int warp, int lane, int ntasks, const double* r) {
+    const int ld = P.ld;
+    const unsigned char* wt = s.wtab + 16 * warp;
+    const int nt = (warp < ntasks) ? wt[0] : 0, na = wt[1];
+    const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+    for (int t = 0; t < kTilesPerWarp; ++t) {
+      if (t < nt) {
+        const int ib = (t < na) ? wt[2] : wt[3], jb = wt[4 + t];
+        const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+        st2(D + i * ld + j, r[2 * t], r[2 * t + 1]);
+        if (ib != jb) {
+          D[j * ld + i] = r[2 * t];
+          D[(j + 1) * ld + i] = r[2 * t + 1];
+        }
+      }
+    }
+  }
+
+  MCD_HD void dmma_product(const double* X, const double* Y, double* D, const int* cnt, const int* nsy, double* Pl,
+                           int store) {
     const int n = P.n, np = P.np, ld = P.ld;
     const int ntasks = s.sc->mma_tasks;
     ex.par([&](int tid) {
@@ -686,6 +786,17 @@ struct Chain {
 #pragma unroll
       for (int t = 0; t < kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
       const int fr = lane >> 2, fk = lane & 3;   // fragment row (m or n) and k index of this lane
+      // symmetric counts of the two entries per tile this lane owns, fetched before the k loop
+      int nsv[kTilesPerWarp][2];
+      if (cnt) {
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
+          const int* q = nsy + (size_t)(ib * 8 + fr) * np + jb * 8 + 2 * fk;
+          nsv[t][0] = (t < nt) ? q[0] : 0;
+          nsv[t][1] = (t < nt) ? q[1] : 0;
+        }
+      }
       if (active) {
 #if defined(__CUDA_ARCH__)
         int offB[kTilesPerWarp];
@@ -717,29 +828,22 @@ struct Chain {
         }
 #endif
       }
-      // likelihood epilogue: this lane owns G[i][j], G[i][j+1] (and their mirrors)
+      // likelihood epilogue: this lane owns G[i][j], G[i][j+1]; inside diagonal tiles only i <= j
       if (cnt && nt > 0) {
         double part = 0.0;
-        const double clip = P.clip;
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
           if (t < nt) {
             const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
             const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
-            const double eai = s.ea[i], ebi = s.eb[i];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int jj = j + e;
-              const double g = c[t][e];
-              const int nij = cnt[(size_t)i * np + jj];
-              const double pij = eai * g * s.eb[jj];
-              if (nij != 0) part += (double)nij * log(fmax(pij, clip));
-              if (Pl && i < n && jj < n) Pl[(size_t)i * n + jj] = pij;
-              if (ib != jb) {
-                const int nji = cnt[(size_t)jj * np + i];
-                const double pji = s.ea[jj] * g * ebi;
-                if (nji != 0) part += (double)nji * log(fmax(pji, clip));
-                if (Pl && i < n && jj < n) Pl[(size_t)jj * n + i] = pji;
+              if (ib == jb && jj < i) continue;
+              part += pair_term(c[t][e], nsv[t][e], i, jj, cnt);
+              if (Pl && i < n && jj < n) {
+                Pl[(size_t)i * n + jj] = s.ea[i] * c[t][e] * s.eb[jj];
+                Pl[(size_t)jj * n + i] = s.ea[jj] * c[t][e] * s.eb[i];
               }
             }
           }
@@ -749,27 +853,10 @@ struct Chain {
       double* r = ex.regs(tid);
 #pragma unroll
       for (int t = 0; t < kTilesPerWarp; ++t) { r[2 * t] = c[t][0]; r[2 * t + 1] = c[t][1]; }
+      if (store == 1) dmma_store(D, warp, lane, ntasks, r);
     });
-    if (store) {
-      ex.par([&](int tid) {
-        const int warp = tid >> 5, lane = tid & 31;
-        const unsigned char* wt = s.wtab + 16 * warp;
-        const int nt = (warp < ntasks) ? wt[0] : 0, na = wt[1];
-        const int fr = lane >> 2, fk = lane & 3;
-        const double* r = ex.regs(tid);
-#pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) {
-          if (t < nt) {
-            const int ib = (t < na) ? wt[2] : wt[3], jb = wt[4 + t];
-            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
-            st2(D + i * ld + j, r[2 * t], r[2 * t + 1]);
-            if (ib != jb) {
-              D[j * ld + i] = r[2 * t];
-              D[(j + 1) * ld + i] = r[2 * t + 1];
-            }
-          }
-        }
-      });
+    if (store == 2) {
+      ex.par([&](int tid) { dmma_store(D, tid >> 5, tid & 31, ntasks, ex.regs(tid)); });
     }
   }
 
@@ -799,72 +886,107 @@ struct Chain {
     int nsq = 0;
     for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
     const double h = ldexp(t0, -nsq);
-    const int m = taylor_m > 0 ? taylor_m : 20;
+    // Taylor order.  T_m(x) = e^x (1 - x^(m+1)/(m+1)! ...) per eigenmode, and the error is amplified
+    // 2^s times by the squarings -- but only modes with t0 |lambda| <= 45 survive in G(t0) at all
+    // (e^-45 = 3e-20), i.e. |x| <= x* = min(1, 45 / 2^s).  Smallest m with 2^s x*^(m+1)/(m+1)! <= 1e-17.
+    int m = taylor_m;
+    if (m <= 0) {
+      const double two_s = ldexp(1.0, nsq);
+      const double xs = fmin(1.0, 45.0 / two_s);
+      double term = two_s * xs;   // 2^s x^(k) / k!  for k = 1
+      m = 1;
+      while (m < 24 && !(term * xs / (double)(m + 1) <= 1.0e-17)) {
+        term = term * xs / (double)(m + 1);
+        ++m;
+      }
+      if (m < 6) m = 6;
+    }
     double* A = s.XT;
     double* B = s.B2;
-    // ---- T_m(hS) by Horner, band-limited: H <- I + (hS H)/k, k = m..1, ping-pong A/B ----
+    // ---- T_m(hS) by Horner:  H <- I + (hS H)/k, k = m..1, ping-pong ----
+    // H is banded (half-width t after t steps): only the band is touched.  A row is shared by
+    // `tpr` consecutive threads that walk its band with stride tpr (contiguous columns across
+    // lanes); the three coefficients of the row stay in registers for the whole pass.
     ex.par([&](int tid) {
-      for (int e = tid; e < np * ld; e += Exec::nthr()) { A[e] = 0.0; B[e] = 0.0; }
       s.part[tid] = 0.0;
+      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(A + e, 0.0, 0.0); st2(B + e, 0.0, 0.0); }
     });
-    double* src = (m & 1) ? B : A;   // after m steps the result sits in A
-    double* dst = (m & 1) ? A : B;
+    double* src = A;
+    double* dst = B;
     ex.par([&](int tid) {
       for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
     });
+    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
+    const int rows_per_pass = Exec::nthr() / tpr;
     for (int t = 1; t <= m; ++t) {
       const double f = h / (double)(m - t + 1);
       const int width = (2 * t + 1 < n) ? 2 * t + 1 : n;
       const bool full = (width == n);
       ex.par([&](int tid) {
-        for (int e = tid; e < n * width; e += Exec::nthr()) {
-          const int i = e / width, dd = e - i * width;
-          int j;
-          if (full) j = dd;
-          else {
-            j = i - t + dd;
-            if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
-            else if (j < 0 || j >= n) continue;
-          }
+        const int r = tid % tpr;
+        for (int i = tid / tpr; i < n; i += rows_per_pass) {
           const int im = (i == 0) ? n - 1 : i - 1;
           const int ip = (i == n - 1) ? 0 : i + 1;
-          const double val = s.a[i] * src[i * ld + j] + s.b[im] * src[im * ld + j] + s.b[i] * src[ip * ld + j];
-          dst[i * ld + j] = ((i == j) ? 1.0 : 0.0) + f * val;
+          const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.b[i];
+          const double* s0 = src + i * ld;
+          const double* sm = src + im * ld;
+          const double* sp = src + ip * ld;
+          double* d0 = dst + i * ld;
+          for (int dd = r; dd < width; dd += tpr) {
+            int j;
+            if (full) j = dd;
+            else {
+              j = i - t + dd;
+              if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
+              else if (j < 0 || j >= n) continue;
+            }
+            d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
+          }
         }
       });
       double* tmp = src; src = dst; dst = tmp;
     }
-    // ---- G(t0) = T^(2^s) ----
+    // ---- G(t0) = T^(2^s): out-of-place squarings src -> dst (direct stores), the last one carries
+    //      the likelihood epilogue of lag 0 ----
+    double* G = src;      // current power
+    double* O = dst;      // the other buffer
     for (int q = 0; q < nsq; ++q) {
-      if (use_mma) dmma_product(A, A, A, nullptr, nullptr, true);
-      else sym_product(A, A, A, nullptr, nullptr, true, nullptr);
+      const bool last = (q + 1 == nsq);
+      const int* cnt = last ? P.counts : nullptr;
+      const int* nsy = last ? P.nsym : nullptr;
+      if (use_mma) dmma_product(G, G, O, cnt, nsy, last ? Pout : nullptr, 1);
+      else sym_product(G, G, O, cnt, nsy, last ? Pout : nullptr, 1);
+      double* tmp = G; G = O; O = tmp;
     }
-    // ---- likelihood of lag 0 straight from A, then the progression G((l+1) t0) = G(l t0) G(t0) ----
-    {
+    if (nsq == 0) {   // lag 0 straight from the Taylor polynomial
       const int* cnt = P.counts;
+      const int* nsy = P.nsym;
       ex.par([&](int tid) {
         if (tid < s.ntiles) {
           const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
-          i4 nij[4], nji[4];
-          load_counts(cnt, ib, jb, nij, nji);
+          i4 ns[4];
+          load_counts(nsy, ib, jb, ns);
           double c[4][4];
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
-            const d2 g01 = ld2(A + (ib * 4 + a) * ld + jb * 4), g23 = ld2(A + (ib * 4 + a) * ld + jb * 4 + 2);
+            const d2 g01 = ld2(G + (ib * 4 + a) * ld + jb * 4), g23 = ld2(G + (ib * 4 + a) * ld + jb * 4 + 2);
             c[a][0] = g01.x; c[a][1] = g01.y; c[a][2] = g23.x; c[a][3] = g23.y;
           }
-          s.part[tid] += tile_loglike(c, ib, jb, nij, nji, Pout);
+          s.part[tid] += tile_loglike(c, ib, jb, ns, cnt, Pout);
         }
       });
     }
+    // ---- progression G((l+1) t0) = G(l t0) G(t0): first product out of place, then in place ----
     for (int l = 1; l < P.nlag; ++l) {
       const int* cnt = P.counts + (size_t)l * np * np;
+      const int* nsy = P.nsym + (size_t)l * np * np;
       double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
-      if (use_mma) dmma_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag);
-      else sym_product(l == 1 ? A : B, A, B, cnt, Pl, l + 1 < P.nlag, nullptr);
+      const int store = (l + 1 < P.nlag) ? (l == 1 ? 1 : 2) : 0;
+      if (use_mma) dmma_product(l == 1 ? G : O, G, O, cnt, nsy, Pl, store);
+      else sym_product(l == 1 ? G : O, G, O, cnt, nsy, Pl, store);
     }
     if (squarings_out) *squarings_out = nsq;
-    return ex.sum([&](int tid) { return s.part[tid]; });
+    return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
   }
 
   // Full likelihood of the profile (v, w) at lag times lagt.

@@ -108,6 +108,29 @@ __global__ void mcd_pack_counts_kernel(const int* __restrict__ src, int* __restr
   }
 }
 
+// nsym[l][i][j] = N_ij + N_ji (i != j), N_ii on the diagonal   (padded layout)
+__global__ void mcd_sym_counts_kernel(const int* __restrict__ cnt, int* __restrict__ nsym, int L, int np) {
+  const size_t total = (size_t)L * np * np;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % np);
+    const int i = (int)((e / np) % np);
+    const size_t base = (e / ((size_t)np * np)) * (size_t)np * np;
+    nsym[e] = (i == j) ? cnt[e] : cnt[base + (size_t)i * np + j] + cnt[base + (size_t)j * np + i];
+  }
+}
+
+// rvec[k] = sum_l (sum_i N[l][i][k] - sum_j N[l][k][j])
+__global__ void mcd_rvec_kernel(const int* __restrict__ cnt, double* __restrict__ rvec, int L, int np) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  long long acc = 0;
+  for (int l = 0; l < L; ++l) {
+    const int* c = cnt + (size_t)l * np * np;
+    for (int i = 0; i < np; ++i) acc += (long long)c[(size_t)i * np + k] - (long long)c[(size_t)k * np + i];
+  }
+  rvec[k] = (double)acc;
+}
+
 // dense DFMA throughput probe: 8 independent chains per thread
 __global__ void __launch_bounds__(256) mcd_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -188,22 +211,27 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   p->h = h;
   const size_t b_lag = align256((size_t)d->nlag * 8);
   const size_t b_cnt = align256((size_t)d->nlag * np * np * 4);
+  const size_t b_rv = align256((size_t)np * 8);
   const size_t b_vb = align256((size_t)n * d->ncosF * 8);
   const size_t b_wb = align256((size_t)dim_w * d->ncosD * 8);
   const size_t b_sv = d->spring_k > 0.0 ? align256((size_t)dim_w * dim_w * 8) : 0;
   unsigned char* blob = nullptr;
-  cudaError_t e = cudaMalloc(&blob, b_lag + b_cnt + b_vb + b_wb + b_sv + 256);
+  cudaError_t e = cudaMalloc(&blob, b_lag + 2 * b_cnt + b_rv + b_vb + b_wb + b_sv + 256);
   if (e != cudaSuccess) { delete p; return (int)e; }
   p->blob = blob;
   unsigned char* q = blob;
   double* lag = (double*)q; q += b_lag;
   int* cnt = (int*)q; q += b_cnt;
+  int* nsym = (int*)q; q += b_cnt;
+  double* rvec = (double*)q; q += b_rv;
   double* vb = (double*)q; q += b_vb;
   double* wb = (double*)q; q += b_wb;
   double* sv = (double*)q;
   cudaMemcpyAsync(lag, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToDevice, st);
   mcd_pack_counts_kernel<<<h->sm_count, 256, 0, st>>>(d->counts, cnt, d->nlag, n, np);
-  h->launches++;
+  mcd_sym_counts_kernel<<<h->sm_count, 256, 0, st>>>(cnt, nsym, d->nlag, np);
+  mcd_rvec_kernel<<<(np + 127) / 128, 128, 0, st>>>(cnt, rvec, d->nlag, np);
+  h->launches += 3;
   if (d->ncosF > 0) cudaMemcpyAsync(vb, d->v_basis, (size_t)n * d->ncosF * 8, cudaMemcpyDeviceToDevice, st);
   if (d->ncosD > 0) cudaMemcpyAsync(wb, d->w_basis, (size_t)dim_w * d->ncosD * 8, cudaMemcpyDeviceToDevice, st);
   if (d->spring_k > 0.0)
@@ -214,7 +242,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   Problem& P = p->P;
   P.n = n; P.np = np; P.ld = ld; P.dim_w = dim_w; P.pbc = d->pbc ? 1 : 0; P.nlag = d->nlag;
   P.ncosF = d->ncosF; P.ncosD = d->ncosD;
-  P.lagtimes = lag; P.counts = cnt;
+  P.lagtimes = lag; P.counts = cnt; P.nsym = nsym; P.rvec = rvec;
   P.v_basis = d->ncosF > 0 ? vb : nullptr;
   P.w_basis = d->ncosD > 0 ? wb : nullptr;
   P.svecs = d->spring_k > 0.0 ? sv : nullptr;

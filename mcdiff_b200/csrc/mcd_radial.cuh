@@ -40,7 +40,8 @@ mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, dou
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Problem P;
   P.n = R.n; P.np = R.np; P.ld = R.ld; P.dim_w = R.dim_w; P.pbc = R.pbc; P.nlag = R.nlag;
-  P.ncosF = 0; P.ncosD = 0; P.lagtimes = R.lagtimes; P.counts = nullptr; P.v_basis = nullptr;
+  P.ncosF = 0; P.ncosD = 0; P.lagtimes = R.lagtimes; P.counts = nullptr; P.nsym = nullptr; P.rvec = nullptr;
+  P.v_basis = nullptr;
   P.w_basis = nullptr; P.svecs = nullptr; P.spring_k = 0.0; P.clip = R.clip;
   const size_t mat_bytes = smem_matrix_bytes(R.np, R.ld);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);

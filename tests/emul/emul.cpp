@@ -19,7 +19,8 @@ using namespace mcd;
 namespace {
 struct HostProblem {
   Problem P;
-  std::vector<int> counts;
+  std::vector<int> counts, nsym;
+  std::vector<double> rvec;
 };
 
 void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
@@ -31,8 +32,21 @@ void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
   for (int l = 0; l < d->nlag; ++l)
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) hp.counts[((size_t)l * np + i) * np + j] = d->counts[((size_t)l * n + i) * n + j];
+  hp.nsym.assign((size_t)d->nlag * np * np, 0);
+  hp.rvec.assign(np, 0.0);
+  for (int l = 0; l < d->nlag; ++l) {
+    const int* c = hp.counts.data() + (size_t)l * np * np;
+    for (int i = 0; i < np; ++i)
+      for (int j = 0; j < np; ++j) {
+        hp.nsym[((size_t)l * np + i) * np + j] = (i == j) ? c[i * np + j] : c[i * np + j] + c[j * np + i];
+        hp.rvec[j] += c[i * np + j];
+        hp.rvec[i] -= c[i * np + j];
+      }
+  }
   P.lagtimes = d->lagtimes;
   P.counts = hp.counts.data();
+  P.nsym = hp.nsym.data();
+  P.rvec = hp.rvec.data();
   P.v_basis = d->v_basis;
   P.w_basis = d->w_basis;
   P.svecs = d->string_vecs;
@@ -93,6 +107,21 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
     ch.run(mp, cio, c, nsteps);
   }
   return 0;
+}
+
+// fast_log of the likelihood epilogue, for the accuracy test
+void emul_fast_log(const double* x, double* y, int n) {
+  Problem P;
+  std::memset(&P, 0, sizeof(P));
+  P.n = 8; P.np = 8; P.ld = 12; P.nlag = 1; P.dim_w = 8; P.pbc = 1;
+  std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
+  std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
+  std::vector<double> store((size_t)kThreads * kMaxRegs);
+  Smem s = carve(P, mat.data(), vec.data());
+  HostExec ex(store.data());
+  Chain<HostExec> ch(ex, P, s);
+  ch.build_tables();
+  for (int i = 0; i < n; ++i) y[i] = ch.fast_log(x[i]);
 }
 
 void emul_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {

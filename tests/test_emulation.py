@@ -96,3 +96,15 @@ def test_philox_known_answers():
         H.lib().emul_philox(*ctr, *key, out)
         assert tuple(out) == want
         assert philox.philox4x32_10(*ctr, *key) == want
+
+
+def test_fast_log_accuracy():
+    """The branch-free logarithm of the likelihood epilogue vs libm on its whole input range."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-10.5, 1.5, 200000), 1 + rng.uniform(-1e-3, 1e-3, 10000),
+                        np.array([1.0, 0.5, 2.0, 1e-10, 1 - 2.0 ** -53, 1 + 2.0 ** -52])])
+    y = np.zeros_like(x)
+    H.lib().emul_fast_log(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_int(len(x)))
+    ref = np.log(x)
+    assert np.all(np.abs(y - ref) <= 4e-16 + 1.6e-16 * np.abs(ref))

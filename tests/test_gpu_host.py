@@ -1,0 +1,117 @@
+"""End to end through the reference-facing host API (find_parameters / MCState) on the GPU:
+output files in the reference's formats, restart through --initf, chain 0 equal to the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _files(tmp, G, key="P"):
+    from mcdiff_b200.transitions import write_Tmat_square
+    files = []
+    for l, lag in enumerate(G[key + "_lags"]):
+        fn = os.path.join(tmp, "transitions.nbins100.%d.pbc.dat" % int(lag))
+        write_Tmat_square(G[key + "_counts"][l], fn, float(lag), "pbc", edges=G[key + "_edges"], dt=1.0, dn=int(lag))
+        files.append(fn)
+    return files
+
+
+def test_find_parameters_outputs_and_restart(engine, gold_ll, tmp_path, capsys):
+    from mcdiff_b200 import outreading as outr
+    from mcdiff_b200 import philox
+    from mcdiff_b200.log import load_logger
+    from mcdiff_b200.mc import find_parameters
+    from oracle import mcdiff_oracle as O
+    G = gold_ll
+    tmp = str(tmp_path)
+    files = _files(tmp, G)
+    out = os.path.join(tmp, "out.nbins100.pbc.dat")
+    nmc, nch, seed = 300, 8, 3
+    MC, logger = find_parameters(files, True, "CosinusModel", 0.05, 0.05, 0.5, 1.0, 0.1, 1.0, 1.0, nmc, 100.0, seed,
+                                 out, 10, 6, 0, False, None, -1, -1, False, None, nchains=nch)
+    text = capsys.readouterr().out
+    ll_first = float([l for l in text.splitlines() if l.startswith("initial log-likelihood:")][0].split()[-1])
+    assert ll_first == pytest.approx(float(G["P_flat_ll"]), rel=1e-9)
+    for suffix in ("", ".pic", ".pic.ave.dat", ".chains.npz"):
+        assert os.path.exists(out + suffix), suffix
+
+    # chain 0 == oracle replay on the tape the device Philox stream produces
+    n = 100
+    vb, wb = O.cos_basis_center(n, 10), O.cos_basis_border(n, n, 6)
+    wc0 = np.zeros(6)
+    wc0[0] = G["P_flat_w"][0]
+    cfg = O.ChainConfig(G["P_counts"], G["P_lags"], True, v_basis=vb, w_basis=wb, dv=0.05, dw=0.05, temp=1.0,
+                        temp_end=1.0, nmc=nmc, num_mc_update=100.0)
+    tu, ti = philox.chain_tape(seed, 0, 0, nmc, n, n, 10, 6)
+    ref = O.replay(cfg, np.zeros(n), wb @ wc0, tu, ti, v_coeff0=np.zeros(10), w_coeff0=wc0)
+    assert (MC.naccv, MC.naccw) == (ref["naccv"], ref["naccw"])
+    np.testing.assert_allclose(MC.log_like, ref["ll"], rtol=1e-9)
+    np.testing.assert_allclose(MC.model.v_coeff, ref["v_coeff"], atol=1e-13)
+    np.testing.assert_allclose([MC.dv, MC.dw], [ref["dv"], ref["dw"]], rtol=1e-13)
+
+    # `.dat` = chain 0 in the reference's text format
+    np.testing.assert_allclose(outr.read_Fcoeffs(out, final=True), ref["v_coeff"], rtol=1e-8, atol=1e-12)
+    F, D, edges = outr.read_F_D_edges(out)
+    np.testing.assert_allclose(F, ref["v"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(D, np.exp(ref["w"] + MC.model.wunit), rtol=1e-8)
+    dv, dw = outr.read_dv_dw(out, final=True)
+    assert dv == pytest.approx(ref["dv"]) and dw == pytest.approx(ref["dw"])
+
+    # `.pic` = pooled Logger: nch * (nmc/100 + 1) rows, chain 0 rows equal the oracle's samples
+    lg = load_logger(out + ".pic")
+    assert lg.nf == nch * 4 and lg.v_coeff.shape == (nch * 4, 10)
+    np.testing.assert_allclose(lg.log_like[:4], ref["samples"][:, 0], rtol=1e-9)
+    np.testing.assert_allclose(lg.v_coeff[:4], ref["samples"][:, 6:16], atol=1e-13)
+    Fa, Da, ea = outr.read_F_D_edges(out + ".pic.ave.dat")
+    np.testing.assert_allclose(Fa, (lg.v_coeff @ vb.T).mean(axis=0), rtol=1e-7, atol=1e-9)
+    ch = np.load(out + ".chains.npz")
+    assert ch["log_like"].shape == (nch,) and not ch["status"].any()
+    assert len(np.unique(ch["log_like"])) == nch              # independent streams
+    np.testing.assert_allclose(ch["log_like"][0], ref["ll"], rtol=1e-9)
+
+    # restart: --initf reads the final coefficients back (lib/MCState.py:139-201)
+    out2 = os.path.join(tmp, "run2.dat")
+    MC2, _ = find_parameters(files, True, "CosinusModel", 0.05, 0.05, 0.5, 1.0, 0.1, 1.0, 1.0, 100, 100.0, 5,
+                             out2, 10, 6, 0, False, out, -1, -1, False, None, nchains=2)
+    text2 = capsys.readouterr().out
+    ll_init = float([l for l in text2.splitlines() if l.startswith("initial log-likelihood:")][0].split()[-1])
+    assert ll_init == pytest.approx(ref["ll"], rel=2e-7)      # coefficients are stored with 9 digits
+
+
+def test_per_bin_model_and_nopbc(engine, gold_ll, tmp_path, capsys):
+    from mcdiff_b200 import outreading as outr
+    from mcdiff_b200.mc import find_parameters
+    from mcdiff_b200.transitions import write_Tmat_square
+    G = gold_ll
+    tmp = str(tmp_path)
+    fn = os.path.join(tmp, "cut.dat")
+    write_Tmat_square(G["C_counts"][0], fn, 20.0, "cut", edges=G["C_edges"], dt=1.0, dn=20)
+    out = os.path.join(tmp, "cut.out.dat")
+    MC, lg = find_parameters([fn], False, "Model", 0.1, 0.1, 0.5, 1.0, 0.1, 1.0, 1.0, 200, 100.0, 1, out,
+                             0, 0, 0, False, None, -1, -1, False, None, nchains=4)
+    capsys.readouterr()
+    F, D, edges = outr.read_F_D_edges(out)
+    assert len(F) == 60 and len(D) == 59
+    assert lg.v.shape == (4 * 3, 60) and lg.w.shape == (4 * 3, 59)
+    assert MC.log_like > float(MC.chain_log_like.min()) - 1e9 and not MC.chain_status.any()
+    with pytest.raises(AssertionError):      # pbc flag must agree with the counting method (lib/MCState.py:99)
+        find_parameters([fn], True, "Model", 0.1, 0.1, 0.5, 1.0, 0.1, 1.0, 1.0, 10, 100.0, 1, None,
+                        0, 0, 0, False, None, -1, -1, False, None)
+    with pytest.raises(NotImplementedError):
+        find_parameters([fn], False, "Model", 0.1, 0.1, 0.5, 1.0, 0.1, 1.0, 1.0, 10, 100.0, 1, None,
+                        0, 0, 0, False, None, -1, -1, False, 0.1)
+
+
+def test_initial_nan_raises_like_reference(engine, gold_ll):
+    """lib/MCState.py:114-117: a non-finite first likelihood is a ValueError."""
+    from mcdiff_b200.engine import ChainBatch, DeviceProblem
+    G = gold_ll
+    prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True)
+    ch = ChainBatch(prob, 2)
+    v = np.zeros((2, 100))
+    v[1, 0] = np.inf
+    ch.set_state(v, np.tile(G["P_flat_w"], (2, 1)), dv=0.1, dw=0.1)
+    with pytest.raises(ValueError, match="Initial likelihood diverges"):
+        ch.init_log_like()
