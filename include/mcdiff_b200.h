@@ -165,6 +165,41 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
                           const double* bessels, const double* b0zeros, double clip, int32_t B,
                           const double* wrad, double* out_ll, double* out_P, int32_t* status, void* stream);
 
+/* Radial Monte-Carlo loop (only wrad is sampled; v and w are frozen), one CTA per chain.
+ * Replaces the lmax > 0 branch of do_mc_cycles (lib/mc.py:29-30) = MCState.mcmove_diffusion_radial
+ * (lib/MCState.py:306-340) + the dwrad update (lib/MCState.py:383-386). */
+typedef struct {
+  double num_mc_update;
+  double dtemp;
+  int32_t sample_every;
+  int32_t use_tape;
+  int32_t ncosDrad;      /* 0: per-bin moves of wrad, >0: wrad = wrad_basis . wrad_coeff */
+  int32_t reserved;
+  uint64_t seed;
+  int64_t chain_offset;
+  int64_t tape_stride;
+  int64_t nsamples_cap;
+} mcd_rad_mc_params;
+
+typedef struct {
+  double* wrad;            /* [C][n] */
+  double* wcoef;           /* [C][ncosDrad] */
+  double* scal;            /* [C][8]  {log_like, dwrad, temp, ...} */
+  int64_t* counters;       /* [C][8]  {naccwrad, naccwrad_update, step, status, ...} */
+  int64_t* nacc_coeff;     /* [C][max(ncosDrad,1)] */
+  const double* wrad_basis;/* [n][ncosDrad] (lib/model.py:349-352) */
+  const double* tape_u;    /* [nsteps][5]: column 1 = delta uniform, column 2 = accept uniform */
+  const int32_t* tape_idx; /* [nsteps] */
+  uint8_t* decisions;      /* [C][nsteps] or NULL */
+  double* ll_try;          /* [C][nsteps] or NULL */
+  double* samples;         /* [C][nsamples_cap][3 + (ncosDrad ? ncosDrad : n)] = {log_like, dwrad, temp, wrad|coeff...} */
+} mcd_rad_chain_io;
+
+int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
+                   const double* v, const double* w, const double* lagtimes, const double* counts,
+                   const double* bessels, const double* b0zeros, double clip, const mcd_rad_mc_params* params,
+                   const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream);
+
 /* FP64 FMA micro-benchmark: fills *tflops with the measured dense DFMA rate of the device
  * (the roofline denominator bench.py reports against).  Synchronous. */
 int mcd_fp64_peak(mcd_handle* h, double* tflops);

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcdiff_b200.so")
+LIB_PATH = os.environ.get("MCDIFF_B200_LIB", os.path.join(_HERE, "libmcdiff_b200.so"))
 
 MCD_NSCAL = 8
 MCD_NCOUNT = 8
@@ -49,10 +49,26 @@ class ChainIO(C.Structure):
     ]
 
 
+class RadMcParams(C.Structure):
+    _fields_ = [
+        ("num_mc_update", C.c_double), ("dtemp", C.c_double), ("sample_every", C.c_int32),
+        ("use_tape", C.c_int32), ("ncosDrad", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
+        ("chain_offset", C.c_int64), ("tape_stride", C.c_int64), ("nsamples_cap", C.c_int64),
+    ]
+
+
+class RadChainIO(C.Structure):
+    _fields_ = [
+        ("wrad", c_dp), ("wcoef", c_dp), ("scal", c_dp), ("counters", c_dp), ("nacc_coeff", c_dp),
+        ("wrad_basis", c_dp), ("tape_u", c_dp), ("tape_idx", c_dp), ("decisions", c_dp), ("ll_try", c_dp),
+        ("samples", c_dp),
+    ]
+
+
 EXPORTS = (
     "mcd_version", "mcd_error_string", "mcd_create", "mcd_destroy", "mcd_problem_create",
     "mcd_problem_destroy", "mcd_problem_info", "mcd_loglike_batch", "mcd_mc_run",
-    "mcd_rad_loglike_batch", "mcd_fp64_peak", "mcd_launch_count",
+    "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_fp64_peak", "mcd_launch_count",
 )
 
 _lib = None
@@ -88,11 +104,14 @@ def load():
     lib.mcd_rad_loglike_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int32,
                                           c_dp, c_dp, c_dp, c_dp, C.c_void_p]
+    lib.mcd_rad_mc_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.POINTER(RadMcParams),
+                                   C.POINTER(RadChainIO), C.c_int32, C.c_int32, C.c_void_p]
     lib.mcd_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.mcd_launch_count.restype = C.c_int64
     lib.mcd_launch_count.argtypes = [C.c_void_p]
     for f in ("mcd_create", "mcd_destroy", "mcd_problem_create", "mcd_problem_destroy", "mcd_problem_info",
-              "mcd_loglike_batch", "mcd_mc_run", "mcd_rad_loglike_batch", "mcd_fp64_peak"):
+              "mcd_loglike_batch", "mcd_mc_run", "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_fp64_peak"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib

@@ -543,7 +543,7 @@ struct Chain {
   // Natural logarithm for positive, finite, normal arguments (the likelihood epilogue only calls it
   // with g >= gmin >= clip > 0).  Branch-free: g = 2^e m, m in [1,2); table of 128 reciprocals c_k
   // brings r = m c_k - 1 into |r| < 2^-8; log g = e ln2 - log c_k + (r - r^2/2 + ... - r^6/6).
-  // Absolute error < 4e-16 + 1.6e-16 |log g| (checked against libm in tests/test_emulation.py).
+  // Within 4e-16 + 1 ulp of libm (checked in tests/test_emulation.py).
   MCD_HD double fast_log(double g) const {
 #if defined(__CUDA_ARCH__)
     const long long bits = __double_as_longlong(g);

@@ -392,6 +392,41 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
   return (int)cudaGetLastError();
 }
 
+static_assert(sizeof(mcd_rad_mc_params) == sizeof(RadMcParams), "mcd_rad_mc_params layout");
+static_assert(sizeof(mcd_rad_chain_io) == sizeof(RadChainIO), "mcd_rad_chain_io layout");
+
+int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
+                   const double* v, const double* w, const double* lagtimes, const double* counts,
+                   const double* bessels, const double* b0zeros, double clip, const mcd_rad_mc_params* params,
+                   const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream) {
+  if (!h || !v || !w || !lagtimes || !counts || !bessels || !b0zeros || !params || !io) return MCD_E_ARG;
+  if (!io->wrad || !io->scal || !io->counters) return MCD_E_ARG;
+  if (n < 3 || n > 256 || nlag < 1 || nlag > kMaxLag || dim_rad < 1 || lmax < 1 || lmax > kMaxBessel) return MCD_E_ARG;
+  if (params->ncosDrad < 0 || params->ncosDrad > kMaxCoef) return MCD_E_ARG;
+  if (params->ncosDrad > 0 && (!io->wcoef || !io->wrad_basis || !io->nacc_coeff)) return MCD_E_ARG;
+  if (params->use_tape && (!io->tape_u || !io->tape_idx)) return MCD_E_ARG;
+  if (nchains <= 0 || nsteps <= 0) return nchains < 0 || nsteps < 0 ? MCD_E_ARG : MCD_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RadProblem R;
+  R.n = n; R.np = padded_bins(n); R.ld = leading_dim(R.np); R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
+  R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
+  R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
+  R.clip = clip;
+  int rc = ensure_gws(h, (size_t)nchains * rad_workspace_doubles(R) * sizeof(double));
+  if (rc != MCD_OK) return rc;
+  const size_t smem = rad_smem_bytes(R);
+  if (smem > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  RadMcParams mp;
+  RadChainIO cio;
+  std::memcpy(&mp, params, sizeof(mp));
+  std::memcpy(&cio, io, sizeof(cio));
+  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mcd_rad_mc_run_kernel<<<nchains, kThreads, smem, st>>>(R, mp, cio, nsteps, h->gws);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
 int mcd_fp64_peak(mcd_handle* h, double* tflops) {
   if (!h || !tflops) return MCD_E_ARG;
   CUDA_TRY(cudaSetDevice(h->device));

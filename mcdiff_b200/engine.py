@@ -306,3 +306,106 @@ def rad_loglike(eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad
                                               _dev(out), _dev(P), _dev(status), eng.stream_ptr()),
                 "mcd_rad_loglike_batch")
         return out.cpu().numpy(), (None if P is None else P.cpu().numpy()), status.cpu().numpy()
+
+
+class RadialChains:
+    """C independent chains of the radial Monte-Carlo loop (only wrad is sampled; v, w frozen):
+    lib/mc.py:29-30, MCState.mcmove_diffusion_radial (lib/MCState.py:306-340)."""
+
+    def __init__(self, eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, nchains, wrad_basis=None,
+                 clip=1e-32):
+        self.eng = eng
+        f64 = torch.float64
+        counts = np.asarray(counts, dtype=np.float64)
+        self.nlag, self.dim_rad, self.n, _ = counts.shape
+        self.lmax = int(np.asarray(bessels).shape[0])
+        self.pbc = bool(pbc)
+        self.C = int(nchains)
+        self.clip = float(clip)
+        self.ncos = 0 if wrad_basis is None else int(np.asarray(wrad_basis).shape[1])
+        dev = eng.device
+        with torch.cuda.device(dev):
+            self.d_v, self.d_w = eng.to_device(np.asarray(v, dtype=np.float64), f64), eng.to_device(np.asarray(w, dtype=np.float64), f64)
+            self.d_lag = eng.to_device(np.asarray(lagtimes, dtype=np.float64), f64)
+            self.d_counts = eng.to_device(counts, f64)
+            self.d_bess = eng.to_device(np.asarray(bessels, dtype=np.float64), f64)
+            self.d_zeros = eng.to_device(np.asarray(b0zeros, dtype=np.float64), f64)
+            self.d_basis = None if wrad_basis is None else eng.to_device(np.asarray(wrad_basis, dtype=np.float64), f64)
+            self.wrad = torch.zeros((self.C, self.n), dtype=f64, device=dev)
+            self.wcoef = torch.zeros((self.C, max(self.ncos, 1)), dtype=f64, device=dev)
+            self.scal = torch.zeros((self.C, 8), dtype=f64, device=dev)
+            self.counters = torch.zeros((self.C, 8), dtype=torch.int64, device=dev)
+            self.nacc_coeff = torch.zeros((self.C, max(self.ncos, 1)), dtype=torch.int64, device=dev)
+
+    @property
+    def sample_dim(self):
+        return 3 + (self.ncos if self.ncos > 0 else self.n)
+
+    def set_state(self, wrad, wcoef=None, *, dwrad, temp=1.0):
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            wr = np.broadcast_to(np.asarray(wrad, dtype=np.float64), (self.C, self.n))
+            self.wrad.copy_(eng.to_device(np.ascontiguousarray(wr), torch.float64))
+            if self.ncos > 0:
+                wc = np.broadcast_to(np.asarray(wcoef, dtype=np.float64), (self.C, self.ncos))
+                self.wcoef.copy_(eng.to_device(np.ascontiguousarray(wc), torch.float64))
+            sc = np.zeros((self.C, 8))
+            sc[:, 1], sc[:, 2] = dwrad, temp
+            self.scal.copy_(eng.to_device(sc, torch.float64))
+            self.counters.zero_()
+            self.nacc_coeff.zero_()
+
+    def init_log_like(self):
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            out = torch.empty(self.C, dtype=torch.float64, device=eng.device)
+            status = torch.empty(self.C, dtype=torch.int32, device=eng.device)
+            K.check(eng.lib.mcd_rad_loglike_batch(eng.handle, self.n, int(self.pbc), self.nlag, self.dim_rad, self.lmax,
+                                                  _dev(self.d_v), _dev(self.d_w), _dev(self.d_lag), _dev(self.d_counts),
+                                                  _dev(self.d_bess), _dev(self.d_zeros), self.clip, self.C,
+                                                  _dev(self.wrad), _dev(out), None, _dev(status), eng.stream_ptr()),
+                    "mcd_rad_loglike_batch")
+            self.scal[:, 0] = out
+            host = out.cpu().numpy()
+        if np.any(np.isnan(host)):
+            raise ValueError("Initial likelihood diverges")
+        return host
+
+    def run(self, nsteps, *, num_mc_update, dtemp=0.0, seed=0, chain_offset=0, tape_u=None, tape_idx=None,
+            record=False, nsamples_cap=0):
+        eng = self.eng
+        dev = eng.device
+        with torch.cuda.device(dev):
+            mp = K.RadMcParams()
+            mp.num_mc_update, mp.dtemp, mp.sample_every = float(num_mc_update), float(dtemp), 100
+            mp.use_tape, mp.ncosDrad, mp.seed = int(tape_u is not None), self.ncos, int(seed)
+            mp.chain_offset, mp.tape_stride, mp.nsamples_cap = int(chain_offset), 0, int(nsamples_cap)
+            io = K.RadChainIO()
+            io.wrad, io.wcoef, io.scal = self.wrad.data_ptr(), self.wcoef.data_ptr(), self.scal.data_ptr()
+            io.counters, io.nacc_coeff = self.counters.data_ptr(), self.nacc_coeff.data_ptr()
+            io.wrad_basis = None if self.d_basis is None else self.d_basis.data_ptr()
+            keep = []
+            if tape_u is not None:
+                tu = eng.to_device(np.asarray(tape_u, dtype=np.float64), torch.float64)
+                ti = eng.to_device(np.asarray(tape_idx, dtype=np.int32), torch.int32)
+                keep += [tu, ti]
+                io.tape_u, io.tape_idx = tu.data_ptr(), ti.data_ptr()
+            dec = llt = smp = None
+            if record:
+                dec = torch.zeros((self.C, nsteps), dtype=torch.uint8, device=dev)
+                llt = torch.zeros((self.C, nsteps), dtype=torch.float64, device=dev)
+                io.decisions, io.ll_try = dec.data_ptr(), llt.data_ptr()
+            if nsamples_cap > 0:
+                smp = torch.zeros((self.C, nsamples_cap, self.sample_dim), dtype=torch.float64, device=dev)
+                io.samples = smp.data_ptr()
+            K.check(eng.lib.mcd_rad_mc_run(eng.handle, self.n, int(self.pbc), self.nlag, self.dim_rad, self.lmax,
+                                           _dev(self.d_v), _dev(self.d_w), _dev(self.d_lag), _dev(self.d_counts),
+                                           _dev(self.d_bess), _dev(self.d_zeros), self.clip, C.byref(mp), C.byref(io),
+                                           self.C, int(nsteps), eng.stream_ptr()), "mcd_rad_mc_run")
+            self._keep = keep
+        return dec, llt, smp
+
+    def host_state(self):
+        with torch.cuda.device(self.eng.device):
+            return dict(wrad=self.wrad.cpu().numpy(), wcoef=self.wcoef.cpu().numpy(), scal=self.scal.cpu().numpy(),
+                        counters=self.counters.cpu().numpy(), nacc_coeff=self.nacc_coeff.cpu().numpy())

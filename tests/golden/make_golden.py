@@ -10,12 +10,14 @@ Outputs (committed):
     tests/golden/loglike_golden.npz   log-likelihood / propagator known answers
     tests/golden/replay_golden.npz    tape-driven MC trajectories of the reference
     tests/golden/radial_golden.npz    radial (Bessel) likelihood known answers
+    tests/golden/radial_replay_golden.npz  tape-driven radial MC trajectories of the reference
 
 Nothing here is product code and nothing is copied from the reference: the
 reference functions are *called* and their outputs recorded.
 """
 import contextlib
 import io
+import zlib
 import os
 import sys
 import tempfile
@@ -304,7 +306,6 @@ def main():
             tr = Transitions(files)
         nn = tr.dim_trans
         dim_w = nn if kw["pbc"] else nn - 1
-        import zlib
         r = np.random.default_rng(zlib.crc32(tag.encode()))
         tu, ti = tape_for(r, nmc, nn, dim_w, kw["ncosF"], kw["ncosD"], kw["dv"], kw["dw"])
         out = run_reference_replay(files, tape_u=tu, tape_idx=ti, **kw)
@@ -362,7 +363,66 @@ def main():
     Rd["P0"] = propagator_radial_diffusion(nr, dim_rad, rate, wrads[0], rlags[0], lmax, zeros, table)
     np.savez_compressed(os.path.join(HERE, "radial_golden.npz"), **Rd)
     print("radial ll:", Rd["ll"])
-    for f in ("loglike_golden.npz", "replay_golden.npz", "radial_golden.npz"):
+
+    # ---- radial Monte-Carlo trajectories of the reference (lib/mc.py:29-30, lib/MCState.py:306-340) ----
+    from mcdiff.tools.extract import write_Tmat_cube
+    import mcdiff.MCState as mcs
+    from mcdiff.transitions import RadTransitions
+    from mcdiff.log import Logger
+    edges = np.linspace(-4.0, 4.0, nr + 1)
+    redges = np.arange(dim_rad) * 0.5
+    rfiles = []
+    for il, lag in enumerate(rlags):
+        fn = os.path.join(tmp, "rad.%d.dat" % il)
+        write_Tmat_cube(cube[il].astype(int), fn, float(lag), "pbc", edges=edges, redges=redges, dt=1.0, dn=int(lag))
+        rfiles.append(fn)
+    RR = {}
+    for tag, ncosDrad, nmc in (("radbin", 0, 120), ("radcos", 4, 120)):
+        r = np.random.default_rng(zlib.crc32(tag.encode()))
+        tu = r.random((nmc, 5))
+        ti = r.integers(0, nr if ncosDrad == 0 else ncosDrad, nmc).astype(np.int32)
+        with quiet():
+            MC = mcs.MCState(True, lmax)
+            MC.set_MC_params(0.5, 0.5, 0.4, 1.0, 0.1, 1.0, nmc, 40.0, False, -1.0, temp_end=1.0)
+            data = RadTransitions(rfiles)
+            MC.set_model("RadCosinusModel", data, 0, 0, ncosDrad, None)
+            logger = Logger(MC)
+            wrad0 = MC.model.wrad.copy()
+            wc0 = MC.model.wrad_coeff.copy() if ncosDrad > 0 else np.zeros(0)
+            rng_ = TapeRNG(tu, ti, radial=True)
+            saved = (np.random.rand, np.random.randint, np.random.random)
+            np.random.rand, np.random.randint, np.random.random = rng_.rand, rng_.randint, rng_.random
+            acc, ll_after, widths = [], [], []
+            try:
+                MC.init_log_like()
+                ll0 = float(MC.log_like)
+                logger.log(0, MC)
+                for imc in range(nmc):
+                    na = MC.naccwrad
+                    MC.mcmove_diffusion_radial()
+                    acc.append(int(MC.naccwrad - na))
+                    ll_after.append(float(MC.log_like))
+                    logger.log(imc + 1, MC)
+                    d_b = MC.dwrad
+                    MC.update_movewidth(imc)
+                    MC.update_temp(imc)
+                    if MC.dwrad != d_b:
+                        widths.append((imc, MC.dwrad))
+            finally:
+                np.random.rand, np.random.randint, np.random.random = saved
+        out = dict(tape_u=tu, tape_idx=ti, ll0=ll0, accepted=np.array(acc, dtype=np.int8), ll_after=np.array(ll_after),
+                   widths=np.array(widths).reshape(-1, 2), wrad0=wrad0, wc0=wc0, wrad=np.array(MC.model.wrad),
+                   wc=np.array(MC.model.wrad_coeff) if ncosDrad > 0 else np.zeros(0), ll=float(MC.log_like),
+                   dwrad=float(MC.dwrad), naccwrad=int(MC.naccwrad), v=np.array(MC.model.v), w=np.array(MC.model.w),
+                   zeros=np.array(MC.model.bessel0_zeros), table=np.array(MC.model.bessels),
+                   counts=np.array(data.list_trans), lags=np.array(data.list_lt, dtype=np.float64),
+                   wradunit=float(MC.model.wradunit), log_ll=logger.log_like.copy(),
+                   log_wrad=(logger.wrad_coeff if ncosDrad > 0 else logger.wrad).copy(), dim_rad=dim_rad, lmax=lmax)
+        for key, val in out.items():
+            RR[tag + "/" + key] = val
+        print(tag, "ll0", ll0, "ll", out["ll"], "acc", out["naccwrad"], "dwrad", out["dwrad"])
+    np.savez_compressed(os.path.join(HERE, "radial_replay_golden.npz"), **RR)
+    for f in ("loglike_golden.npz", "replay_golden.npz", "radial_golden.npz", "radial_replay_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

