@@ -4,7 +4,7 @@
 Metric (BASELINE.json): MC steps/sec summed over all chains at 100 bins x 4 lag times,
 plus the fraction of the FP64 roofline.  One bench "step" = ONE launch of the fused chain
 kernel that advances every chain of this rank by MC_PER_LAUNCH Monte-Carlo steps (one MC
-step = proposal + rate matrix + eigendecomposition + 4 propagators + log L + Metropolis,
+step = proposal + rate matrix + 4 propagators expm(lag R) + log L + Metropolis,
 i.e. one iteration of lib/mc.py:27 of the reference).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -32,6 +32,7 @@ MC_PER_LAUNCH = 200
 NCOS_F, NCOS_D = 10, 6           # the reference's own example model (examples/example-HexdWat-run1.sh)
 DV = DW = 0.05
 NMC_UPDATE = 1000.0
+NCU_DRAM_BYTES_PER_LAUNCH = 4115968 + 7168
 METRIC = "MC steps/sec (all chains, 100 bins x 4 lags)"
 UNIT = "MC steps/s"
 
@@ -99,11 +100,15 @@ def cpu_port_steps_per_s(wl, nsteps, seed=1):
     return nsteps / (time.perf_counter() - t0)
 
 
+_WL_CACHE = None
+
+
 def _ref_worker(args):
+    global _WL_CACHE
     nsteps, seed = args
-    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[var] = "1"
-    wl = workload()
+    if _WL_CACHE is None:              # once per worker process, outside the timed steps (warm-up)
+        _WL_CACHE = workload()
+    wl = _WL_CACHE
     from oracle import mcdiff_oracle as O
     cfg = O.ChainConfig(wl["counts"], wl["lags"], True, v_basis=wl["vb"], w_basis=wl["wb"], dv=DV, dw=DW,
                         temp=1.0, nmc=nsteps, num_mc_update=NMC_UPDATE)
@@ -120,17 +125,17 @@ def run_reference(args):
         return
     import multiprocessing as mp
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[var] = "1"
+        os.environ[var] = "1"      # BLAS threads hurt at n = 100; one chain per core instead
     cores = os.cpu_count() or 1
-    per_step = 40            # MC steps per worker per bench step (bounded sample)
+    per_step = 150           # MC steps per worker per bench step (bounded sample, ~0.3 s per step)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        for w in range(args.warmup):
-            pool.map(_ref_worker, [(8, 1000 + w * cores + c) for c in range(cores)])
+        for w in range(max(1, args.warmup)):
+            pool.map(_ref_worker, [(8, 1000 + w * cores + c) for c in range(cores)], chunksize=1)
         t0 = time.perf_counter()
         done = 0
         for k in range(args.steps):
-            done += sum(pool.map(_ref_worker, [(per_step, k * cores + c) for c in range(cores)]))
+            done += sum(pool.map(_ref_worker, [(per_step, k * cores + c) for c in range(cores)], chunksize=1))
         el = time.perf_counter() - t0
     val = done / el
     line = {
@@ -314,7 +319,11 @@ def run_gpu(args):
             "mean_acceptance": float((summary_all[:, 6] + summary_all[:, 7]).sum() / max(1.0, float(world) * st["counters"][:, 5].sum())),
         },
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved_tf / peak_tf if peak_tf else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this configuration
+                     # (ncu --set full, profiles/r01_ncu_full_mc_run_bench_launch.csv): 4.12 MB
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (nch, MC_PER_LAUNCH) == (1024, 200) else None,
+                     "traffic_unit": "bytes of DRAM traffic per launch (ncu); the kernel is not HBM bound",
                      "peak_source": "measured here by mcd_fp64_peak (dense DFMA loop); MEASURED_PEAKS.json has no FP64 "
                                     "figure; nominal 148 SM x 64 DFMA x 2 x 1.965 GHz = 37.2",
                      "algorithmic_flops_per_mc_step": fl, "kernel": "mcd_mc_run_kernel<true>",
