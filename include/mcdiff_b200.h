@@ -55,8 +55,10 @@ enum {
  *  EIGEN    : in-CTA parallel Jacobi eigendecomposition of the detailed-balance-symmetrised
  *             generator, P = Pi^1/2 V exp(lag Lambda) V^T Pi^-1/2; any lag times, time-offset moves.
  *  SQUARING : symmetric scaling-and-squaring, all products as FP64 tensor-core (mma.sync m8n8k4)
- *             GEMMs on shared-memory operands; needs lag times in arithmetic progression lag_l = (l+1) lag_0, no time-offset
- *             move and n <= 108 (work matrices in shared memory). */
+ *             GEMMs on shared-memory operands.  Lag times are visited in ascending order,
+ *             G(t_i) = G(t_{i-1}) G(t_i - t_{i-1}); every distinct operand is an earlier G(t_j) or gets its
+ *             own squaring chain (at most 8), so arithmetic progressions (10,20,30,40 / a single lag) need
+ *             one chain, time-offset moves (--t0) two.  Needs n <= 104 (work matrices in shared memory). */
 enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2,
        MCD_METHOD_SQUARING_DFMA = 3 /* same algorithm, products on the FP64 vector pipe (A/B reference) */ };
 

@@ -20,9 +20,25 @@
 
 namespace mcd {
 
-constexpr int kMaxLag = 64;
+constexpr int kMaxLag = 64;   // LagPlan arrays are sized for this
 constexpr int kMaxCoef = 64;
 constexpr int kMaxSweeps = 60;
+
+// How the squaring engine reaches every lag time (built on the host, mcd_lib.cu::plan_lags).
+// Lags are visited in ascending order; G(t_i) = G(t_{i-1}) G(delta_i), delta_i = t_i - t_{i-1}.  Each
+// distinct operand G(delta) comes from its own squaring chain or is an earlier G(t_j) parked in a
+// per-CTA global (L2 resident) slot.  `fast`: arithmetic progression t_i = (i+1) t_0, no slots.
+constexpr int kMaxChains = 8;
+constexpr int kMaxSlots = 8;
+struct LagPlan {
+  int ok = 0, fast = 0, nchain = 0, nslots = 0;
+  signed char order[64] = {};             // lag index visited i-th (ascending lag time)
+  signed char chain_a[kMaxChains] = {};   // chain time = lagt[a] - (b >= 0 ? lagt[b] : 0); the LAST chain is G(t_0)
+  signed char chain_b[kMaxChains] = {};
+  signed char chain_slot[kMaxChains] = {};  // slot the chain result is parked in, -1: none
+  signed char op_slot[64] = {};           // i >= 1: slot holding G(delta_i); -1: delta_i = 0 (same kernel as i-1)
+  signed char park[64] = {};              // slot G(t_i) is parked in after lag i, -1: none
+};
 
 struct Problem {
   int n, np, ld, dim_w, pbc, nlag;
@@ -36,7 +52,68 @@ struct Problem {
   const double* svecs;     // [dim_w][dim_w]  Laplacian eigenvectors (null when spring_k <= 0)
   double spring_k;
   double clip;
+  LagPlan plan[2];         // [0]: lag times as given, [1]: lag times shifted by a time offset (--t0)
 };
+
+MCD_HOSTDEV bool plan_close(double a, double b) { return fabs(a - b) <= 1e-12 * fabs(b); }
+
+// Build the LagPlan of the squaring engine (see mcd_chain.cuh).  shifted: a time offset is added to
+// every lag at run time, so only DIFFERENCES of lag times are known to coincide.
+MCD_HOSTDEV void plan_lags(const double* lag, int L, bool shifted, LagPlan* pl) {
+  *pl = LagPlan();
+  int ord[kMaxLag];
+  for (int i = 0; i < L; ++i) ord[i] = i;
+  for (int i = 1; i < L; ++i)
+    for (int j = i; j > 0 && lag[ord[j]] < lag[ord[j - 1]]; --j) { int t = ord[j]; ord[j] = ord[j - 1]; ord[j - 1] = t; }
+  for (int i = 0; i < L; ++i) { pl->order[i] = (signed char)ord[i]; pl->op_slot[i] = -1; pl->park[i] = -1; }
+  if (!(lag[ord[0]] > 0.0)) return;
+
+  // operand descriptors: either "G(t_j)" (j = sorted index) or a fresh chain for a difference
+  int nslots = 0, nchain = 0;
+  int slot_of_R[kMaxLag];
+  for (int i = 0; i < L; ++i) slot_of_R[i] = -1;
+  int chain_first[kMaxChains];          // sorted index i whose difference the chain computes
+  bool fast = !shifted;
+  for (int i = 1; i < L; ++i) {
+    const double ti = lag[ord[i]], tp = lag[ord[i - 1]];
+    const double delta = ti - tp;
+    if (!(delta > 1e-12 * ti)) { fast = false; continue; }      // duplicate lag time: op_slot = -1
+    int slot = -1;
+    if (!shifted) {
+      for (int j = 0; j < i && slot < 0; ++j)
+        if (plan_close(lag[ord[j]], delta)) {
+          if (slot_of_R[j] < 0) { if (nslots >= kMaxSlots) return; slot_of_R[j] = nslots++; }
+          slot = slot_of_R[j];
+          if (j != 0) fast = false;
+        }
+    }
+    for (int c = 0; c < nchain && slot < 0; ++c) {
+      const int k = chain_first[c];
+      if (plan_close(lag[ord[k]] - lag[ord[k - 1]], delta)) slot = pl->chain_slot[c];
+    }
+    if (slot < 0) {
+      if (nchain >= kMaxChains - 1 || nslots >= kMaxSlots) return;
+      fast = false;
+      chain_first[nchain] = i;
+      pl->chain_a[nchain] = (signed char)ord[i];
+      pl->chain_b[nchain] = (signed char)ord[i - 1];
+      pl->chain_slot[nchain] = (signed char)nslots;
+      slot = nslots++;
+      ++nchain;
+    }
+    pl->op_slot[i] = (signed char)slot;
+  }
+  // the G(t_0) chain comes last
+  pl->chain_a[nchain] = (signed char)ord[0];
+  pl->chain_b[nchain] = -1;
+  pl->chain_slot[nchain] = (signed char)slot_of_R[0];
+  ++nchain;
+  for (int i = 1; i < L; ++i) pl->park[i] = (signed char)slot_of_R[i];
+  pl->nchain = nchain;
+  pl->nslots = fast ? 0 : nslots;
+  pl->fast = fast ? 1 : 0;
+  pl->ok = 1;
+}
 
 struct McParams {
   double num_mc_update;  // lib/MCState.py:382 (parsed as float by the CLI)
@@ -861,33 +938,19 @@ struct Chain {
   }
 
   // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
-  MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, int taylor_m, bool tensor,
-                            double* Pout, int* squarings_out) {
-    const bool use_mma = tensor && dmma_ok();
+  // exp(t S) by Taylor + squarings.  Uses both work buffers; returns the one holding the result
+  // (*other receives the second one).  epi >= 0: the likelihood terms of lag index epi are added
+  // (fused into the last squaring).  Returns nullptr for a non-finite / absurd scale.
+  MCD_HD double* sq_chain(double t, double gersh, int taylor_m, bool use_mma, int epi, double* Pout, double** other,
+                          int* nsq_out) {
     const int n = P.n, np = P.np, ld = P.ld;
-    build_S(v, w);
-    // Gershgorin bound of ||S||
-    const double gersh = ex.max([&](int tid) {
-      double m = 0.0;
-      for (int i = tid; i < n; i += Exec::nthr()) {
-        const int im = (i == 0) ? n - 1 : i - 1;
-        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
-        m = (r > m || r != r) ? r : m;
-      }
-      return m;
-    });
-    const double t0 = lagt[0];
-    const double rho = t0 * gersh;
-    if (!(rho < 1.0e9) || !(t0 > 0.0)) {  // non-finite profile or absurd scale
-      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
-      if (squarings_out) *squarings_out = -1;
-      return nan("");
-    }
+    const double rho = t * gersh;
+    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
     int nsq = 0;
     for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
-    const double h = ldexp(t0, -nsq);
+    const double h = ldexp(t, -nsq);
     // Taylor order.  T_m(x) = e^x (1 - x^(m+1)/(m+1)! ...) per eigenmode, and the error is amplified
-    // 2^s times by the squarings -- but only modes with t0 |lambda| <= 45 survive in G(t0) at all
+    // 2^s times by the squarings -- but only modes with t |lambda| <= 45 survive in G(t) at all
     // (e^-45 = 3e-20), i.e. |x| <= x* = min(1, 45 / 2^s).  Smallest m with 2^s x*^(m+1)/(m+1)! <= 1e-17.
     int m = taylor_m;
     if (m <= 0) {
@@ -908,7 +971,6 @@ struct Chain {
     // `tpr` consecutive threads that walk its band with stride tpr (contiguous columns across
     // lanes); the three coefficients of the row stay in registers for the whole pass.
     ex.par([&](int tid) {
-      s.part[tid] = 0.0;
       for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(A + e, 0.0, 0.0); st2(B + e, 0.0, 0.0); }
     });
     double* src = A;
@@ -918,9 +980,9 @@ struct Chain {
     });
     const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
     const int rows_per_pass = Exec::nthr() / tpr;
-    for (int t = 1; t <= m; ++t) {
-      const double f = h / (double)(m - t + 1);
-      const int width = (2 * t + 1 < n) ? 2 * t + 1 : n;
+    for (int tt = 1; tt <= m; ++tt) {
+      const double f = h / (double)(m - tt + 1);
+      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
       const bool full = (width == n);
       ex.par([&](int tid) {
         const int r = tid % tpr;
@@ -936,7 +998,7 @@ struct Chain {
             int j;
             if (full) j = dd;
             else {
-              j = i - t + dd;
+              j = i - tt + dd;
               if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
               else if (j < 0 || j >= n) continue;
             }
@@ -946,46 +1008,130 @@ struct Chain {
       });
       double* tmp = src; src = dst; dst = tmp;
     }
-    // ---- G(t0) = T^(2^s): out-of-place squarings src -> dst (direct stores), the last one carries
-    //      the likelihood epilogue of lag 0 ----
+    // ---- G(t) = T^(2^s): out-of-place squarings (direct stores), the last one carries the
+    //      likelihood epilogue of lag `epi` ----
     double* G = src;      // current power
     double* O = dst;      // the other buffer
+    const int* cnt_e = (epi >= 0) ? P.counts + (size_t)epi * np * np : nullptr;
+    const int* nsy_e = (epi >= 0) ? P.nsym + (size_t)epi * np * np : nullptr;
     for (int q = 0; q < nsq; ++q) {
       const bool last = (q + 1 == nsq);
-      const int* cnt = last ? P.counts : nullptr;
-      const int* nsy = last ? P.nsym : nullptr;
+      const int* cnt = last ? cnt_e : nullptr;
+      const int* nsy = last ? nsy_e : nullptr;
       if (use_mma) dmma_product(G, G, O, cnt, nsy, last ? Pout : nullptr, 1);
       else sym_product(G, G, O, cnt, nsy, last ? Pout : nullptr, 1);
       double* tmp = G; G = O; O = tmp;
     }
-    if (nsq == 0) {   // lag 0 straight from the Taylor polynomial
-      const int* cnt = P.counts;
-      const int* nsy = P.nsym;
-      ex.par([&](int tid) {
-        if (tid < s.ntiles) {
-          const int ib = s.tiles[2 * tid], jb = s.tiles[2 * tid + 1];
-          i4 ns[4];
-          load_counts(nsy, ib, jb, ns);
-          double c[4][4];
+    if (nsq == 0 && epi >= 0) buffer_loglike(G, cnt_e, nsy_e, Pout);
+    *other = O;
+    if (nsq_out) *nsq_out += nsq;
+    return G;
+  }
+
+  // likelihood terms of a kernel that already sits in a buffer (no product needed)
+  MCD_HD void buffer_loglike(const double* G, const int* cnt, const int* nsy, double* Pl) {
+    const int ld = P.ld;
+    ex.par([&](int tid) {
+      for (int tt = tid; tt < s.ntiles; tt += Exec::nthr()) {
+        const int ib = s.tiles[2 * tt], jb = s.tiles[2 * tt + 1];
+        i4 ns[4];
+        load_counts(nsy, ib, jb, ns);
+        double c[4][4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const d2 g01 = ld2(G + (ib * 4 + a) * ld + jb * 4), g23 = ld2(G + (ib * 4 + a) * ld + jb * 4 + 2);
-            c[a][0] = g01.x; c[a][1] = g01.y; c[a][2] = g23.x; c[a][3] = g23.y;
-          }
-          s.part[tid] += tile_loglike(c, ib, jb, ns, cnt, Pout);
+        for (int a = 0; a < 4; ++a) {
+          const d2 g01 = ld2(G + (ib * 4 + a) * ld + jb * 4), g23 = ld2(G + (ib * 4 + a) * ld + jb * 4 + 2);
+          c[a][0] = g01.x; c[a][1] = g01.y; c[a][2] = g23.x; c[a][3] = g23.y;
         }
-      });
+        s.part[tid] += tile_loglike(c, ib, jb, ns, cnt, Pl);
+      }
+    });
+  }
+
+  MCD_HD void copy_buffer(double* dst, const double* src) {
+    const int total = P.np * P.ld;
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < total; e += 2 * Exec::nthr()) {
+        const d2 x = ld2(src + e);
+        st2(dst + e, x.x, x.y);
+      }
+    });
+  }
+
+  // log L of (v, w) at the lag times lagt with the squaring engine, following LagPlan `pl`.
+  // slots: per-CTA global scratch of pl.nslots work matrices (only read/written when pl.fast == 0).
+  MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* slots,
+                            int taylor_m, bool tensor, double* Pout, int* squarings_out) {
+    const bool use_mma = tensor && dmma_ok();
+    const int n = P.n, np = P.np;
+    const size_t nn = (size_t)n * n, slot_elems = (size_t)np * P.ld;
+    build_S(v, w);
+    // Gershgorin bound of ||S||
+    const double gersh = ex.max([&](int tid) {
+      double m = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) {
+        const int im = (i == 0) ? n - 1 : i - 1;
+        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+        m = (r > m || r != r) ? r : m;
+      }
+      return m;
+    });
+    ex.par([&](int tid) { s.part[tid] = 0.0; });
+    int nsq = 0;
+    bool bad = false;
+    double* R = nullptr;   // running kernel G(t_i)
+    double* O = nullptr;   // the other shared buffer
+    const int l0 = pl.order[0];
+    const bool fast = pl.fast != 0;
+    // operand chains first (their results are parked in the slots), the G(t_0) chain last.
+    // ONE inlined call site for the chain and ONE for the products below: the kernel is large and
+    // duplicated bodies cost instruction-cache misses (measured: -12 % with two copies).
+    for (int c = 0; c < pl.nchain && !bad; ++c) {
+      const bool is_first_lag = (c == pl.nchain - 1);
+      const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
+      double* other = nullptr;
+      double* G = sq_chain(t, gersh, taylor_m, use_mma, is_first_lag ? l0 : -1,
+                           (is_first_lag && Pout) ? Pout + (size_t)l0 * nn : nullptr, &other, &nsq);
+      if (!G) { bad = true; break; }
+      if (!fast && pl.chain_slot[c] >= 0) copy_buffer(slots + (size_t)pl.chain_slot[c] * slot_elems, G);
+      R = G;
+      O = other;
     }
-    // ---- progression G((l+1) t0) = G(l t0) G(t0): first product out of place, then in place ----
-    for (int l = 1; l < P.nlag; ++l) {
+    // fast (arithmetic progression): G((i+1) t0) = G(i t0) G(t0), first product out of place into O,
+    // then in place on O with G(t0) staying in R.  general: R <- R G(delta_i) in place, operand in O.
+    double* G0 = R;
+    int in_O = -1;   // slot currently loaded in O (general plans)
+    for (int i = 1; i < P.nlag && !bad; ++i) {
+      const int l = pl.order[i];
       const int* cnt = P.counts + (size_t)l * np * np;
       const int* nsy = P.nsym + (size_t)l * np * np;
-      double* Pl = Pout ? Pout + (size_t)l * n * n : nullptr;
-      const int store = (l + 1 < P.nlag) ? (l == 1 ? 1 : 2) : 0;
-      if (use_mma) dmma_product(l == 1 ? G : O, G, O, cnt, nsy, Pl, store);
-      else sym_product(l == 1 ? G : O, G, O, cnt, nsy, Pl, store);
+      double* Pl = Pout ? Pout + (size_t)l * nn : nullptr;
+      if (!fast && pl.op_slot[i] < 0) {
+        buffer_loglike(R, cnt, nsy, Pl);          // same lag time as the previous one
+      } else {
+        const double* X;
+        const double* Y;
+        double* D;
+        int store;
+        if (fast) {
+          X = (i == 1) ? G0 : O; Y = G0; D = O;
+          store = (i + 1 < P.nlag) ? (i == 1 ? 1 : 2) : 0;
+        } else {
+          if (in_O != pl.op_slot[i]) {
+            copy_buffer(O, slots + (size_t)pl.op_slot[i] * slot_elems);
+            in_O = pl.op_slot[i];
+          }
+          X = R; Y = O; D = R; store = 2;
+        }
+        if (use_mma) dmma_product(X, Y, D, cnt, nsy, Pl, store);
+        else sym_product(X, Y, D, cnt, nsy, Pl, store);
+      }
+      if (!fast && pl.park[i] >= 0) copy_buffer(slots + (size_t)pl.park[i] * slot_elems, R);
     }
-    if (squarings_out) *squarings_out = nsq;
+    if (squarings_out) *squarings_out = bad ? -1 : nsq;
+    if (bad) {
+      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      return nan("");
+    }
     return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
   }
 
@@ -1035,7 +1181,7 @@ struct Chain {
   // ------------------------------------------------------------------------------------
   // The MC loop of lib/mc.py:27-51 for one chain.
   // ------------------------------------------------------------------------------------
-  MCD_HD void run(const McParams& mp, const ChainIO& io, long long chain, int nsteps) {
+  MCD_HD void run(const McParams& mp, const ChainIO& io, long long chain, int nsteps, double* sq_slots) {
     const int n = P.n, np = P.np, ld = P.ld, dim_w = P.dim_w;
     const int ncosF = P.ncosF, ncosD = P.ncosD;
     const int sdim = sample_dim(P);
@@ -1193,7 +1339,8 @@ struct Chain {
         int sw = 0;
         double ll_new;
         if (mp.method >= 2) {
-          ll_new = evaluate_sq(vtry, wtry, lagp, mp.taylor_m, mp.method == 2, nullptr, &sw);
+          ll_new = evaluate_sq(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, mp.method == 2,
+                               nullptr, &sw);
         } else {
           ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
           have_basis = (sw >= 0);

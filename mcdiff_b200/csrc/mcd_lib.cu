@@ -56,7 +56,9 @@ mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
   Smem s = carve(P, mat, vec);
   DeviceExec ex(s.red);
   Chain<DeviceExec> ch(ex, P, s);
-  ch.run(mp, io, (long long)blockIdx.x, nsteps);
+  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+  double* slots = kSmemMat ? gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld : nullptr;
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, slots);
 }
 
 template <bool kSmemMat>
@@ -68,6 +70,7 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
   const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
   double* mat = kSmemMat ? reinterpret_cast<double*>(smem_raw)
                          : gws + (size_t)blockIdx.x * (mat_bytes / sizeof(double));
+  double* slots = gws;   // squaring engine (kSmemMat): gws holds the parked operands of LagPlan
   unsigned char* vec = kSmemMat ? smem_raw + mat_bytes : smem_raw;
   Smem s = carve(P, mat, vec);
   DeviceExec ex(s.red);
@@ -86,7 +89,9 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
     });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = (kSmemMat && method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, method == MCD_METHOD_SQUARING, Pb, &sw)
+    const double ll = (kSmemMat && method >= MCD_METHOD_SQUARING)
+                          ? ch.evaluate_sq(s.v, s.w, s.lag, P.plan[0], slots + (size_t)blockIdx.x * P.plan[0].nslots * P.np * P.ld,
+                                           0, method == MCD_METHOD_SQUARING, Pb, &sw)
                                                                   : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
@@ -194,6 +199,7 @@ int64_t mcd_launch_count(const mcd_handle* h) { return h ? h->launches : 0; }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+
 int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, mcd_problem** out) {
   if (!h || !d || !out) return MCD_E_ARG;
   if (d->n < 3 || d->n > 508 || d->nlag < 1 || d->nlag > kMaxLag) return MCD_E_ARG;
@@ -256,10 +262,9 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     double hl[kMaxLag];
     CUDA_TRY(cudaMemcpyAsync(hl, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    int ok = p->in_smem && hl[0] > 0.0;
-    for (int l = 1; l < d->nlag && ok; ++l)
-      if (!(fabs(hl[l] - (l + 1) * hl[0]) <= 1e-12 * hl[l])) ok = 0;
-    p->squaring_ok = ok;
+    plan_lags(hl, d->nlag, false, &P.plan[0]);
+    plan_lags(hl, d->nlag, true, &P.plan[1]);
+    p->squaring_ok = p->in_smem && P.plan[0].ok && P.plan[1].ok;
   }
   p->smem_bytes = p->in_smem ? full : smem_vectors_bytes(np);
   if (!p->in_smem && ntiles > kThreads) {
@@ -311,10 +316,14 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   const Problem& P = p->P;
   if (p->in_smem) {
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
+    if (method >= MCD_METHOD_SQUARING && P.plan[0].nslots > 0) {
+      int rc = ensure_gws(h, (size_t)grid * P.plan[0].nslots * P.np * P.ld * sizeof(double));
+      if (rc != MCD_OK) return rc;
+    }
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
     mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
-                                                                     status, nullptr);
+                                                                     status, h->gws);
   } else {
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
     int rc = ensure_gws(h, (size_t)grid * smem_matrix_bytes(P.np, P.ld));
@@ -344,14 +353,19 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   ChainIO cio;
   std::memcpy(&mp, params, sizeof(mp));
   std::memcpy(&cio, io, sizeof(cio));
-  const bool sq_ok = p->squaring_ok && !mp.move_timezero;
+  const bool sq_ok = p->squaring_ok;
   if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (mp.method < MCD_METHOD_EIGEN || mp.method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
   if (mp.method >= MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
   if (p->in_smem) {
+    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+    if (mp.method >= MCD_METHOD_SQUARING && pl.nslots > 0) {
+      int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));
+      if (rc != MCD_OK) return rc;
+    }
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, nullptr);
+    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
   } else {
     const int ntiles = (P.np / 4) * (P.np / 4 + 1) / 2;
     if (ntiles > kThreads) mp.refresh_every = 1;  // always cold: warm product needs one tile per thread

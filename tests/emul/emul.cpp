@@ -52,6 +52,8 @@ void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
   P.svecs = d->string_vecs;
   P.spring_k = d->spring_k;
   P.clip = d->clip;
+  plan_lags(d->lagtimes, d->nlag, false, &P.plan[0]);
+  plan_lags(d->lagtimes, d->nlag, true, &P.plan[1]);
 }
 }  // namespace
 
@@ -78,7 +80,8 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     s.sc->status = 0;
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
-    out_ll[b] = (method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, 0, method == MCD_METHOD_SQUARING, Pb, &sw)
+    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
+    out_ll[b] = (method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, P.plan[0], slots.data(), 0, method == MCD_METHOD_SQUARING, Pb, &sw)
                                                 : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
     if (status) status[b] = (int)s.sc->status;
     if (sweeps) sweeps[b] = sw;
@@ -104,7 +107,8 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
     Smem s = carve(P, mat.data(), vec.data());
     HostExec ex(store.data());
     Chain<HostExec> ch(ex, P, s);
-    ch.run(mp, cio, c, nsteps);
+    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
+    ch.run(mp, cio, c, nsteps, slots.data());
   }
   return 0;
 }
@@ -122,6 +126,13 @@ void emul_fast_log(const double* x, double* y, int n) {
   Chain<HostExec> ch(ex, P, s);
   ch.build_tables();
   for (int i = 0; i < n; ++i) y[i] = ch.fast_log(x[i]);
+}
+
+int emul_plan(const double* lag, int L, int shifted, int* out) {
+  LagPlan pl;
+  plan_lags(lag, L, shifted != 0, &pl);
+  out[0] = pl.ok; out[1] = pl.fast; out[2] = pl.nchain; out[3] = pl.nslots;
+  return 0;
 }
 
 void emul_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {

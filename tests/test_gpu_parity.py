@@ -96,12 +96,11 @@ def test_random_profiles_all_fixtures(engine, gold_ll):
         ll, _, st = prob.loglike(v, w)
         assert not st.any()
         np.testing.assert_allclose(ll, ref, rtol=RTOL)
-        if prob.squaring_ok:       # lag times 20 | 10,20,30,40: the squaring engine applies
-            ll2, _, st2 = prob.loglike(v, w, method=METHODS["squaring"])
+        assert prob.squaring_ok    # incl. lags 5, 12.5 (no progression: two squaring chains)
+        for m in ("squaring", "squaring_dfma"):
+            ll2, _, st2 = prob.loglike(v, w, method=METHODS[m])
             assert not st2.any()
             np.testing.assert_allclose(ll2, ref, rtol=RTOL)
-        else:                      # 5, 12.5 is no arithmetic progression
-            assert list(lags) == [5.0, 12.5]
     # flat start of the 4-lag fixture (-23355.373632376784)
     prob = DeviceProblem(engine, G["P_counts"], G["P_lags"], True)
     ll, _, _ = prob.loglike(np.zeros(100), G["P_flat_w"])
@@ -141,8 +140,6 @@ def test_replay_against_reference_trajectories(engine, gold_replay, tag, method)
     from mcdiff_b200.engine import ChainBatch
     case = replay_case(gold_replay, tag)
     g = case["g"]
-    if method != "eigen" and case["move_timezero"]:
-        pytest.skip("time-offset moves run on the eigen engine")
     prob = _problem(engine, case)
     nch = 3
     ch = ChainBatch(prob, nch)
@@ -312,14 +309,40 @@ def test_engines_agree_step_by_step(engine):
         np.testing.assert_allclose(out["eigen"][2]["v"], out[other][2]["v"], atol=1e-13)
 
 
-def test_squaring_rejects_unsupported(engine, gold_ll):
+def test_squaring_general_lag_sets(engine, gold_ll):
+    """Lag sets that are no arithmetic progression, unsorted, with duplicates (replica files of the
+    same lag), and the shipped 11-lag pattern: the squaring engine plans chains / parked operands."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    G = gold_ll
+    v, w = G["rand_v"][:2], G["rand_wP"][:2]
+    for lags in ([10.0, 20.0, 35.0, 40.0], [10.0, 20.0, 20.0, 40.0], [40.0, 10.0, 30.0, 20.0], [7.5, 20.0, 30.0, 45.0]):
+        prob = DeviceProblem(engine, G["P_counts"], lags, True)
+        assert prob.squaring_ok
+        ll, P, st = prob.loglike(v, w, method=METHODS["squaring"], want_P=True)
+        assert not st.any()
+        ref = [O.log_like_lag(v[b], w[b], lags, G["P_counts"], True) for b in range(2)]
+        np.testing.assert_allclose(ll, ref, rtol=RTOL)
+        Pref = O.propagator(v[0], w[0], lags[2], True)
+        assert np.max(np.abs(P[0, 2] - Pref)) <= RTOL * np.max(Pref)
+    lags11 = [1.0, 2.0, 3.0, 4.0, 5.0, 10.0, 15.0, 20.0, 30.0, 40.0, 50.0]
+    counts11 = np.concatenate([G["P_counts"], G["P_counts"], G["P_counts"][:3]])
+    prob = DeviceProblem(engine, counts11, lags11, True)
+    ll, _, st = prob.loglike(v, w, method=METHODS["squaring"])
+    ref = [O.log_like_lag(v[b], w[b], lags11, counts11, True) for b in range(2)]
+    np.testing.assert_allclose(ll, ref, rtol=RTOL)
+
+
+def test_squaring_rejects_unsupported(engine):
+    """n = 200 does not fit the shared-memory work matrices: SQUARING is refused, AUTO falls back."""
     from mcdiff_b200.engine import DeviceProblem
     from mcdiff_b200._capi import McdError
-    G = gold_ll
-    prob = DeviceProblem(engine, G["S_counts"], G["S_lags"], True)     # lags 5, 12.5
-    assert not prob.squaring_ok
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 5, size=(1, 200, 200))
+    prob = DeviceProblem(engine, counts, [10.0], True)
+    assert not prob.squaring_ok and not prob.in_smem
     with pytest.raises(McdError):
-        prob.loglike(G["S_v"], G["S_w"], method=METHODS["squaring"])
+        prob.loglike(np.zeros(200), np.zeros(200), method=METHODS["squaring"])
 
 
 @pytest.mark.parametrize("tag", ["radbin", "radcos"])
