@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _capi as K
 from .model import MODELS_1D, Model, RadCosinusModel, RadModel
-from .outreading import read_Dcoeffs, read_Fcoeffs, read_F_D_edges, read_dv_dw
+from .outreading import read_Dcoeffs, read_Dradcoeffs, read_Drad, read_Fcoeffs, read_F_D_edges, read_dv_dw
 from .parallel import shard_range
 
 
@@ -133,6 +133,23 @@ class MCState:
                 raise AssertionError("initfile has %d D values, model has %d" % (len(D), len(m.w)))
             print("USING initfile for w", initfile, len(D), "values")
             m.w = np.log(D) - m.wunit
+        if self.do_radial:                    # lib/MCState.py:170-197
+            if getattr(m, "ncosDrad", 0) > 0:
+                c = read_Dradcoeffs(initfile, final=True)
+                if len(c) == 0:
+                    c = read_Dcoeffs(initfile, final=True)     # the reference falls back to w_coeff
+                if len(c) > 0:
+                    print("USING initfile for wrad_coeff", initfile, len(c), "coeffs")
+                    k = min(len(c), m.ncosDrad)
+                    m.wrad_coeff[:k] = c[:k]
+                    m.wrad_coeff[0] -= m.wradunit
+                    m.update_wrad()
+            else:
+                Drad, redges = read_Drad(initfile)
+                if len(Drad) != len(m.wrad):
+                    raise AssertionError("initfile has %d Drad values, model has %d" % (len(Drad), len(m.wrad)))
+                print("USING initfile for wrad", initfile, len(Drad), "values")
+                m.wrad = np.log(Drad) - m.wradunit
         read_dv_dw(initfile, final=True)      # read but not applied, like lib/MCState.py:199-201
 
     # ---- device set-up -----------------------------------------------------------------------
@@ -140,11 +157,26 @@ class MCState:
         if self.chains is not None:
             return
         from .engine import ChainBatch, DeviceProblem, Engine
-        if self.do_radial:
-            raise NotImplementedError("radial Monte-Carlo moves are not part of this build; the radial "
-                                      "likelihood is available as engine.rad_loglike")
         m = self.model
         self.engine = Engine(self.device)
+        if self.do_radial:
+            from .engine import RadialChains
+            ncos = getattr(m, "ncosDrad", 0)
+            self.chains = RadialChains(self.engine, m.v, m.w, self.pbc, self.data.list_lt, self.data.list_trans,
+                                       m.bessels, m.bessel0_zeros, self.nchains,
+                                       wrad_basis=m.wrad_basis if ncos > 0 else None)
+            wrad = np.tile(m.wrad, (self.nchains, 1))
+            wc = np.tile(m.wrad_coeff, (self.nchains, 1)) if ncos > 0 else None
+            if self.jitter > 0:
+                rng = np.random.default_rng(self.seed ^ 0x5DEECE66D)
+                skip = 1 if self.rank == 0 else 0
+                if ncos > 0:
+                    wc[skip:] += self.jitter * rng.standard_normal(wc[skip:].shape)
+                    wrad = wc @ m.wrad_basis.T
+                else:
+                    wrad[skip:] += self.jitter * rng.standard_normal(wrad[skip:].shape)
+            self.chains.set_state(wrad, wc, dwrad=self.dwrad, temp=self.temp)
+            return
         svecs = _string_vecs(m.dim_w, self.pbc) if self.k > 0 else None
         self.string_vecs = svecs
         counts = np.asarray(self.data.list_trans)
@@ -187,6 +219,8 @@ class MCState:
             self.naccv_coeff = np.zeros(m.ncosF, int)
         if m.ncosD > 0:
             self.naccw_coeff = np.zeros(m.ncosD, int)
+        if self.do_radial and getattr(m, "ncosDrad", 0) > 0:
+            self.naccwrad_coeff = np.zeros(m.ncosDrad, int)
         return ll
 
     # ---- the hot loop: lib/mc.py:27-51 on the GPU ------------------------------------------------
@@ -212,6 +246,13 @@ class MCState:
         self._ensure_device()
         first = self.steps_done
         nsamp = (first + nsteps) // 100 - first // 100 if want_samples else 0
+        if self.do_radial:
+            _, _, smp = self.chains.run(nsteps, num_mc_update=float(self.num_MC_update), dtemp=float(self.dtemp),
+                                        seed=self.seed & 0xFFFFFFFFFFFFFFFF, chain_offset=self.chain_lo,
+                                        nsamples_cap=nsamp)
+            self.steps_done += nsteps
+            self.sync_from_device()
+            return None if smp is None else smp.cpu().numpy()
         _, _, smp = self.chains.run(nsteps, self.mc_params(), nsamples_cap=nsamp)
         self.steps_done += nsteps
         self.sync_from_device()
@@ -219,6 +260,21 @@ class MCState:
 
     def sync_from_device(self):
         st = self.chains.host_state()
+        if self.do_radial:
+            m = self.model
+            sc, ct = st["scal"], st["counters"]
+            self.chain_wrad, self.chain_wrad_coeff = st["wrad"], st["wcoef"]
+            self.chain_log_like = sc[:, 0].copy()
+            self.chain_dwrad, self.chain_temp = sc[:, 1].copy(), sc[:, 2].copy()
+            self.chain_naccwrad, self.chain_status = ct[:, 0].copy(), ct[:, 3].copy()
+            m.wrad = st["wrad"][0].copy()
+            if getattr(m, "ncosDrad", 0) > 0:
+                m.wrad_coeff = st["wcoef"][0].copy()
+                self.naccwrad_coeff = st["nacc_coeff"][0].copy()
+            self.log_like = float(sc[0, 0])
+            self.dwrad, self.temp = float(sc[0, 1]), float(sc[0, 2])
+            self.naccwrad = int(ct[0, 0])
+            return
         self.chain_v, self.chain_w = st["v"], st["w"]
         self.chain_v_coeff, self.chain_w_coeff = st["vcoef"], st["wcoef"]
         sc, ct = st["scal"], st["counters"]
@@ -284,8 +340,15 @@ class MCState:
                 for i, val in enumerate(arr):
                     print("%8d %8d %5.1f %s %5.1f %s" % (i, val, float(val) / tot * 100, "%",
                                                         float(val) / self.nmc * 100, "%"), file=f)
+        if self.do_radial and getattr(m, "ncosDrad", 0) > 0:
+            tot = max(1, np.sum(self.naccwrad_coeff))
+            print("naccwrad_coeff", file=f)
+            for i, val in enumerate(self.naccwrad_coeff):
+                print("%8d %8d %5.1f %s %5.1f %s" % (i, val, float(val) / tot * 100, "%",
+                                                    float(val) / self.nmc * 100, "%"), file=f)
         if self.nchains > 1:
-            acc = (self.chain_naccv + self.chain_naccw) / float(max(1, self.nmc))
+            acc = ((self.chain_naccwrad if self.do_radial else self.chain_naccv + self.chain_naccw)
+                   / float(max(1, self.nmc)))
             print("===== Statistics over %d chains =====" % self.nchains, file=f)
             print("acceptance mean/min/max %6.3f %6.3f %6.3f" % (acc.mean(), acc.min(), acc.max()), file=f)
             print("log-like   mean/min/max", self.chain_log_like.mean(), self.chain_log_like.min(),
@@ -294,11 +357,13 @@ class MCState:
     def print_coeffs_laststate(self, f, final=False):
         from .log import print_coeffs
         m = self.model
-        print_coeffs(f, m, m.v_coeff if m.ncosF > 0 else None, m.w_coeff if m.ncosD > 0 else None, None,
+        wrad_coeff = m.wrad_coeff if (self.do_radial and getattr(m, "ncosDrad", 0) > 0) else None
+        print_coeffs(f, m, m.v_coeff if m.ncosF > 0 else None, m.w_coeff if m.ncosD > 0 else None, wrad_coeff,
                      m.timezero if self.move_timezero else None, final=final)
 
     def print_laststate(self, f, final=False):
         from .log import print_profiles
         self.print_MC_params(f, final=final)
         self.print_coeffs_laststate(f, final=final)
-        print_profiles(f, self.model, self.model.v, self.model.w, wrad=None, final=final)
+        print_profiles(f, self.model, self.model.v, self.model.w, wrad=self.model.wrad if self.do_radial else None,
+                       final=final)

@@ -51,7 +51,10 @@ class Engine:
         """Host array -> device tensor through pinned memory (async on the current stream)."""
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
         if t.dtype != dtype:
             t = t.to(dtype)
         return t.pin_memory().to(self.device, non_blocking=True)

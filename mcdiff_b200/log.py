@@ -76,6 +76,31 @@ class Logger:
         else:
             self.w[a:b] = pw
 
+    def fill_rows_radial(self, chain, first_row, rows, MC):
+        """rows: [k][3 + nw] = {log_like, dwrad, temp, wrad | wrad_coeff}; v, w are frozen in radial runs."""
+        k = rows.shape[0]
+        if k == 0:
+            return
+        m = MC.model
+        a = chain * self.nf_chain + first_row
+        b = a + k
+        self.log_like[a:b] = rows[:, 0]
+        self.dwrad[a:b] = rows[:, 1]
+        self.temp[a:b] = rows[:, 2]
+        self.dv[a:b], self.dw[a:b], self.dtimezero[a:b] = MC.dv, MC.dw, MC.dtimezero
+        if m.ncosF > 0:
+            self.v_coeff[a:b] = m.v_coeff
+        else:
+            self.v[a:b] = m.v
+        if m.ncosD > 0:
+            self.w_coeff[a:b] = m.w_coeff
+        else:
+            self.w[a:b] = m.w
+        if getattr(m, "ncosDrad", 0) > 0:
+            self.wrad_coeff[a:b] = rows[:, 3:]
+        else:
+            self.wrad[a:b] = rows[:, 3:]
+
     def chain_rows(self, chain):
         return slice(chain * self.nf_chain, (chain + 1) * self.nf_chain)
 

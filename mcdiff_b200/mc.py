@@ -33,6 +33,8 @@ def do_mc_cycles(MC, logger, chunk=1000):
     MC.init_log_like()
     MC.sync_from_device()
     m = MC.model
+    if MC.do_radial:
+        return _do_mc_cycles_radial(MC, logger, chunk)
     # row 0 = initial state (logger.log(0, MC), lib/mc.py:25)
     nv = m.ncosF if m.ncosF > 0 else m.dim_v
     nw = m.ncosD if m.ncosD > 0 else m.dim_w
@@ -59,6 +61,54 @@ def do_mc_cycles(MC, logger, chunk=1000):
     logger.dwrad[:] = MC.dwrad
 
 
+def _finish_radial(MC, logger, outfile, nmc, rank):
+    local = np.concatenate([MC.chain_log_like[:, None], MC.chain_dwrad[:, None],
+                            MC.chain_naccwrad[:, None].astype(float), MC.chain_status[:, None].astype(float),
+                            MC.chain_wrad], axis=1)
+    allrows = all_gather_rows(local, MC.nchains_total)
+    if rank != 0:
+        return MC, logger
+    if outfile is None:
+        MC.print_statistics(f=sys.stdout)
+        MC.print_laststate(sys.stdout, final=True)
+        picfile = "mc.pic"
+    else:
+        with open(outfile, "w") as f:
+            MC.print_statistics(f=sys.stdout)
+            MC.print_laststate(f, final=True)
+        picfile = outfile + ".pic"
+    logger.model = MC.model
+    logger.dump(picfile)
+    write_average_from_pic(picfile, picfile + ".ave.dat")
+    np.savez_compressed((outfile or "mc") + ".chains.npz", log_like=allrows[:, 0], dwrad=allrows[:, 1],
+                        naccwrad=allrows[:, 2], status=allrows[:, 3], wrad=allrows[:, 4:],
+                        edges=np.asarray(MC.model.edges), nmc=nmc, seed=MC.seed)
+    return MC, logger
+
+
+def _do_mc_cycles_radial(MC, logger, chunk):
+    """lib/mc.py:29-30: only MCState.mcmove_diffusion_radial is called."""
+    m = MC.model
+    ncos = getattr(m, "ncosDrad", 0)
+    pw = MC.chain_wrad_coeff if ncos > 0 else MC.chain_wrad
+    nw = ncos if ncos > 0 else m.dim_wrad
+    row0 = np.zeros((1, 3 + nw))
+    for c in range(MC.nchains):
+        row0[0, :3] = (MC.chain_log_like[c], MC.chain_dwrad[c], MC.chain_temp[c])
+        row0[0, 3:] = pw[c][:nw]
+        logger.fill_rows_radial(c, 0, row0, MC)
+    done, next_row = 0, 1
+    while done < MC.nmc:
+        n = min(chunk, MC.nmc - done)
+        samples = MC.advance(n)
+        done += n
+        if samples is not None and samples.shape[1] > 0:
+            for c in range(MC.nchains):
+                logger.fill_rows_radial(c, next_row, samples[c], MC)
+            next_row += samples.shape[1]
+        MC.print_intermediate(done - 1)
+
+
 def find_parameters(filenames, pbc, model, dv, dw, dwrad, D0, dtimezero, temp, temp_end, nmc, nmc_update, seed,
                     outfile, ncosF, ncosD, ncosDrad, move_timezero, initfile, k, lmax, reduction, pull,
                     nchains=1, device=None, method="auto", jitter=0.0, chunk=1000):
@@ -78,6 +128,8 @@ def find_parameters(filenames, pbc, model, dv, dw, dwrad, D0, dtimezero, temp, t
 
     # ---- one collective: per-chain summaries of every rank (lib/mc.py has a single chain) ----
     m = MC.model
+    if MC.do_radial:
+        return _finish_radial(MC, logger, outfile, nmc, rank)
     pv = MC.chain_v_coeff if m.ncosF > 0 else MC.chain_v
     pw = MC.chain_w_coeff if m.ncosD > 0 else MC.chain_w
     local = np.concatenate([MC.chain_log_like[:, None], MC.chain_dv[:, None], MC.chain_dw[:, None],

@@ -115,3 +115,40 @@ def test_initial_nan_raises_like_reference(engine, gold_ll):
     ch.set_state(v, np.tile(G["P_flat_w"], (2, 1)), dv=0.1, dw=0.1)
     with pytest.raises(ValueError, match="Initial likelihood diverges"):
         ch.init_log_like()
+
+
+def test_radial_find_parameters(engine, tmp_path, capsys):
+    """run-mcdiff --rad LMAX --model RadCosinusModel: radial MC on the device, `===== final Drad =====`
+    section readable by read_Drad, chain 0 equal to the reference trajectory fixture's start."""
+    from mcdiff_b200 import outreading as outr
+    from mcdiff_b200.log import load_logger
+    from mcdiff_b200.mc import find_parameters
+    from mcdiff_b200.transitions import write_Tmat_cube
+    RR = np.load(os.path.join(os.path.dirname(__file__), "golden", "radial_replay_golden.npz"))
+    g = lambda k: RR["radcos/" + k]  # noqa: E731
+    counts, lags = g("counts"), g("lags")
+    nr, dim_rad, lmax = counts.shape[-1], int(g("dim_rad")), int(g("lmax"))
+    tmp = str(tmp_path)
+    edges = np.linspace(-4.0, 4.0, nr + 1)
+    redges = np.arange(dim_rad) * 0.5
+    files = []
+    for il, lag in enumerate(lags):
+        fn = os.path.join(tmp, "rad.%d.dat" % il)
+        write_Tmat_cube(counts[il].astype(int), fn, float(lag), "pbc", edges=edges, redges=redges, dt=1.0, dn=int(lag))
+        files.append(fn)
+    out = os.path.join(tmp, "rad.out.dat")
+    MC, lg = find_parameters(files, True, "RadCosinusModel", 0.5, 0.5, 0.4, 1.0, 0.1, 1.0, 1.0, 200, 40.0, 9, out,
+                             0, 0, 4, False, None, -1, lmax, False, None, nchains=3)
+    text = capsys.readouterr().out
+    ll_first = float([l for l in text.splitlines() if l.startswith("initial log-likelihood:")][0].split()[-1])
+    assert ll_first == pytest.approx(float(g("ll0")), rel=1e-9)        # same start as the reference fixture
+    assert MC.log_like > ll_first and MC.naccwrad > 0 and not MC.chain_status.any()
+    Drad, redg = outr.read_Drad(out)
+    np.testing.assert_allclose(Drad, np.exp(MC.model.wrad + MC.model.wradunit), rtol=1e-8)
+    assert "===== final wrad_coeff =====" in open(out).read()
+    lgr = load_logger(out + ".pic")
+    assert lgr.wrad_coeff.shape == (3 * 3, 4)
+    Da, _ = outr.read_Drad(out + ".pic.ave.dat")
+    assert len(Da) == nr
+    ch = np.load(out + ".chains.npz")
+    assert ch["wrad"].shape == (3, nr) and len(np.unique(ch["log_like"])) == 3
