@@ -309,7 +309,7 @@ struct Chain {
       // two A fragments serve all of its MMAs.  wtab[w] = {nt, na, rowA, rowB, jb[8]}: tiles
       // t < na belong to rowA, na <= t < nt to rowB, t >= nt are padding (computed, not used).
       {
-        const int nb8 = P.np / 8, cap = 8, maxw = kThreads / 32;
+        const int nb8 = P.np / 8, cap = (kThreads >= 512) ? 6 : 8, maxw = kThreads / 32;
         unsigned char sib[64], sjb[64], sln[64], used[64];
         int nseg = 0;
         for (int ib = 0; ib < nb8; ++ib)
@@ -799,7 +799,7 @@ struct Chain {
   // 8 consecutive upper-triangular 8x8 tiles (row-major, so the A fragment is mostly reused) and
   // keeps their 2-doubles-per-lane accumulators in registers; results are register-staged and
   // written back in place after the barrier, like the DFMA version.
-  static constexpr int kTilesPerWarp = 8;
+  static constexpr int kTilesPerWarp = (kThreads >= 512) ? 6 : 8;
   MCD_HD bool dmma_ok() const { return s.sc->mma_tasks > 0; }
 
 #if defined(__CUDA_ARCH__)

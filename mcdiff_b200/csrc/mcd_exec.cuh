@@ -20,7 +20,10 @@
 
 namespace mcd {
 
-constexpr int kThreads = 384;   // 12 warps, 3 per SM sub-partition
+#ifndef MCD_THREADS
+#define MCD_THREADS 384
+#endif
+constexpr int kThreads = MCD_THREADS;   // 12 warps, 3 per SM sub-partition (512 / 6 tiles per warp measured slower)
 constexpr int kMaxRegs = 16;    // per-thread doubles that must survive a barrier
 
 struct d2 {

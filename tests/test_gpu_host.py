@@ -152,3 +152,28 @@ def test_radial_find_parameters(engine, tmp_path, capsys):
     assert len(Da) == nr
     ch = np.load(out + ".chains.npz")
     assert ch["wrad"].shape == (3, nr) and len(np.unique(ch["log_like"])) == 3
+
+
+def test_lag_scan_concurrent_streams(engine, gold_ll, tmp_path, capsys):
+    """BASELINE config 4 shape: independent single-lag problems on concurrent CUDA streams, then the
+    mcdiff-infty extrapolation.  Each problem's chain 0 equals the same problem run alone."""
+    from mcdiff_b200.infty import extrapolate, run_lag_scan
+    from mcdiff_b200.mc import find_parameters
+    from mcdiff_b200 import outreading as outr
+    G = gold_ll
+    tmp = str(tmp_path)
+    files = _files(tmp, G)
+    by_lag = {float(l): f for l, f in zip(G["P_lags"], files)}
+    outs = run_lag_scan(by_lag, os.path.join(tmp, "scan"), ncosF=6, ncosD=4, dv=0.2, dw=0.2, nmc=200, nmc_update=100.0,
+                        seed=21, nchains=64)
+    assert [os.path.basename(o) for o in outs] == ["out.nbins100.%d.pbc.dat" % l for l in (10, 20, 30, 40)]
+    # problem k alone (seed + k), same chain 0
+    alone = os.path.join(tmp, "alone.dat")
+    find_parameters([files[2]], True, "CosinusModel", 0.2, 0.2, 0.5, 1.0, 0.1, 1.0, 1.0, 200, 100.0, 23, alone,
+                    6, 4, 0, False, None, -1, -1, False, None, nchains=64)
+    capsys.readouterr()
+    np.testing.assert_array_equal(outr.read_Fcoeffs(outs[2], final=True), outr.read_Fcoeffs(alone, final=True))
+    np.testing.assert_array_equal(outr.read_F_D_edges(outs[2])[1], outr.read_F_D_edges(alone)[1])
+    lts, Dreal, t0 = extrapolate(outs, os.path.join(tmp, "hexd."))
+    np.testing.assert_array_equal(lts, [10.0, 20.0, 30.0, 40.0])
+    assert Dreal.shape == (100,) and np.all(np.isfinite(Dreal))

@@ -222,3 +222,44 @@ def test_philox_tape_index_ranges():
     np.testing.assert_array_equal(u2, u[100:110])               # counter-based: resumable anywhere
     u3, _ = philox.chain_tape(1, 6, 0, 10, 100, 100, 10, 6)
     assert not np.array_equal(u3, u[:10])
+
+
+def test_infty_fit_equals_reference_lstsq(tmp_path):
+    """Closed-form per-bin fit == the reference's big lstsq (scripts/mcdiff-infty:99-117)."""
+    from mcdiff_b200.infty import extract_lagtimes_from_filenames, fit_line_inverse, extrapolate
+    rng = np.random.default_rng(4)
+    lts = np.array([1.0, 2.0, 5.0, 10.0, 20.0, 50.0])
+    nb = 12
+    Dtrue, t0true = rng.uniform(0.2, 1.0, nb), rng.uniform(0.5, 3.0, nb)
+    D = Dtrue[:, None] * (1.0 + t0true[:, None] / lts[None, :]) + rng.normal(0, 1e-3, (nb, len(lts)))
+    A = np.zeros((nb * len(lts), 2 * nb))
+    res = np.zeros(nb * len(lts))
+    for i, lt in enumerate(lts):            # the reference's design matrix
+        for j in range(nb):
+            res[i * nb + j] = D[j, i]
+            A[i * nb + j, j] = 1.0
+            A[i * nb + j, j + nb] = 1.0 / lt
+    x = np.linalg.lstsq(A, res, rcond=-1)[0]
+    Dreal, t0 = fit_line_inverse(lts, D)
+    np.testing.assert_allclose(Dreal, x[:nb], rtol=1e-10)
+    np.testing.assert_allclose(t0, x[nb:] / x[:nb], rtol=1e-9)
+    np.testing.assert_allclose(Dreal, Dtrue, atol=5e-3)
+    names = ["/x/out.nbins100.%d.pbc.dat" % l for l in (1, 20, 50)]
+    np.testing.assert_array_equal(extract_lagtimes_from_filenames(names), [1.0, 20.0, 50.0])
+    # end to end on result files written in the reference's profile format
+    from mcdiff_b200 import log as mlog
+
+    class M:
+        pbc, dim_v, wunit = True, nb, 0.0
+        edges = np.arange(nb + 1.0)
+    files = []
+    for i, lt in enumerate(lts):
+        fn = os.path.join(str(tmp_path), "out.nbins%d.%d.pbc.dat" % (nb, int(lt)))
+        with open(fn, "w") as f:
+            mlog.print_profiles(f, M, np.zeros(nb), np.log(D[:, i]), final=True)
+        files.append(fn)
+    l2, Dr2, t2 = extrapolate(files, os.path.join(str(tmp_path), "sys."))
+    np.testing.assert_allclose(Dr2, Dreal, rtol=1e-6)
+    assert os.path.exists(os.path.join(str(tmp_path), "sys.Dreal.dat")) and os.path.exists(os.path.join(str(tmp_path), "sys.t0.dat"))
+    row = open(os.path.join(str(tmp_path), "sys.Dreal.dat")).read().splitlines()
+    assert row[0] == "   index  bin-str  bin-end" and row[-1] == "=" * 10
