@@ -655,12 +655,16 @@ struct Chain {
   MCD_HD double pair_term(double g, int ns, int i, int j, const int* cnt) const {
     if (ns == 0) return 0.0;
     if (g >= s.sc->gmin) return (double)ns * fast_log(g);
-    const int np = P.np;
-    const double clip = P.clip;
+    return pair_term_clipped(g, ns, i, j, cnt, P.np, P.clip, s.ea, s.eb, s.hv);
+  }
+  // Rare branch (an entry below the clip), kept out of line and free of `this`: the epilogues are
+  // unrolled 16-32 times per thread and the kernel is instruction-cache sensitive.
+  static MCD_NOINLINE double pair_term_clipped(double g, int ns, int i, int j, const int* cnt, int np, double clip,
+                                               const double* ea, const double* eb, const double* hv) {
     if (i == j) return (double)ns * log(fmax(g, clip));
     const int nij = cnt[(size_t)i * np + j], nji = cnt[(size_t)j * np + i];
-    const double pij = s.ea[i] * g * s.eb[j], pji = s.ea[j] * g * s.eb[i];
-    double part = -(double)(nij - nji) * (s.hv[j] - s.hv[i]);   // undo this pair's share of sc->lin
+    const double pij = ea[i] * g * eb[j], pji = ea[j] * g * eb[i];
+    double part = -(double)(nij - nji) * (hv[j] - hv[i]);   // undo this pair's share of sc->lin
     if (nij != 0) part += (double)nij * log(fmax(pij, clip));
     if (nji != 0) part += (double)nji * log(fmax(pji, clip));
     return part;

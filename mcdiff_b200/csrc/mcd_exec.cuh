@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define MCD_HD __device__ __forceinline__
 #define MCD_HOSTDEV __host__ __device__ inline
+#define MCD_NOINLINE __device__ __noinline__
 #else
 #define MCD_HD inline
 #define MCD_HOSTDEV inline
+#define MCD_NOINLINE inline
 #endif
 
 namespace mcd {

@@ -1,0 +1,26 @@
+"""Config-3 shape (n = 200, 8 lags, ncosF = 12, ncosD = 8): time per MC step on the generic path."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mcdiff_b200 import _capi as K
+from mcdiff_b200.engine import Engine, DeviceProblem, ChainBatch
+from oracle import mcdiff_oracle as O
+
+n = 200
+lags = (5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0)
+counts, lags, edges, F, w_true = O.synthetic_counts(n=n, lags=lags, seed=3, total=1.0e6)
+vb, wb = O.cos_basis_center(n, 12), O.cos_basis_border(n, n, 8)
+eng = Engine(0)
+prob = DeviceProblem(eng, counts, lags, True, v_basis=vb, w_basis=wb)
+nch = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+ch = ChainBatch(prob, nch)
+wc0 = np.zeros(8); wc0[0] = -np.log(0.25)
+ch.set_state(np.zeros(n), wb @ wc0, np.zeros(12), wc0, dv=0.05, dw=0.05)
+t = time.time(); ch.init_log_like(); torch.cuda.synchronize(); print("init_log_like %.3f s" % (time.time() - t))
+mp = K.McParams(); mp.num_mc_update = 1000.0; mp.min_lt = 5.0; mp.sample_every = 100; mp.refresh_every = 512; mp.seed = 1
+ch.run(2, mp); torch.cuda.synchronize()
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+t = time.time(); ch.run(nsteps, mp); torch.cuda.synchronize(); el = time.time() - t
+st = ch.host_state()
+print("n=200 L=8: %d chains x %d steps in %.3f s -> %.1f MC steps/s, %.2f ms per step per wave, sweeps/step %.2f, status %s, in_smem %s squaring_ok %s" % (
+    nch, nsteps, el, nch * nsteps / el, 1e3 * el / nsteps, st["counters"][:, 7].sum() / st["counters"][:, 5].sum(), st["counters"][:, 6].any(), prob.in_smem, prob.squaring_ok))
