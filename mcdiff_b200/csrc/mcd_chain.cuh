@@ -43,6 +43,7 @@ struct LagPlan {
 struct Problem {
   int n, np, ld, dim_w, pbc, nlag;
   int ncosF, ncosD;
+  int nbk, lds, blocked;   // shared-memory panel size and pitch (= np, ld unless blocked), see set_layout
   const double* lagtimes;  // [nlag]
   const int* counts;       // [nlag][np][np]  (padded, counts[l][i][j] = # transitions j -> i)
   const int* nsym;         // [nlag][np][np]  N_ij + N_ji (i != j), N_ii on the diagonal
@@ -165,6 +166,19 @@ struct ChainIO {
 MCD_HOSTDEV int padded_bins(int n) { return (n + 7) & ~7; }
 MCD_HOSTDEV int leading_dim(int np) { return np + 4; }
 
+// Largest bin count whose two work matrices fit in shared memory; up to twice that the squaring
+// engine runs blocked: matrices live in a per-CTA global workspace (L2) and are multiplied as
+// 2 x 2 blocks whose nbk x nbk panels are staged through the two shared-memory buffers.
+constexpr int kMaxSmemBins = 104;
+MCD_HOSTDEV void set_layout(Problem& P, int n) {
+  P.n = n;
+  P.blocked = (n > kMaxSmemBins && n <= 2 * kMaxSmemBins) ? 1 : 0;
+  P.np = P.blocked ? ((n + 15) & ~15) : padded_bins(n);
+  P.ld = leading_dim(P.np);
+  P.nbk = P.blocked ? P.np / 2 : P.np;
+  P.lds = leading_dim(P.nbk);
+}
+
 MCD_HOSTDEV int sample_dim(const Problem& P) {
   return 6 + (P.ncosF > 0 ? P.ncosF : P.n) + (P.ncosD > 0 ? P.ncosD : P.dim_w);
 }
@@ -226,13 +240,16 @@ MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
   return (bytes + 15) & ~(size_t)15;
 }
 MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
+// global workspace of one chain of the blocked squaring engine: 3 work matrices + the plan's slots
+MCD_HOSTDEV size_t blocked_ws_doubles(const Problem& P, int nslots) { return (size_t)(3 + nslots) * P.np * P.ld; }
 
 // mat: storage for XT and B2 (2*np*ld doubles; shared or global), vec: shared storage.
-MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
+// panels: mat holds the two nbk x lds operand panels of the blocked squaring engine.
+MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels = false) {
   Smem s;
   const int np = P.np;
   s.XT = mat;
-  s.B2 = mat + (size_t)np * P.ld;
+  s.B2 = mat + (panels ? (size_t)P.nbk * P.lds : (size_t)np * P.ld);
   double* d = reinterpret_cast<double*>(vec);
   s.a = d; d += np;
   s.b = d; d += np;
@@ -272,7 +289,7 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <class Exec>
+template <class Exec, bool kBlocked = false>
 struct Chain {
   Exec& ex;
   const Problem& P;
@@ -292,7 +309,7 @@ struct Chain {
       }
     });
     ex.single([&]() {
-      const int nb = P.np / 4;
+      const int nb = kBlocked ? 0 : P.np / 4;
       int t = 0;
       for (int pi = 0; pi < nb; pi += 4)
         for (int pj = (pi / 8) * 8; pj < nb; pj += 8)
@@ -309,7 +326,7 @@ struct Chain {
       // two A fragments serve all of its MMAs.  wtab[w] = {nt, na, rowA, rowB, jb[8]}: tiles
       // t < na belong to rowA, na <= t < nt to rowB, t >= nt are padding (computed, not used).
       {
-        const int nb8 = P.np / 8, cap = (kThreads >= 512) ? 6 : 8, maxw = kThreads / 32;
+        const int nb8 = P.nbk / 8, cap = (kThreads >= 512) ? 6 : 8, maxw = kThreads / 32;
         unsigned char sib[64], sjb[64], sln[64], used[64];
         int nseg = 0;
         for (int ib = 0; ib < nb8; ++ib)
@@ -355,7 +372,7 @@ struct Chain {
         }
         s.sc->mma_tasks = ok ? nw : 0;
       }
-      const int h = P.np / 2;
+      const int h = kBlocked ? 0 : P.np / 2;
       int q = 0;
       for (int ka = 0; ka < h; ++ka)
         for (int kb = ka + 1; kb < h; ++kb) {
@@ -941,6 +958,23 @@ struct Chain {
     }
   }
 
+  // Taylor order of the squaring engines.  T_m(x) = e^x (1 - x^(m+1)/(m+1)! ...) per eigenmode, and the
+  // error is amplified 2^s times by the squarings -- but only modes with t |lambda| <= 45 survive in
+  // G(t) at all (e^-45 = 3e-20), i.e. |x| <= x* = min(1, 45 / 2^s).  Smallest m with
+  // 2^s x*^(m+1)/(m+1)! <= 1e-17.
+  static MCD_HD int taylor_order(int nsq, int taylor_m) {
+    if (taylor_m > 0) return taylor_m;
+    const double two_s = ldexp(1.0, nsq);
+    const double xs = fmin(1.0, 45.0 / two_s);
+    double term = two_s * xs;   // 2^s x^(k) / k!  for k = 1
+    int m = 1;
+    while (m < 24 && !(term * xs / (double)(m + 1) <= 1.0e-17)) {
+      term = term * xs / (double)(m + 1);
+      ++m;
+    }
+    return m < 6 ? 6 : m;
+  }
+
   // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
   // exp(t S) by Taylor + squarings.  Uses both work buffers; returns the one holding the result
   // (*other receives the second one).  epi >= 0: the likelihood terms of lag index epi are added
@@ -953,21 +987,7 @@ struct Chain {
     int nsq = 0;
     for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
     const double h = ldexp(t, -nsq);
-    // Taylor order.  T_m(x) = e^x (1 - x^(m+1)/(m+1)! ...) per eigenmode, and the error is amplified
-    // 2^s times by the squarings -- but only modes with t |lambda| <= 45 survive in G(t) at all
-    // (e^-45 = 3e-20), i.e. |x| <= x* = min(1, 45 / 2^s).  Smallest m with 2^s x*^(m+1)/(m+1)! <= 1e-17.
-    int m = taylor_m;
-    if (m <= 0) {
-      const double two_s = ldexp(1.0, nsq);
-      const double xs = fmin(1.0, 45.0 / two_s);
-      double term = two_s * xs;   // 2^s x^(k) / k!  for k = 1
-      m = 1;
-      while (m < 24 && !(term * xs / (double)(m + 1) <= 1.0e-17)) {
-        term = term * xs / (double)(m + 1);
-        ++m;
-      }
-      if (m < 6) m = 6;
-    }
+    const int m = taylor_order(nsq, taylor_m);
     double* A = s.XT;
     double* B = s.B2;
     // ---- T_m(hS) by Horner:  H <- I + (hS H)/k, k = m..1, ping-pong ----
@@ -1139,6 +1159,317 @@ struct Chain {
     return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
   }
 
+  // ------------------------------------------------------------------------------------
+  // Blocked squaring engine (kBlocked, kMaxSmemBins < n <= 2 kMaxSmemBins).
+  // The np x np matrices (np = 2 nbk) live in a per-CTA global workspace that stays in L2; a product
+  //   C_IJ = sum_K X_KI^T Y_KJ      (I, J, K in {0, 1}; X, Y symmetric and commuting)
+  // is done block by block with the nbk x nbk operand panels staged in the two shared-memory buffers
+  // and the m8n8k4 loop of the in-smem engine.  Diagonal blocks use the symmetric warp tasks of
+  // build_tables, the off-diagonal block C_01 is cut into tasks of 2 tile rows x 4 tile columns;
+  // C_10 is stored as its transpose.  The K = 0 partial sums are parked in the destination and
+  // picked up again by the same lane at K = 1, which also carries the likelihood epilogue.
+  // ------------------------------------------------------------------------------------
+  MCD_HD void blk_load(double* dA, const double* GA, int KA, int IA, double* dB, const double* GB, int KB, int IB) {
+    const int nbk = P.nbk, lds = P.lds, ldg = P.ld, half = nbk / 2;
+    const double* sa = dA ? GA + (size_t)KA * nbk * ldg + IA * nbk : nullptr;
+    const double* sb = dB ? GB + (size_t)KB * nbk * ldg + IB * nbk : nullptr;
+    ex.par([&](int tid) {
+      for (int e = tid; e < nbk * half; e += Exec::nthr()) {
+        const int r = e / half, c = (e - r * half) * 2;
+        if (sa) { const d2 x = ld2(sa + (size_t)r * ldg + c); st2(dA + r * lds + c, x.x, x.y); }
+        if (sb) { const d2 y = ld2(sb + (size_t)r * ldg + c); st2(dB + r * lds + c, y.x, y.y); }
+      }
+    });
+  }
+
+  // One block: D (+)= A^T B.  sym: diagonal block (upper tiles, mirrored inside the block on the final
+  // pass); otherwise the full block, whose transpose goes to Dt on the final pass.  (i_off, j_off):
+  // position of the block in the full matrix (likelihood epilogue).
+  MCD_HD void blk_mma(const double* A, const double* B, bool sym, double* D, double* Dt, bool first, bool fin,
+                      int i_off, int j_off, const int* cnt, const int* nsy, double* Pl) {
+    const int n = P.n, np = P.np, ldg = P.ld, lds = P.lds, nbk = P.nbk, nb8 = nbk / 8;
+    const int ncg = (nb8 + 3) / 4, nrp = (nb8 + 1) / 2;
+    const int ntask = sym ? s.sc->mma_tasks : ncg * nrp;
+    const int nwarp = Exec::nthr() / 32;
+    const bool epi = fin && cnt != nullptr;
+    for (int base = 0; base < ntask; base += nwarp) {
+      ex.par([&](int tid) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int q = base + warp;
+        const bool active = q < ntask;
+        int nt = 0, na = 1, rowA = 0, rowB = 0;
+        int jbs[kTilesPerWarp];
+        if (sym) {
+          const unsigned char* wt = s.wtab + 16 * warp;
+          if (active) { nt = wt[0]; na = wt[1]; rowA = wt[2]; rowB = wt[3]; }
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) jbs[t] = active ? wt[4 + t] : 0;
+        } else {
+          const int rp = active ? q / ncg : 0, cg = active ? q - rp * ncg : 0;
+          const int col0 = 4 * cg, ncol = (nb8 - col0 < 4) ? nb8 - col0 : 4;
+          const bool two = 2 * rp + 1 < nb8;
+          rowA = 2 * rp; rowB = two ? rowA + 1 : rowA;
+          na = ncol; nt = active ? (two ? 2 * ncol : ncol) : 0;
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) jbs[t] = col0 + ((t < nt) ? (t < na ? t : t - na) : 0);
+        }
+        const int fr = lane >> 2, fk = lane & 3;
+        double c[kTilesPerWarp][2];
+        int nsv[kTilesPerWarp][2];
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          const int ib = (t < na) ? rowA : rowB;
+          const int i = ib * 8 + fr, j = jbs[t] * 8 + 2 * fk;
+          c[t][0] = 0.0; c[t][1] = 0.0;
+          if (!first && t < nt) { const d2 x = ld2(D + (size_t)i * ldg + j); c[t][0] = x.x; c[t][1] = x.y; }
+          nsv[t][0] = 0; nsv[t][1] = 0;
+          if (epi && t < nt) {
+            const int* qn = nsy + (size_t)(i_off + i) * np + j_off + j;
+            nsv[t][0] = qn[0]; nsv[t][1] = qn[1];
+          }
+        }
+        if (active) {
+#if defined(__CUDA_ARCH__)
+          int offB[kTilesPerWarp];
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = jbs[t] * 64;
+          const unsigned ax = (unsigned)__cvta_generic_to_shared(A) + (unsigned)(fk * lds + fr) * 8u;
+          const unsigned ay = (unsigned)__cvta_generic_to_shared(B) + (unsigned)(fk * lds + fr) * 8u;
+          const int pitch4 = 4 * lds * 8, nk4 = nbk / 4;
+          switch (na) {
+            case 1: mma_loop<1>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 2: mma_loop<2>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 3: mma_loop<3>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 4: mma_loop<4>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 5: mma_loop<5>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 6: mma_loop<6>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 7: mma_loop<7>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            default: mma_loop<8>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+          }
+#else
+          for (int t = 0; t < nt; ++t) {
+            const int ib = (t < na) ? rowA : rowB;
+            const int i = ib * 8 + fr;
+            for (int e = 0; e < 2; ++e) {
+              const int j = jbs[t] * 8 + 2 * fk + e;
+              double acc = c[t][e];
+              for (int k = 0; k < nbk; ++k) acc = fma(A[k * lds + i], B[k * lds + j], acc);
+              c[t][e] = acc;
+            }
+          }
+#endif
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          if (t < nt) {
+            const int ib = (t < na) ? rowA : rowB, jb = jbs[t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+            if (epi) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int gi = i_off + i, gj = j_off + j + e;
+                if (sym && ib == jb && gj < gi) continue;
+                part += pair_term(c[t][e], nsv[t][e], gi, gj, cnt);
+                if (Pl && gi < n && gj < n) {
+                  Pl[(size_t)gi * n + gj] = s.ea[gi] * c[t][e] * s.eb[gj];
+                  Pl[(size_t)gj * n + gi] = s.ea[gj] * c[t][e] * s.eb[gi];
+                }
+              }
+            }
+            st2(D + (size_t)i * ldg + j, c[t][0], c[t][1]);
+            if (fin) {
+              if (!sym) {
+                Dt[(size_t)j * ldg + i] = c[t][0];
+                Dt[(size_t)(j + 1) * ldg + i] = c[t][1];
+              } else if (ib != jb) {
+                D[(size_t)j * ldg + i] = c[t][0];
+                D[(size_t)(j + 1) * ldg + i] = c[t][1];
+              }
+            }
+          }
+        }
+        if (epi) s.part[tid] += part;
+      });
+    }
+  }
+
+  // Dg <- Xg Yg for symmetric commuting matrices in the global workspace (Dg distinct from both).
+  // cnt != nullptr: Dg is the kernel of a lag time, its likelihood terms are added to s.part.
+  MCD_HD void blk_product(const double* Xg, const double* Yg, double* Dg, const int* cnt, const int* nsy, double* Pl) {
+    const int nbk = P.nbk, ldg = P.ld;
+    const bool same = (Xg == Yg);
+    for (int K = 0; K < 2; ++K)
+      for (int blk = 0; blk < 3; ++blk) {   // C_00, C_01 (+ C_10), C_11: one call site of blk_mma
+        const int I = (blk == 2) ? 1 : 0, J = (blk == 0) ? 0 : 1;
+        const double* A;
+        const double* B;
+        if (same) {   // XT = X_K0, B2 = X_K1 serve all three blocks
+          if (blk == 0) blk_load(s.XT, Xg, K, 0, s.B2, Xg, K, 1);
+          A = I ? s.B2 : s.XT;
+          B = J ? s.B2 : s.XT;
+        } else {      // XT = X_KI, B2 = Y_KJ
+          if (blk == 0) blk_load(s.XT, Xg, K, 0, s.B2, Yg, K, 0);
+          else if (blk == 1) blk_load(nullptr, nullptr, 0, 0, s.B2, Yg, K, 1);
+          else blk_load(s.XT, Xg, K, 1, nullptr, nullptr, 0, 0);
+          A = s.XT;
+          B = s.B2;
+        }
+        blk_mma(A, B, I == J, Dg + (size_t)I * nbk * ldg + J * nbk, Dg + (size_t)J * nbk * ldg + I * nbk, K == 0, K == 1,
+                I * nbk, J * nbk, cnt, nsy, Pl);
+      }
+  }
+
+  // likelihood terms of a kernel sitting in the global workspace (pairs i <= j)
+  MCD_HD void blk_buffer_loglike(const double* G, const int* cnt, const int* nsy, double* Pl) {
+    const int n = P.n, np = P.np, ldg = P.ld;
+    ex.par([&](int tid) {
+      double part = 0.0;
+      for (int e = tid; e < n * n; e += Exec::nthr()) {
+        const int i = e / n, j = e - i * n;
+        if (j < i) continue;
+        const double g = G[(size_t)i * ldg + j];
+        part += pair_term(g, nsy[(size_t)i * np + j], i, j, cnt);
+        if (Pl) {
+          Pl[(size_t)i * n + j] = s.ea[i] * g * s.eb[j];
+          Pl[(size_t)j * n + i] = s.ea[j] * g * s.eb[i];
+        }
+      }
+      s.part[tid] += part;
+    });
+  }
+
+  MCD_HD void blk_copy(double* dst, const double* src) {
+    const int total = P.np * P.ld;
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < total; e += 2 * Exec::nthr()) {
+        const d2 x = ld2(src + e);
+        st2(dst + e, x.x, x.y);
+      }
+    });
+  }
+
+  // log L with the blocked engine.  ws: blocked_ws_doubles(P, pl.nslots) doubles of this chain.
+  MCD_HD double evaluate_blk(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* ws,
+                             int taylor_m, double* Pout, int* squarings_out) {
+    const int n = P.n, np = P.np, ldg = P.ld;
+    const size_t nn = (size_t)n * n, melems = (size_t)np * ldg;
+    double* buf[3] = {ws, ws + melems, ws + 2 * melems};
+    double* slots = ws + 3 * melems;
+    build_S(v, w);
+    const double gersh = ex.max([&](int tid) {
+      double m = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) {
+        const int im = (i == 0) ? n - 1 : i - 1;
+        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+        m = (r > m || r != r) ? r : m;
+      }
+      return m;
+    });
+    ex.par([&](int tid) { s.part[tid] = 0.0; });
+    int nsq_total = 0;
+    bool bad = false;
+    const int l0 = pl.order[0];
+    const bool fast = pl.fast != 0;
+    double* R = nullptr;
+    // ---- squaring chains (the G(t_0) chain last): Horner in buf[0]/buf[1], squarings rotate
+    //      through the three buffers ----
+    for (int c = 0; c < pl.nchain && !bad; ++c) {
+      const bool is_first_lag = (c == pl.nchain - 1);
+      const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
+      const double rho = t * gersh;
+      if (!(rho < 1.0e9) || !(t > 0.0)) { bad = true; break; }
+      int nsq = 0;
+      for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
+      const double h = ldexp(t, -nsq);
+      const int m = taylor_order(nsq, taylor_m);
+      double* src = buf[0];
+      double* dst = buf[1];
+      ex.par([&](int tid) {
+        for (int e = tid * 2; e < np * ldg; e += 2 * Exec::nthr()) { st2(src + e, 0.0, 0.0); st2(dst + e, 0.0, 0.0); }
+      });
+      ex.par([&](int tid) {
+        for (int i = tid; i < n; i += Exec::nthr()) src[(size_t)i * ldg + i] = 1.0;
+      });
+      const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
+      const int rows_per_pass = Exec::nthr() / tpr;
+      for (int tt = 1; tt <= m; ++tt) {
+        const double f = h / (double)(m - tt + 1);
+        const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
+        const bool full = (width == n);
+        ex.par([&](int tid) {
+          const int r = tid % tpr;
+          for (int i = tid / tpr; i < n; i += rows_per_pass) {
+            const int im = (i == 0) ? n - 1 : i - 1;
+            const int ip = (i == n - 1) ? 0 : i + 1;
+            const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.b[i];
+            const double* s0 = src + (size_t)i * ldg;
+            const double* sm = src + (size_t)im * ldg;
+            const double* sp = src + (size_t)ip * ldg;
+            double* d0 = dst + (size_t)i * ldg;
+            for (int dd = r; dd < width; dd += tpr) {
+              int j;
+              if (full) j = dd;
+              else {
+                j = i - tt + dd;
+                if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
+                else if (j < 0 || j >= n) continue;
+              }
+              d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
+            }
+          }
+        });
+        double* tmp = src; src = dst; dst = tmp;
+      }
+      double* G = src;
+      double* O = dst;
+      const int* cnt_e = is_first_lag ? P.counts + (size_t)l0 * np * np : nullptr;
+      const int* nsy_e = is_first_lag ? P.nsym + (size_t)l0 * np * np : nullptr;
+      double* Pl0 = (is_first_lag && Pout) ? Pout + (size_t)l0 * nn : nullptr;
+      for (int q = 0; q < nsq; ++q) {
+        const bool last = (q + 1 == nsq);
+        blk_product(G, G, O, last ? cnt_e : nullptr, last ? nsy_e : nullptr, last ? Pl0 : nullptr);
+        double* tmp = G; G = O; O = tmp;
+      }
+      if (nsq == 0 && is_first_lag) blk_buffer_loglike(G, cnt_e, nsy_e, Pl0);
+      nsq_total += nsq;
+      if (!fast && pl.chain_slot[c] >= 0) blk_copy(slots + (size_t)pl.chain_slot[c] * melems, G);
+      R = G;
+    }
+    // ---- remaining lags: R <- R G(delta_i), out of place into one of the two buffers that do not
+    //      hold G(t_0) (the operand of the fast plan) ----
+    if (!bad) {
+      double* G0 = R;
+      double* fr[2];
+      int nf = 0;
+      for (int b = 0; b < 3; ++b) if (buf[b] != G0) fr[nf++] = buf[b];
+      int which = 0;
+      for (int i = 1; i < P.nlag; ++i) {
+        const int l = pl.order[i];
+        const int* cnt = P.counts + (size_t)l * np * np;
+        const int* nsy = P.nsym + (size_t)l * np * np;
+        double* Pl = Pout ? Pout + (size_t)l * nn : nullptr;
+        if (!fast && pl.op_slot[i] < 0) {
+          blk_buffer_loglike(R, cnt, nsy, Pl);
+        } else {
+          const double* Y = fast ? G0 : slots + (size_t)pl.op_slot[i] * melems;
+          double* D = fr[which];
+          if (D == R) D = fr[which ^= 1];
+          blk_product(R, Y, D, cnt, nsy, Pl);
+          R = D;
+          which ^= 1;
+        }
+        if (!fast && pl.park[i] >= 0) blk_copy(slots + (size_t)pl.park[i] * melems, R);
+      }
+    }
+    if (squarings_out) *squarings_out = bad ? -1 : nsq_total;
+    if (bad) {
+      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      return nan("");
+    }
+    return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
+  }
+
   // Full likelihood of the profile (v, w) at lag times lagt.
   // mode 0: warm start from the eigenvectors in XT, 1: cold start, 2: reuse XT/lam as they are
   // (same v, w as the last solve; only the lag times changed).
@@ -1214,7 +1545,7 @@ struct Chain {
       for (int l = tid; l < P.nlag; l += Exec::nthr()) s.lag[l] = P.lagtimes[l] + sc->timezero;
     });
     int have_basis = 0;
-    if (io.basis && io.basis_valid[chain]) {
+    if (!kBlocked && io.basis && io.basis_valid[chain]) {
       const double* src = io.basis + (size_t)chain * np * ld;
       ex.par([&](int tid) {
         for (int e = tid; e < np * ld; e += Exec::nthr()) s.XT[e] = src[e];
@@ -1342,7 +1673,9 @@ struct Chain {
 
         int sw = 0;
         double ll_new;
-        if (mp.method >= 2) {
+        if constexpr (kBlocked) {
+          ll_new = evaluate_blk(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, nullptr, &sw);
+        } else if (mp.method >= 2) {
           ll_new = evaluate_sq(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, mp.method == 2,
                                nullptr, &sw);
         } else {

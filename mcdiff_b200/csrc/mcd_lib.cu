@@ -32,8 +32,10 @@ struct mcd_problem {
   Problem P;       // device pointers below are owned by this object
   void* blob;      // one allocation holding all private copies
   int in_smem;
-  int squaring_ok;  // lag times in arithmetic progression, work matrices in shared memory
+  int squaring_ok;  // a LagPlan exists and the work matrices (or their panels, `blocked`) fit in shared memory
+  int blocked;      // squaring engine runs blocked (kMaxSmemBins < n <= 2 kMaxSmemBins)
   size_t smem_bytes;
+  size_t blk_smem_bytes;
 };
 
 #define CUDA_TRY(x)                          \
@@ -93,6 +95,50 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
                           ? ch.evaluate_sq(s.v, s.w, s.lag, P.plan[0], slots + (size_t)blockIdx.x * P.plan[0].nslots * P.np * P.ld,
                                            0, method == MCD_METHOD_SQUARING, Pb, &sw)
                                                                   : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    ex.par([&](int tid) {
+      if (tid == 0) {
+        out_ll[b] = ll;
+        if (status) status[b] = (int)s.sc->status;
+      }
+    });
+  }
+}
+
+// Blocked squaring engine: operand panels in shared memory, matrices in the per-CTA slice of gws.
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec, true> ch(ex, P, s);
+  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * blocked_ws_doubles(P, pl.nslots));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
+                       double* __restrict__ out_ll, double* __restrict__ out_P, int* __restrict__ status, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec, true> ch(ex, P, s);
+  ch.build_tables();
+  const int n = P.n, np = P.np, dim_w = P.dim_w;
+  double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, P.plan[0].nslots);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += kThreads) {
+        s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
+        s.w[i] = (i < dim_w) ? w[(size_t)b * dim_w + i] : 0.0;
+      }
+      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = P.lagtimes[l];
+      if (tid == 0) s.sc->status = 0;
+    });
+    int sw = 0;
+    double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
+    const double ll = ch.evaluate_blk(s.v, s.w, s.lag, P.plan[0], ws, 0, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -210,11 +256,12 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int n = d->n, dim_w = d->pbc ? n : n - 1;
-  const int np = padded_bins(n), ld = leading_dim(np);
 
   mcd_problem* p = new (std::nothrow) mcd_problem();
   if (!p) return MCD_E_NOMEM;
   p->h = h;
+  set_layout(p->P, n);
+  const int np = p->P.np, ld = p->P.ld;
   const size_t b_lag = align256((size_t)d->nlag * 8);
   const size_t b_cnt = align256((size_t)d->nlag * np * np * 4);
   const size_t b_rv = align256((size_t)np * 8);
@@ -246,7 +293,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
 
   Problem& P = p->P;
-  P.n = n; P.np = np; P.ld = ld; P.dim_w = dim_w; P.pbc = d->pbc ? 1 : 0; P.nlag = d->nlag;
+  P.dim_w = dim_w; P.pbc = d->pbc ? 1 : 0; P.nlag = d->nlag;
   P.ncosF = d->ncosF; P.ncosD = d->ncosD;
   P.lagtimes = lag; P.counts = cnt; P.nsym = nsym; P.rvec = rvec;
   P.v_basis = d->ncosF > 0 ? vb : nullptr;
@@ -264,7 +311,9 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     CUDA_TRY(cudaStreamSynchronize(st));
     plan_lags(hl, d->nlag, false, &P.plan[0]);
     plan_lags(hl, d->nlag, true, &P.plan[1]);
-    p->squaring_ok = p->in_smem && P.plan[0].ok && P.plan[1].ok;
+    p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np);
+    p->blocked = (P.blocked && p->blk_smem_bytes <= (size_t)h->max_smem_optin) ? 1 : 0;
+    p->squaring_ok = (p->in_smem || p->blocked) && P.plan[0].ok && P.plan[1].ok;
   }
   p->smem_bytes = p->in_smem ? full : smem_vectors_bytes(np);
   if (!p->in_smem && ntiles > kThreads) {
@@ -314,7 +363,15 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const Problem& P = p->P;
-  if (p->in_smem) {
+  if (p->blocked && method >= MCD_METHOD_SQUARING) {
+    if (method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
+    const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+    int rc = ensure_gws(h, (size_t)grid * blocked_ws_doubles(P, P.plan[0].nslots) * sizeof(double));
+    if (rc != MCD_OK) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->blk_smem_bytes));
+    mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, out_ll, out_P, status, h->gws);
+  } else if (p->in_smem) {
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
     if (method >= MCD_METHOD_SQUARING && P.plan[0].nslots > 0) {
       int rc = ensure_gws(h, (size_t)grid * P.plan[0].nslots * P.np * P.ld * sizeof(double));
@@ -357,7 +414,15 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (mp.method < MCD_METHOD_EIGEN || mp.method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
   if (mp.method >= MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
-  if (p->in_smem) {
+  if (p->blocked && mp.method >= MCD_METHOD_SQUARING) {
+    if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
+    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+    int rc = ensure_gws(h, (size_t)nchains * blocked_ws_doubles(P, pl.nslots) * sizeof(double));
+    if (rc != MCD_OK) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->blk_smem_bytes));
+    mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+  } else if (p->in_smem) {
     const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
     if (mp.method >= MCD_METHOD_SQUARING && pl.nslots > 0) {
       int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));

@@ -1,4 +1,5 @@
-"""Config-3 shape (n = 200, 8 lags, ncosF = 12, ncosD = 8): time per MC step on the generic path."""
+"""Config-3 shape (n = 200, 8 lags, ncosF = 12, ncosD = 8): time per MC step.
+usage: prof_n200.py [nchains] [nsteps] [method: 1 eigen on global matrices, 2 blocked tensor-core squaring]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -18,9 +19,10 @@ wc0 = np.zeros(8); wc0[0] = -np.log(0.25)
 ch.set_state(np.zeros(n), wb @ wc0, np.zeros(12), wc0, dv=0.05, dw=0.05)
 t = time.time(); ch.init_log_like(); torch.cuda.synchronize(); print("init_log_like %.3f s" % (time.time() - t))
 mp = K.McParams(); mp.num_mc_update = 1000.0; mp.min_lt = 5.0; mp.sample_every = 100; mp.refresh_every = 512; mp.seed = 1
+mp.method = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 ch.run(2, mp); torch.cuda.synchronize()
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 t = time.time(); ch.run(nsteps, mp); torch.cuda.synchronize(); el = time.time() - t
 st = ch.host_state()
-print("n=200 L=8: %d chains x %d steps in %.3f s -> %.1f MC steps/s, %.2f ms per step per wave, sweeps/step %.2f, status %s, in_smem %s squaring_ok %s" % (
+print("method %d" % mp.method, "n=200 L=8: %d chains x %d steps in %.3f s -> %.1f MC steps/s, %.2f ms per step per wave, sweeps/step %.2f, status %s, in_smem %s squaring_ok %s" % (
     nch, nsteps, el, nch * nsteps / el, 1e3 * el / nsteps, st["counters"][:, 7].sum() / st["counters"][:, 5].sum(), st["counters"][:, 6].any(), prob.in_smem, prob.squaring_ok))

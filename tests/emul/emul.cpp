@@ -25,8 +25,10 @@ struct HostProblem {
 
 void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
   Problem& P = hp.P;
-  const int n = d->n, np = padded_bins(n);
-  P.n = n; P.np = np; P.ld = leading_dim(np); P.pbc = d->pbc ? 1 : 0; P.dim_w = d->pbc ? n : n - 1;
+  const int n = d->n;
+  set_layout(P, n);
+  const int np = P.np;
+  P.pbc = d->pbc ? 1 : 0; P.dim_w = d->pbc ? n : n - 1;
   P.nlag = d->nlag; P.ncosF = d->ncosF; P.ncosD = d->ncosD;
   hp.counts.assign((size_t)d->nlag * np * np, 0);
   for (int l = 0; l < d->nlag; ++l)
@@ -67,6 +69,27 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
   std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
   std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
   std::vector<double> store((size_t)kThreads * kMaxRegs);
+  if (P.blocked && method == MCD_METHOD_SQUARING) {   // blocked squaring engine (panels + global workspace)
+    Smem s = carve(P, mat.data(), vec.data(), true);
+    HostExec ex(store.data());
+    Chain<HostExec, true> ch(ex, P, s);
+    ch.build_tables();
+    std::vector<double> ws(blocked_ws_doubles(P, P.plan[0].nslots));
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < P.np; ++i) {
+        s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
+        s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
+      }
+      for (int l = 0; l < P.nlag; ++l) s.lag[l] = P.lagtimes[l];
+      s.sc->status = 0;
+      int sw = 0;
+      double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
+      out_ll[b] = ch.evaluate_blk(s.v, s.w, s.lag, P.plan[0], ws.data(), 0, Pb, &sw);
+      if (status) status[b] = (int)s.sc->status;
+      if (sweeps) sweeps[b] = sw;
+    }
+    return 0;
+  }
   Smem s = carve(P, mat.data(), vec.data());
   HostExec ex(store.data());
   Chain<HostExec> ch(ex, P, s);
@@ -103,6 +126,17 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
   std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
   std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
   std::vector<double> store((size_t)kThreads * kMaxRegs);
+  if (P.blocked && mp.method == MCD_METHOD_SQUARING) {
+    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+    std::vector<double> ws(blocked_ws_doubles(P, pl.nslots));
+    for (int c = 0; c < nchains; ++c) {
+      Smem s = carve(P, mat.data(), vec.data(), true);
+      HostExec ex(store.data());
+      Chain<HostExec, true> ch(ex, P, s);
+      ch.run(mp, cio, c, nsteps, ws.data());
+    }
+    return 0;
+  }
   for (int c = 0; c < nchains; ++c) {
     Smem s = carve(P, mat.data(), vec.data());
     HostExec ex(store.data());
@@ -117,7 +151,7 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
 void emul_fast_log(const double* x, double* y, int n) {
   Problem P;
   std::memset(&P, 0, sizeof(P));
-  P.n = 8; P.np = 8; P.ld = 12; P.nlag = 1; P.dim_w = 8; P.pbc = 1;
+  set_layout(P, 8); P.nlag = 1; P.dim_w = 8; P.pbc = 1;
   std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
   std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
   std::vector<double> store((size_t)kThreads * kMaxRegs);

@@ -109,3 +109,68 @@ def test_fast_log_accuracy():
     ref = np.log(x)
     # 1 ulp of the result (libm's own error is up to 1 ulp as well)
     assert np.all(np.abs(y - ref) <= 4e-16 + 2.3e-16 * np.abs(ref))
+
+
+def _blocked_problem(n, lags, pbc, seed=3):
+    from oracle import mcdiff_oracle as O
+    rng = np.random.default_rng(seed)
+    if pbc:
+        counts = O.synthetic_counts(n, lags, seed=seed, total=2.0e5, dz=1.0)[0]
+    else:
+        counts = rng.integers(0, 50, size=(len(lags), n, n)).astype(np.int32)
+        ii, jj = np.indices((n, n))
+        counts[:, np.abs(ii - jj) > 12] = 0
+    return counts, rng
+
+
+@pytest.mark.parametrize("n,lags,pbc", [(120, (5.0, 10.0, 15.0), True), (200, (5.0, 10.0, 20.0, 40.0), True),
+                                        (136, (3.0, 7.0, 10.0), False), (106, (10.0,), True),
+                                        (208, (5.0, 10.0), True)])
+def test_blocked_squaring_engine(n, lags, pbc):
+    """104 < n <= 208: matrices in a global workspace, 2 x 2 block products through the
+    shared-memory panels (fast plan, general plans with parked operands, non-periodic, a single
+    lag, the largest size) against the oracle."""
+    from oracle import mcdiff_oracle as O
+    lags = np.array(lags)
+    counts, rng = _blocked_problem(n, lags, pbc)
+    dim_w = n if pbc else n - 1
+    v = rng.normal(0, 0.5, (2, n))
+    w = rng.normal(-1.0, 0.3, (2, dim_w))
+    prob = H.HostProblem(counts, lags, pbc)
+    ll, P, st, nsq = H.loglike_batch(prob, v, w, want_P=True, method=SQUARING)
+    assert not st.any() and (nsq > 0).all()
+    for b in range(2):
+        np.testing.assert_allclose(ll[b], O.log_like_lag(v[b], w[b], lags, counts, pbc), rtol=1e-12)
+        for l, lt in enumerate(lags):
+            Pref = O.propagator(v[b], w[b], lt, pbc)
+            assert np.max(np.abs(P[b, l] - Pref)) < 1e-13
+    ll_e, _, st, _ = H.loglike_batch(prob, v[:1], w[:1], method=EIGEN)      # same problem, global-memory eigen path
+    np.testing.assert_allclose(ll_e[0], ll[0], rtol=1e-9)   # eigen route: absolute, not componentwise, accuracy
+
+
+def test_blocked_engine_mc_replay():
+    """MC loop on the blocked engine (n = 120, cosine model, time-offset moves, lag set that
+    needs a parked operand): decisions equal the oracle replay of the same tape."""
+    from oracle import mcdiff_oracle as O
+    n, lags = 120, np.array([5.0, 10.0, 20.0])
+    counts, rng = _blocked_problem(n, lags, True, seed=5)
+    vb, wb = O.cos_basis_center(n, 5), O.cos_basis_border(n, n, 4)
+    wc0 = np.zeros(4)
+    wc0[0] = -1.0
+    w0 = wb @ wc0
+    cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=0.2, dw=0.2, dtimezero=0.3, temp=1.0, nmc=24,
+                        num_mc_update=10.0, move_timezero=True)
+    tu, ti = O.make_tape(np.random.default_rng(11), 24, cfg)
+    ref = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(5), w_coeff0=wc0)
+    prob = H.HostProblem(counts, lags, True, v_basis=vb, w_basis=wb)
+    ll0 = O.log_like_lag(np.zeros(n), w0, lags, counts, True)
+    ch = H.HostChains(prob, 1, np.zeros(n), w0, np.zeros(5), wc0, ll0=ll0, dv=0.2, dw=0.2, dt0=0.3)
+    mp = K.McParams()
+    mp.num_mc_update, mp.dtemp, mp.min_lt, mp.move_timezero = 10.0, 0.0, 5.0, 1
+    mp.sample_every, mp.refresh_every, mp.use_tape, mp.method = 100, 16, 1, SQUARING
+    dec, llt, _ = ch.run(24, mp, tu, ti)
+    assert np.array_equal(dec[0] & 1, ref["accepted"])
+    assert np.array_equal((dec[0] >> 1) & 1, ref["accepted_t0"])
+    assert ref["accepted"].any() and ref["accepted_t0"].any()
+    np.testing.assert_allclose(ch.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
+    np.testing.assert_allclose(ch.scal[0, K.S_T0], ref["timezero"], rtol=1e-13)

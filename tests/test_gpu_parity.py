@@ -270,20 +270,94 @@ def test_radial_likelihood(engine, gold_radial):
 
 def test_large_n_generic_path(engine):
     """n = 200, 8 lags (BASELINE config 3 shape): the work matrices do not fit in shared
-    memory, the generic global-memory path must give the same numbers."""
+    memory.  The eigen engine runs on global work matrices, the squaring engine blocked (2 x 2
+    blocks through shared-memory panels); both must give the oracle's numbers."""
     from mcdiff_b200.engine import DeviceProblem
     from oracle import mcdiff_oracle as O
     lags = (5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0)
     counts, lags, edges, F, w_true = O.synthetic_counts(n=200, lags=lags, seed=3, total=2.0e5)
     prob = DeviceProblem(engine, counts, lags, True)
-    assert not prob.in_smem
+    assert not prob.in_smem and prob.squaring_ok
     rng = np.random.default_rng(1)
     v = F[None, :] + rng.normal(0, 0.2, (3, 200))
     w = w_true[None, :] + rng.normal(0, 0.2, (3, 200))
-    ll, _, st = prob.loglike(v, w)
-    assert not st.any()
     ref = [O.log_like_lag(v[b], w[b], lags, counts, True) for b in range(3)]
-    np.testing.assert_allclose(ll, ref, rtol=RTOL)
+    for method in ("eigen", "squaring"):
+        ll, P, st = prob.loglike(v, w, want_P=True, method=METHODS[method])
+        assert not st.any()
+        np.testing.assert_allclose(ll, ref, rtol=RTOL)
+        for l in (0, 7):
+            Pref = O.propagator(v[1], w[1], lags[l], True)
+            assert np.max(np.abs(P[1, l] - Pref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,lags,pbc", [(120, (5.0, 10.0, 15.0), True), (200, (5.0, 10.0, 20.0, 40.0), True),
+                                        (136, (3.0, 7.0, 10.0), False), (106, (10.0,), True),
+                                        (208, (5.0, 10.0), True), (168, (4.0, 4.0, 9.0), True)])
+def test_blocked_squaring_engine(engine, n, lags, pbc):
+    """104 < n <= 208 on the tensor-core squaring engine: fast and general lag plans, non-periodic,
+    single lag, duplicate lag, the largest size; more profiles than CTAs of one wave are not needed,
+    but several per CTA exercise the workspace reuse."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    lags = np.array(lags)
+    rng = np.random.default_rng(3)
+    if pbc:
+        counts = O.synthetic_counts(n, lags, seed=3, total=2.0e5, dz=1.0)[0]
+    else:
+        counts = rng.integers(0, 50, size=(len(lags), n, n)).astype(np.int32)
+        ii, jj = np.indices((n, n))
+        counts[:, np.abs(ii - jj) > 12] = 0
+    dim_w = n if pbc else n - 1
+    B = 5
+    v = rng.normal(0, 0.5, (B, n))
+    w = rng.normal(-1.0, 0.3, (B, dim_w))
+    prob = DeviceProblem(engine, counts, lags, pbc)
+    assert prob.squaring_ok and not prob.in_smem
+    ll, P, st = prob.loglike(v, w, want_P=True, method=METHODS["squaring"])
+    assert not st.any()
+    for b in range(B):
+        np.testing.assert_allclose(ll[b], O.log_like_lag(v[b], w[b], lags, counts, pbc), rtol=1e-12)
+    for l, lt in enumerate(lags):
+        Pref = O.propagator(v[2], w[2], lt, pbc)
+        assert np.max(np.abs(P[2, l] - Pref)) < 1e-13
+    with pytest.raises(Exception):
+        prob.loglike(v, w, method=METHODS["squaring_dfma"])
+
+
+def test_blocked_engine_mc_matches_oracle(engine):
+    """MC loop on the blocked engine (n = 120, cosine model, time-offset moves, a lag set that
+    needs a parked operand), device Philox: every chain's decisions equal the oracle replay."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from mcdiff_b200 import philox
+    from oracle import mcdiff_oracle as O
+    n, lags = 120, np.array([5.0, 10.0, 20.0])
+    counts = O.synthetic_counts(n, lags, seed=5, total=2.0e5, dz=1.0)[0]
+    vb, wb = O.cos_basis_center(n, 5), O.cos_basis_border(n, n, 4)
+    wc0 = np.zeros(4)
+    wc0[0] = -1.0
+    w0 = wb @ wc0
+    nch, nsteps, seed, off = 3, 40, 77, 10
+    prob = DeviceProblem(engine, counts, lags, True, v_basis=vb, w_basis=wb)
+    ch = ChainBatch(prob, nch)
+    ch.set_state(np.zeros(n), w0, np.zeros(5), wc0, dv=0.2, dw=0.2, dtimezero=0.3)
+    ch.init_log_like()
+    case = dict(nmc_update=10.0, dtemp=0.0, lagtimes=lags, move_timezero=True)
+    mp = _params(case, nsteps, use_tape=0, seed=seed, chain_offset=off, method=METHODS["squaring"])
+    d1, _, _ = ch.run(25, mp, record=True)
+    d2, _, _ = ch.run(15, mp, record=True)
+    dec = np.concatenate([d1.cpu().numpy(), d2.cpu().numpy()], axis=1)
+    st = ch.host_state()
+    assert not st["counters"][:, 6].any()
+    cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=0.2, dw=0.2, dtimezero=0.3, temp=1.0,
+                        nmc=nsteps, num_mc_update=10.0, move_timezero=True)
+    for c in range(nch):
+        tu, ti = philox.chain_tape(seed, off + c, 0, nsteps, n, n, 5, 4)
+        out = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(5), w_coeff0=wc0)
+        assert np.array_equal(dec[c] & 1, out["accepted"]), "chain %d" % c
+        assert np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
+        np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
+        np.testing.assert_allclose(st["scal"][c][1], out["timezero"], rtol=1e-13)
 
 
 def test_engines_agree_step_by_step(engine):
@@ -334,15 +408,20 @@ def test_squaring_general_lag_sets(engine, gold_ll):
 
 
 def test_squaring_rejects_unsupported(engine):
-    """n = 200 does not fit the shared-memory work matrices: SQUARING is refused, AUTO falls back."""
+    """n = 240 exceeds even the blocked squaring engine (n <= 208): SQUARING is refused, AUTO falls
+    back to the eigen engine on global work matrices."""
     from mcdiff_b200.engine import DeviceProblem
     from mcdiff_b200._capi import McdError
+    from oracle import mcdiff_oracle as O
     rng = np.random.default_rng(0)
-    counts = rng.integers(0, 5, size=(1, 200, 200))
+    counts = rng.integers(0, 5, size=(1, 240, 240))
     prob = DeviceProblem(engine, counts, [10.0], True)
     assert not prob.squaring_ok and not prob.in_smem
     with pytest.raises(McdError):
-        prob.loglike(np.zeros(200), np.zeros(200), method=METHODS["squaring"])
+        prob.loglike(np.zeros(240), np.zeros(240), method=METHODS["squaring"])
+    ll, _, st = prob.loglike(np.zeros(240), np.zeros(240))
+    assert not st.any()
+    np.testing.assert_allclose(ll[0], O.log_like_lag(np.zeros(240), np.zeros(240), [10.0], counts, True), rtol=RTOL)
 
 
 @pytest.mark.parametrize("tag", ["radbin", "radcos"])
