@@ -1169,16 +1169,31 @@ struct Chain {
   // C_10 is stored as its transpose.  The K = 0 partial sums are parked in the destination and
   // picked up again by the same lane at K = 1, which also carries the likelihood epilogue.
   // ------------------------------------------------------------------------------------
+  // Stage one or two nbk x nbk panels (block (K, I) of a workspace matrix) into shared memory with
+  // 16-byte cp.async copies: every thread issues all of its chunks back to back, so the L2 latency
+  // is paid once per panel instead of once per element.
   MCD_HD void blk_load(double* dA, const double* GA, int KA, int IA, double* dB, const double* GB, int KB, int IB) {
     const int nbk = P.nbk, lds = P.lds, ldg = P.ld, half = nbk / 2;
     const double* sa = dA ? GA + (size_t)KA * nbk * ldg + IA * nbk : nullptr;
     const double* sb = dB ? GB + (size_t)KB * nbk * ldg + IB * nbk : nullptr;
     ex.par([&](int tid) {
+#if defined(__CUDA_ARCH__)
+      const unsigned a0 = dA ? (unsigned)__cvta_generic_to_shared(dA) : 0u;
+      const unsigned b0 = dB ? (unsigned)__cvta_generic_to_shared(dB) : 0u;
+      for (int e = tid; e < nbk * half; e += Exec::nthr()) {
+        const int r = e / half, c = (e - r * half) * 2;
+        const unsigned so = (unsigned)(r * lds + c) * 8u;
+        if (sa) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + so), "l"(sa + (size_t)r * ldg + c) : "memory");
+        if (sb) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b0 + so), "l"(sb + (size_t)r * ldg + c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#else
       for (int e = tid; e < nbk * half; e += Exec::nthr()) {
         const int r = e / half, c = (e - r * half) * 2;
         if (sa) { const d2 x = ld2(sa + (size_t)r * ldg + c); st2(dA + r * lds + c, x.x, x.y); }
         if (sb) { const d2 y = ld2(sb + (size_t)r * ldg + c); st2(dB + r * lds + c, y.x, y.y); }
       }
+#endif
     });
   }
 
@@ -1385,6 +1400,44 @@ struct Chain {
       const int m = taylor_order(nsq, taylor_m);
       double* src = buf[0];
       double* dst = buf[1];
+      const int W = 2 * m + 1;   // band width of T_m(hS) (cyclic for pbc); storage H[i][d], column j = i - m + d
+      if (W < n && (size_t)2 * n * W <= (size_t)2 * P.nbk * P.lds) {
+        // ---- Horner on the band, ping-pong inside the (contiguous) shared-memory panels ----
+        double* ha = s.XT;
+        double* hb = s.XT + (size_t)n * W;
+        ex.par([&](int tid) {
+          for (int e = tid; e < n * W; e += Exec::nthr()) { ha[e] = (e % W == m) ? 1.0 : 0.0; hb[e] = 0.0; }
+        });
+        for (int tt = 1; tt <= m; ++tt) {
+          const double f = h / (double)(m - tt + 1);
+          const int lo = m - tt, cnt = 2 * tt + 1;   // columns touched after tt steps
+          ex.par([&](int tid) {
+            for (int e = tid; e < n * cnt; e += Exec::nthr()) {
+              const int i = e / cnt, d = lo + (e - i * cnt);
+              const int im = (i == 0) ? n - 1 : i - 1;
+              const int ip = (i == n - 1) ? 0 : i + 1;
+              // row i-1 holds column j at offset d+1, row i+1 at offset d-1
+              const double up = (d + 1 < W) ? ha[im * W + d + 1] : 0.0;
+              const double dn = (d >= 1) ? ha[ip * W + d - 1] : 0.0;
+              hb[i * W + d] = ((d == m) ? 1.0 : 0.0) + f * (s.a[i] * ha[i * W + d] + s.b[im] * up + s.b[i] * dn);
+            }
+          });
+          double* tmp = ha; ha = hb; hb = tmp;
+        }
+        // ---- expand into the dense workspace matrix ----
+        ex.par([&](int tid) {
+          for (int e = tid * 2; e < np * ldg; e += 2 * Exec::nthr()) st2(src + e, 0.0, 0.0);
+        });
+        ex.par([&](int tid) {
+          for (int e = tid; e < n * W; e += Exec::nthr()) {
+            const int i = e / W, d = e - i * W;
+            int j = i - m + d;
+            if (j < 0) j += n; else if (j >= n) j -= n;
+            const double x = ha[e];
+            if (x != 0.0) src[(size_t)i * ldg + j] = x;
+          }
+        });
+      } else {
       ex.par([&](int tid) {
         for (int e = tid * 2; e < np * ldg; e += 2 * Exec::nthr()) { st2(src + e, 0.0, 0.0); st2(dst + e, 0.0, 0.0); }
       });
@@ -1420,6 +1473,7 @@ struct Chain {
           }
         });
         double* tmp = src; src = dst; dst = tmp;
+      }
       }
       double* G = src;
       double* O = dst;
