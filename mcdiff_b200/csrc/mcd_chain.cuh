@@ -1159,6 +1159,55 @@ struct Chain {
     return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
   }
 
+  // Kernels G(lagt[l]) = exp(lagt[l] S) of the generator currently in s.a / s.b for every lag time,
+  // without likelihood terms: each one is copied to dump + l * np * ld (global).  The radial model
+  // needs a Bessel-weighted sum of such kernels before the logarithm (lib/twod.py:118-126).
+  // Same LagPlan walk as evaluate_sq.  Returns false for a non-finite / absurd scale.
+  MCD_HD bool kernels_sq(const double* lagt, const LagPlan& pl, double* slots, double* dump, double gersh, bool use_mma) {
+    const size_t me = (size_t)P.np * P.ld;
+    const bool fast = pl.fast != 0;
+    double* R = nullptr;
+    double* O = nullptr;
+    int nsq = 0;
+    for (int c = 0; c < pl.nchain; ++c) {
+      const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
+      double* other = nullptr;
+      double* G = sq_chain(t, gersh, 0, use_mma, -1, nullptr, &other, &nsq);
+      if (!G) return false;
+      if (!fast && pl.chain_slot[c] >= 0) copy_buffer(slots + (size_t)pl.chain_slot[c] * me, G);
+      R = G;
+      O = other;
+    }
+    copy_buffer(dump + (size_t)pl.order[0] * me, R);
+    double* G0 = R;
+    int in_O = -1;
+    for (int i = 1; i < P.nlag; ++i) {
+      const int l = pl.order[i];
+      const double* res = R;
+      if (fast || pl.op_slot[i] >= 0) {
+        const double* X;
+        const double* Y;
+        double* D;
+        int store;
+        if (fast) {
+          X = (i == 1) ? G0 : O; Y = G0; D = O; store = (i == 1) ? 1 : 2;
+          res = O;
+        } else {
+          if (in_O != pl.op_slot[i]) {
+            copy_buffer(O, slots + (size_t)pl.op_slot[i] * me);
+            in_O = pl.op_slot[i];
+          }
+          X = R; Y = O; D = R; store = 2;
+        }
+        if (use_mma) dmma_product(X, Y, D, nullptr, nullptr, nullptr, store);
+        else sym_product(X, Y, D, nullptr, nullptr, nullptr, store);
+      }
+      copy_buffer(dump + (size_t)l * me, res);
+      if (!fast && pl.park[i] >= 0) copy_buffer(slots + (size_t)pl.park[i] * me, R);
+    }
+    return true;
+  }
+
   // ------------------------------------------------------------------------------------
   // Blocked squaring engine (kBlocked, kMaxSmemBins < n <= 2 kMaxSmemBins).
   // The np x np matrices (np = 2 nbk) live in a per-CTA global workspace that stays in L2; a product

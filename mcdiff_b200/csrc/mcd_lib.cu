@@ -444,6 +444,15 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   return (int)cudaGetLastError();
 }
 
+// LagPlan of the radial squaring route (lag times are a device array: one small synchronous copy).
+static int rad_plan(RadProblem& R, cudaStream_t st) {
+  double hl[kMaxLag];
+  CUDA_TRY(cudaMemcpyAsync(hl, R.lagtimes, (size_t)R.nlag * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  plan_lags(hl, R.nlag, false, &R.plan);
+  return MCD_OK;
+}
+
 int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
                           const double* v, const double* w, const double* lagtimes, const double* counts,
                           const double* bessels, const double* b0zeros, double clip, int32_t B,
@@ -459,6 +468,8 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
   R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
   R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
   R.clip = clip;
+  int prc = rad_plan(R, st);
+  if (prc != MCD_OK) return prc;
   const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
   const size_t per_cta = rad_workspace_doubles(R) * sizeof(double);
   int rc = ensure_gws(h, (size_t)grid * per_cta);
@@ -492,6 +503,8 @@ int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t 
   R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
   R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
   R.clip = clip;
+  int prc = rad_plan(R, st);
+  if (prc != MCD_OK) return prc;
   int rc = ensure_gws(h, (size_t)nchains * rad_workspace_doubles(R) * sizeof(double));
   if (rc != MCD_OK) return rc;
   const size_t smem = rad_smem_bytes(R);

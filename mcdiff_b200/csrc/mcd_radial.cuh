@@ -4,10 +4,12 @@
 //   log L  = sum_l sum_{k,i,j} N[l,k,i,j] log(max(P_l[k,i,j], 1e-32))
 //
 // R - diag(sink_m) is symmetrised by the same Pi = diag(exp(-v)) as the 1-D generator, so every
-// Bessel term is one symmetric eigenproblem shared by all lag times.  One CTA per radial
-// profile: the lmax eigensystems are solved one after the other in shared memory (same
-// parallel Jacobi as the 1-D path) and parked in a per-CTA global (L2 resident) workspace;
-// the likelihood pass then contracts them per (i, j) pair.
+// Bessel term has a symmetric kernel G_m(t) = exp(t S_m) >= 0.  One CTA per radial profile.
+// Default route: the lmax kernels of every lag time are formed one after the other in shared
+// memory by the tensor-core scaling-and-squaring engine of the 1-D path (Chain::kernels_sq, same
+// LagPlan) and parked in a per-CTA global (L2 resident) workspace; the likelihood pass then takes
+// the Bessel-weighted sums per (i, j) pair.  Lag sets without a LagPlan fall back to lmax
+// symmetric eigenproblems (parallel Jacobi) contracted per pair.
 #pragma once
 #include "mcd_chain.cuh"
 
@@ -22,12 +24,15 @@ struct RadProblem {
   const double* bessels;   // [lmax][dim_rad]
   const double* b0zeros;   // [lmax]
   double clip;
+  LagPlan plan;            // squaring-engine route to the lag times (plan.ok == 0: eigen fallback)
 };
 
 constexpr int kMaxBessel = 64;
 
 MCD_HOSTDEV size_t rad_workspace_doubles(const RadProblem& R) {
-  return (size_t)R.lmax * R.np * R.ld + (size_t)R.lmax * R.np;
+  const size_t eig = (size_t)R.lmax * R.np * R.ld + (size_t)R.lmax * R.np;
+  const size_t sq = ((size_t)R.nlag * R.lmax + kMaxSlots) * R.np * R.ld;
+  return eig > sq ? eig : sq;
 }
 MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R) {
   return smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) + ((size_t)R.np + (size_t)R.lmax * R.np) * 8;
@@ -77,7 +82,79 @@ struct RadCtx {
   double* ws_x;    // [lmax][np][ld] eigenvectors per Bessel term (global, L2 resident)
   double* ws_lam;  // [lmax][np]
 
+  // Squaring route: kernels of all lag times per Bessel term -> workspace [nlag][lmax][np][ld]
+  // (+ the plan's slots behind it), then the Bessel sums and the logarithms per pair.
+  __device__ __forceinline__ double loglike_sq(const double* wrad_vec, double* Pb, int* bad_out) {
+    const int n = R.n, np = R.np, ld = R.ld, lmax = R.lmax, dim_rad = R.dim_rad;
+    const double rmax = (double)dim_rad;
+    const size_t me = (size_t)np * ld;
+    double* slots = ws_x + (size_t)R.nlag * lmax * me;
+    const bool use_mma = ch.dmma_ok();
+    int bad = 0;
+    for (int m = 0; m < lmax && !bad; ++m) {
+      const double z = R.b0zeros[m];
+      ex.par([&](int tid) {
+        for (int i = tid; i < np; i += kThreads)
+          s.a[i] = (i < n) ? a0[i] - exp(wrad_vec[i]) * z * z / (rmax * rmax) : 0.0;  // lib/twod.py:113-117
+      });
+      const double gersh = ex.max([&](int tid) {
+        double mx = 0.0;
+        for (int i = tid; i < n; i += kThreads) {
+          const int im = (i == 0) ? n - 1 : i - 1;
+          const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+          mx = (r > mx || r != r) ? r : mx;
+        }
+        return mx;
+      });
+      // workspace layout [lmax][nlag][np][ld]: kernels_sq writes the nlag kernels of term m contiguously
+      if (!ch.kernels_sq(R.lagtimes, R.plan, slots, ws_x + (size_t)m * R.nlag * me, gersh, use_mma)) bad = 1;
+    }
+    if (bad) {
+      if (bad_out) *bad_out = 1;
+      return nan("");
+    }
+    ex.par([&](int tid) { ex.regs(tid)[0] = 0.0; });
+    for (int l = 0; l < R.nlag; ++l) {
+      ex.par([&](int tid) {
+        double part = 0.0;
+        double g[kMaxBessel];
+        const int npairs = n * (n + 1) / 2;
+        for (int e = tid; e < npairs; e += kThreads) {
+          int i = 0, rem = e;   // decode e -> (i <= j)
+          while (rem >= n - i) { rem -= n - i; ++i; }
+          const int j = i + rem;
+          for (int m = 0; m < lmax; ++m) g[m] = ws_x[((size_t)m * R.nlag + l) * me + (size_t)i * ld + j];
+          const double sij = s.ea[i] * s.eb[j], sji = s.ea[j] * s.eb[i];
+          for (int k = 0; k < dim_rad; ++k) {
+            double pk = 0.0;
+            for (int m = 0; m < lmax; ++m) pk = fma(R.bessels[(size_t)m * dim_rad + k], g[m], pk);  // lib/twod.py:125-126
+            const size_t base = (((size_t)l * dim_rad + k) * n) * n;
+            const double pij = sij * pk;
+            const double nij = R.counts[base + (size_t)i * n + j];
+            if (nij != 0.0) part += nij * log(fmax(pij, R.clip));
+            if (Pb) Pb[base + (size_t)i * n + j] = pij;
+            if (i != j) {
+              const double pji = sji * pk;
+              const double nji = R.counts[base + (size_t)j * n + i];
+              if (nji != 0.0) part += nji * log(fmax(pji, R.clip));
+              if (Pb) Pb[base + (size_t)j * n + i] = pji;
+            }
+          }
+        }
+        ex.regs(tid)[0] += part;
+      });
+    }
+    const double ll = ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+    if (bad_out) *bad_out = 0;
+    return ll;
+  }
+
   __device__ __forceinline__ double loglike(const double* wrad_vec, double* Pb, int* bad_out) {
+    if (R.plan.ok) return loglike_sq(wrad_vec, Pb, bad_out);
+    return loglike_eig(wrad_vec, Pb, bad_out);
+  }
+
+  __device__ __forceinline__ double loglike_eig(const double* wrad_vec, double* Pb, int* bad_out) {
     const int n = R.n, np = R.np, ld = R.ld, lmax = R.lmax, dim_rad = R.dim_rad;
     const double rmax = (double)dim_rad;
     int bad = 0;
@@ -155,6 +232,7 @@ struct RadCtx {
   P.n = R.n; P.np = R.np; P.ld = R.ld; P.dim_w = R.dim_w; P.pbc = R.pbc; P.nlag = R.nlag;                        \
   P.ncosF = 0; P.ncosD = 0; P.lagtimes = R.lagtimes; P.counts = nullptr; P.nsym = nullptr; P.rvec = nullptr;     \
   P.v_basis = nullptr; P.w_basis = nullptr; P.svecs = nullptr; P.spring_k = 0.0; P.clip = R.clip;                \
+  P.nbk = R.np; P.lds = R.ld; P.blocked = 0;                                                                    \
   const size_t mat_bytes = smem_matrix_bytes(R.np, R.ld);                                                       \
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);                                 \
   double* a0 = reinterpret_cast<double*>(smem_raw + mat_bytes + smem_vectors_bytes(R.np));                       \

@@ -424,6 +424,35 @@ def test_squaring_rejects_unsupported(engine):
     np.testing.assert_allclose(ll[0], O.log_like_lag(np.zeros(240), np.zeros(240), [10.0], counts, True), rtol=RTOL)
 
 
+@pytest.mark.parametrize("lags", [(5.0,), (5.0, 10.0, 15.0), (4.0, 6.0, 10.0),
+                                  tuple(np.cumsum([1.0, 1.1, 1.23, 1.37, 1.51, 1.69, 1.83, 1.97, 2.11]))])
+def test_radial_likelihood_lag_sets(engine, lags):
+    """Radial likelihood against the oracle for a single lag, an arithmetic progression (fast
+    LagPlan), a general plan with a parked operand, and a lag set without a plan (nine
+    incommensurate differences -> eigen fallback)."""
+    from mcdiff_b200.engine import rad_loglike
+    from oracle import mcdiff_oracle as O
+    n, dim_rad, lmax = 24, 15, 9
+    rng = np.random.default_rng(17)
+    i = np.arange(n)
+    v = 1.2 * np.cos(2 * np.pi * (i + 0.5) / n)
+    w = np.log(0.5 + 0.2 * np.cos(2 * np.pi * (i + 1.0) / n))
+    lags = np.array(lags)
+    zeros, table = O.bessel_tables(lmax, dim_rad)
+    rate = O.rate_matrix(v, w, True)
+    wrad0 = np.full(n, np.log(0.4))
+    counts = np.zeros((len(lags), dim_rad, n, n))
+    for l, lt in enumerate(lags):
+        counts[l] = rng.poisson(300.0 * np.clip(O.radial_propagator(rate, wrad0, lt, zeros, table), 0.0, None))
+    wrad = wrad0[None, :] + rng.normal(0, 0.2, (3, n))
+    ll, P, st = rad_loglike(engine, v, w, True, lags, counts, table, zeros, wrad, want_P=True)
+    assert not st.any()
+    for b in range(3):
+        np.testing.assert_allclose(ll[b], O.rad_log_like_lag(rate, wrad[b], lags, counts, zeros, table), rtol=RTOL)
+    Pref = O.radial_propagator(rate, wrad[1], lags[-1], zeros, table)
+    assert np.max(np.abs(P[1, -1] - Pref)) <= 1e-12 * np.max(np.abs(Pref))
+
+
 @pytest.mark.parametrize("tag", ["radbin", "radcos"])
 def test_radial_mc_replay_against_reference(engine, tag):
     """Radial Monte-Carlo loop (per-bin and cosine wrad moves): decisions bit-exact vs the
