@@ -35,7 +35,8 @@ MCD_HOSTDEV size_t rad_workspace_doubles(const RadProblem& R) {
   return eig > sq ? eig : sq;
 }
 MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R) {
-  return smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) + ((size_t)R.np + (size_t)R.lmax * R.np) * 8;
+  return smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) + ((size_t)R.np + (size_t)R.lmax * R.np) * 8 +
+         (((size_t)R.n * (R.n + 1) + 15) & ~(size_t)15);   // + pair table
 }
 
 // Monte-Carlo schedule and per-chain state of the radial loop (lib/mc.py:29-30,
@@ -79,8 +80,15 @@ struct RadCtx {
   Smem& s;
   double* a0;      // [np] diagonal of the 1-D generator
   double* elm;     // [lmax][np]
-  double* ws_x;    // [lmax][np][ld] eigenvectors per Bessel term (global, L2 resident)
+  double* ws_x;    // squaring: [lmax][nlag][np][ld] kernels; eigen: [lmax][np][ld] eigenvectors (global, L2 resident)
   double* ws_lam;  // [lmax][np]
+  const unsigned char* ptab;  // (i, j) of the pairs i <= j, row-major
+
+  // log(max(p, clip)), lib/twod.py:29; the table-based logarithm needs a positive normal argument
+  __device__ __forceinline__ double clipped_log(double p) const {
+    const double x = fmax(p, R.clip);
+    return (x >= 1.0e-300) ? ch.fast_log(x) : log(x);
+  }
 
   // Squaring route: kernels of all lag times per Bessel term -> workspace [nlag][lmax][np][ld]
   // (+ the plan's slots behind it), then the Bessel sums and the logarithms per pair.
@@ -113,36 +121,51 @@ struct RadCtx {
       if (bad_out) *bad_out = 1;
       return nan("");
     }
+    // ---- Bessel sums + logarithms.  The pairs i <= j are taken in chunks of CH: the lmax kernel
+    //      entries of every pair of the chunk are staged in shared memory (the work matrices are free
+    //      now), then thread (p, kg) handles the radial bins k = kg, kg + KG, ... of pair p ----
     ex.par([&](int tid) { ex.regs(tid)[0] = 0.0; });
+    const int npairs = n * (n + 1) / 2;
+    int CH = (int)((2 * me) / (size_t)lmax);
+    CH = CH >= 128 ? 128 : (CH >= 64 ? 64 : (CH >= 32 ? 32 : CH));
+    const int KG = kThreads / CH;
+    double* gs = s.XT;   // [lmax][CH]
     for (int l = 0; l < R.nlag; ++l) {
-      ex.par([&](int tid) {
-        double part = 0.0;
-        double g[kMaxBessel];
-        const int npairs = n * (n + 1) / 2;
-        for (int e = tid; e < npairs; e += kThreads) {
-          int i = 0, rem = e;   // decode e -> (i <= j)
-          while (rem >= n - i) { rem -= n - i; ++i; }
-          const int j = i + rem;
-          for (int m = 0; m < lmax; ++m) g[m] = ws_x[((size_t)m * R.nlag + l) * me + (size_t)i * ld + j];
-          const double sij = s.ea[i] * s.eb[j], sji = s.ea[j] * s.eb[i];
-          for (int k = 0; k < dim_rad; ++k) {
-            double pk = 0.0;
-            for (int m = 0; m < lmax; ++m) pk = fma(R.bessels[(size_t)m * dim_rad + k], g[m], pk);  // lib/twod.py:125-126
-            const size_t base = (((size_t)l * dim_rad + k) * n) * n;
-            const double pij = sij * pk;
-            const double nij = R.counts[base + (size_t)i * n + j];
-            if (nij != 0.0) part += nij * log(fmax(pij, R.clip));
-            if (Pb) Pb[base + (size_t)i * n + j] = pij;
-            if (i != j) {
-              const double pji = sji * pk;
-              const double nji = R.counts[base + (size_t)j * n + i];
-              if (nji != 0.0) part += nji * log(fmax(pji, R.clip));
-              if (Pb) Pb[base + (size_t)j * n + i] = pji;
+      for (int c0 = 0; c0 < npairs; c0 += CH) {
+        ex.par([&](int tid) {
+          for (int e = tid; e < CH * lmax; e += kThreads) {
+            const int m = e / CH, p = e - m * CH;
+            if (c0 + p < npairs) {
+              const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
+              gs[e] = ws_x[((size_t)m * R.nlag + l) * me + (size_t)i * ld + j];
             }
           }
-        }
-        ex.regs(tid)[0] += part;
-      });
+        });
+        ex.par([&](int tid) {
+          const int kg = tid / CH, p = tid - kg * CH;
+          if (kg < KG && c0 + p < npairs) {
+            const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
+            const double sij = s.ea[i] * s.eb[j], sji = s.ea[j] * s.eb[i];
+            double part = 0.0;
+            for (int k = kg; k < dim_rad; k += KG) {
+              double pk = 0.0;
+              for (int m = 0; m < lmax; ++m) pk = fma(R.bessels[(size_t)m * dim_rad + k], gs[m * CH + p], pk);  // lib/twod.py:125-126
+              const size_t base = (((size_t)l * dim_rad + k) * n) * n;
+              const double pij = sij * pk;
+              const double nij = R.counts[base + (size_t)i * n + j];
+              if (nij != 0.0) part += nij * clipped_log(pij);
+              if (Pb) Pb[base + (size_t)i * n + j] = pij;
+              if (i != j) {
+                const double pji = sji * pk;
+                const double nji = R.counts[base + (size_t)j * n + i];
+                if (nji != 0.0) part += nji * clipped_log(pji);
+                if (Pb) Pb[base + (size_t)j * n + i] = pji;
+              }
+            }
+            ex.regs(tid)[0] += part;
+          }
+        });
+      }
     }
     const double ll = ex.sum([&](int tid) { return ex.regs(tid)[0]; });
     if (bad_out) *bad_out = 0;
@@ -237,6 +260,7 @@ struct RadCtx {
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);                                 \
   double* a0 = reinterpret_cast<double*>(smem_raw + mat_bytes + smem_vectors_bytes(R.np));                       \
   double* elm = a0 + R.np;                                                                                      \
+  unsigned char* ptab = reinterpret_cast<unsigned char*>(elm + (size_t)R.lmax * R.np);                          \
   DeviceExec ex(s.red);                                                                                         \
   Chain<DeviceExec> ch(ex, P, s);                                                                               \
   ch.build_tables();                                                                                            \
@@ -253,8 +277,12 @@ struct RadCtx {
   ch.build_S(s.v, s.w);                                                                                         \
   ex.par([&](int tid) {                                                                                         \
     for (int i = tid; i < np; i += kThreads) a0[i] = s.a[i];                                                    \
+    for (int i = tid; i < n; i += kThreads) {     /* row i of the pair table starts at i n - i (i - 1) / 2 */    \
+      const int row0 = i * n - i * (i - 1) / 2;                                                                 \
+      for (int j = i; j < n; ++j) { ptab[2 * (row0 + j - i)] = (unsigned char)i; ptab[2 * (row0 + j - i) + 1] = (unsigned char)j; } \
+    }                                                                                                           \
   });                                                                                                           \
-  RadCtx ctx{R, ex, ch, s, a0, elm, ws_x, ws_lam};
+  RadCtx ctx{R, ex, ch, s, a0, elm, ws_x, ws_lam, ptab};
 
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, double* __restrict__ out_ll,
