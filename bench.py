@@ -318,7 +318,8 @@ def run_gpu(args):
             "jacobi_sweeps_or_squarings_per_mc_step": sweeps, "chains_with_status": bad,
             "mean_acceptance": float((summary_all[:, 6] + summary_all[:, 7]).sum() / max(1.0, float(world) * st["counters"][:, 5].sum())),
         },
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "bound_detail": "FP64 tensor pipe (DMMA m8n8k4); same nominal peak as the FP64 vector pipe",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this configuration
                      # (ncu --set full, profiles/r01_ncu_full_mc_run_bench_launch.csv): 4.12 MB

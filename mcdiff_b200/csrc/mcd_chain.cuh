@@ -14,6 +14,7 @@
 // S[i,i] = R[i,i]; P = Pi^1/2 V exp(t Lambda) V^T Pi^-1/2, one eigendecomposition serves
 // every lag time.
 #pragma once
+#include <cstdint>
 #include <cstring>
 
 #include "mcd_exec.cuh"
@@ -209,7 +210,7 @@ MCD_HD double u53(uint32_t hi, uint32_t lo) {
 // shared-memory carve-up
 // ---------------------------------------------------------------------------------------
 struct Scalars {
-  double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring, gmin, lin;
+  double ll_cur, ll_try, timezero, t0_try, dv, dw, dt0, temp, scale, delta, e_spring, gmin, lin, gersh;
   long long naccv, naccw, nacct0, naccv_upd, naccw_upd, step, status, sweeps;
   int move, idx, accepted, accepted_t0, nsamp, basis_is_trial, do_t0, mma_tasks;
 };
@@ -226,9 +227,13 @@ struct Smem {
   double* red;
   double* part;  // per-thread likelihood partial sums (squaring engine)
   int *rp, *rq;
+  int* wti;                // warp tasks as 16 ints per warp: {nt, na, rowA, rowB, jb[8], -, -, -, -} (three 128-bit loads)
   unsigned char* tiles;    // 2 bytes per tile (ib, jb), ib <= jb
   unsigned char* jblocks;  // 2 bytes per Jacobi block (ka, kb), ka < kb
   unsigned char* wtab;     // 16 bytes per warp task of the tensor-core product (see build_tables)
+  unsigned char* hrow;     // Horner passes: band row owned by thread tid (tid / tpr) ...
+  unsigned char* hrem;     // ... and its slot inside the row (tid % tpr); 255 = no row
+  unsigned char* tord;     // Taylor order for s = 0..31 squarings
   Scalars* sc;
   int ntiles, nblk;
 };
@@ -236,7 +241,8 @@ struct Smem {
 MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
   size_t d = (size_t)np * 11 + 256 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
   size_t nb = np / 4, h = np / 2;
-  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + nb * (nb + 1) + h * (h - 1) + 16 * (kThreads / 32) + sizeof(Scalars) + 64;
+  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + 64 * (kThreads / 32) /*wti*/ + nb * (nb + 1) + h * (h - 1) + 16 * (kThreads / 32) + sizeof(Scalars) + 64 +
+                 2 * kThreads + 32 /*hrow, hrem, tord*/;
   return (bytes + 15) & ~(size_t)15;
 }
 MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
@@ -275,7 +281,8 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.part = d; d += kThreads;
   s.sc = reinterpret_cast<Scalars*>(d);
   d += (sizeof(Scalars) + 7) / 8;
-  int* ip = reinterpret_cast<int*>(d);
+  int* ip = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(d) + 15) & ~(uintptr_t)15);   // wti: 128-bit loads
+  s.wti = ip; ip += 16 * (kThreads / 32);
   s.rp = ip; ip += np / 2;
   s.rq = ip; ip += np / 2;
   unsigned char* c = reinterpret_cast<unsigned char*>(ip);
@@ -284,7 +291,10 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.nblk = h * (h - 1) / 2;
   s.tiles = c; c += 2 * s.ntiles;
   s.jblocks = c; c += 2 * s.nblk;
-  s.wtab = c;
+  s.wtab = c; c += 16 * (kThreads / 32);
+  s.hrow = c; c += kThreads;
+  s.hrem = c; c += kThreads;
+  s.tord = c;
   return s;
 }
 
@@ -307,6 +317,13 @@ struct Chain {
         s.lgc[tid] = c;
         s.lgl[tid] = -log(c);
       }
+      // Horner passes of the squaring engine: thread -> (band row, slot); runtime integer divisions cost
+      // ~75 dependent cycles each, so they are done once here
+      const int tpr = (Exec::nthr() / P.n > 1) ? Exec::nthr() / P.n : 1;
+      const int row = tid / tpr;
+      s.hrow[tid] = (unsigned char)((row < P.n && row < 255) ? row : 255);
+      s.hrem[tid] = (unsigned char)(tid - row * tpr);
+      if (tid < 32) s.tord[tid] = (unsigned char)taylor_order(tid, 0);
     });
     ex.single([&]() {
       const int nb = kBlocked ? 0 : P.np / 4;
@@ -371,6 +388,12 @@ struct Chain {
           for (int t = wt[0]; t < cap; ++t) wt[4 + t] = wt[4];
         }
         s.sc->mma_tasks = ok ? nw : 0;
+        for (int w = 0; w < maxw; ++w) {
+          const unsigned char* wt = s.wtab + 16 * w;
+          int* q = s.wti + 16 * w;
+          const bool have = ok && w < nw;
+          for (int k = 0; k < 16; ++k) q[k] = (have && k < 12) ? wt[k] : 0;
+        }
       }
       const int h = kBlocked ? 0 : P.np / 2;
       int q = 0;
@@ -407,29 +430,26 @@ struct Chain {
         }
       }
     });
-    double sc = ex.max([&](int tid) {
-      double m = 0.0;
-      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, fabs(s.a[i]));
-      return m;
+    // one fused reduction (two barriers instead of ten): ||diag||_max (Jacobi scale), max / min of v/2
+    // (g >= gmin guarantees P_ij = exp(-v_i/2) g exp(v_j/2) >= clip for every pair), the Gershgorin bound
+    // of ||S|| (squaring engines), and sum_ij N_ij (v_j - v_i)/2 = sum_k (v_k/2) (colsum_k - rowsum_k).
+    // s.part is free here (the likelihood partial sums are zeroed after build_S).
+    const r5 red = ex.max4sum(s.part, [&](int tid) {
+      r5 x{0.0, -1.0e308, -1.0e308, 0.0, 0.0};
+      for (int i = tid; i < n; i += Exec::nthr()) {
+        x.m0 = fmax(x.m0, fabs(s.a[i]));
+        x.m1 = fmax(x.m1, s.hv[i]);
+        x.m2 = fmax(x.m2, -s.hv[i]);
+        const int im = (i == 0) ? n - 1 : i - 1;
+        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+        x.m3 = (r > x.m3 || r != r) ? r : x.m3;
+        if (P.rvec) x.sum += s.hv[i] * P.rvec[i];
+      }
+      return x;
     });
-    // g >= gmin guarantees P_ij = exp(-v_i/2) g exp(v_j/2) >= clip for every pair (i, j)
-    const double hmax = ex.max([&](int tid) {
-      double m = -1.0e308;
-      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, s.hv[i]);
-      return m;
-    });
-    const double hmin = -ex.max([&](int tid) {
-      double m = -1.0e308;
-      for (int i = tid; i < n; i += Exec::nthr()) m = fmax(m, -s.hv[i]);
-      return m;
-    });
-    // sum_ij N_ij (v_j - v_i)/2 = sum_k (v_k/2) (colsum_k - rowsum_k)
-    const double lin = P.rvec ? ex.sum([&](int tid) {
-      double acc = 0.0;
-      for (int i = tid; i < n; i += Exec::nthr()) acc += s.hv[i] * P.rvec[i];
-      return acc;
-    }) : 0.0;
+    const double sc = red.m0, hmax = red.m1, hmin = -red.m2, lin = P.rvec ? red.sum : 0.0;
     ex.single([&]() {
+      s.sc->gersh = red.m3;
       s.sc->scale = sc;
       s.sc->gmin = P.clip * exp(hmax - hmin);
       s.sc->lin = lin;
@@ -851,15 +871,26 @@ struct Chain {
   }
 #endif
 
-  MCD_HD void dmma_store(double* D, int warp, int lane, int ntasks, const double* r) {
+  // decoded warp task (registers): tiles t < na on tile row rowA, na <= t < nt on rowB, jb[t] = tile column
+  struct WarpTask {
+    int nt, na, rowA, rowB, jb[8];
+  };
+  MCD_HD WarpTask load_task(int warp, int ntasks) const {
+    WarpTask k;
+    const i4 h0 = lds4i(s.wti + 16 * warp), h1 = lds4i(s.wti + 16 * warp + 4), h2 = lds4i(s.wti + 16 * warp + 8);
+    k.nt = (warp < ntasks) ? h0.x : 0; k.na = h0.y; k.rowA = h0.z; k.rowB = h0.w;
+    k.jb[0] = h1.x; k.jb[1] = h1.y; k.jb[2] = h1.z; k.jb[3] = h1.w;
+    k.jb[4] = h2.x; k.jb[5] = h2.y; k.jb[6] = h2.z; k.jb[7] = h2.w;
+    return k;
+  }
+
+  MCD_HD void dmma_store(double* D, const WarpTask& k, int lane, const double* r) {
     const int ld = P.ld;
-    const unsigned char* wt = s.wtab + 16 * warp;
-    const int nt = (warp < ntasks) ? wt[0] : 0, na = wt[1];
     const int fr = lane >> 2, fk = lane & 3;
 #pragma unroll
     for (int t = 0; t < kTilesPerWarp; ++t) {
-      if (t < nt) {
-        const int ib = (t < na) ? wt[2] : wt[3], jb = wt[4 + t];
+      if (t < k.nt) {
+        const int ib = (t < k.na) ? k.rowA : k.rowB, jb = k.jb[t];
         const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
         st2(D + i * ld + j, r[2 * t], r[2 * t + 1]);
         if (ib != jb) {
@@ -876,30 +907,32 @@ struct Chain {
     const int ntasks = s.sc->mma_tasks;
     ex.par([&](int tid) {
       const int warp = tid >> 5, lane = tid & 31;
-      const unsigned char* wt = s.wtab + 16 * warp;
+      const WarpTask task = load_task(warp, ntasks);
       const bool active = warp < ntasks;
-      const int nt = active ? wt[0] : 0, na = active ? wt[1] : 0;
-      const int rowA = wt[2], rowB = wt[3];
+      const int nt = task.nt, na = task.na, rowA = task.rowA, rowB = task.rowB;
       double c[kTilesPerWarp][2];
 #pragma unroll
       for (int t = 0; t < kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
       const int fr = lane >> 2, fk = lane & 3;   // fragment row (m or n) and k index of this lane
       // symmetric counts of the two entries per tile this lane owns, fetched before the k loop
+      // (padding tiles t >= nt repeat a valid tile of the task: loaded without a select so that the
+      // loads stay in flight across the k loop instead of being consumed right here)
       int nsv[kTilesPerWarp][2];
-      if (cnt) {
+      if (cnt && active) {
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
-          const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
-          const int* q = nsy + (size_t)(ib * 8 + fr) * np + jb * 8 + 2 * fk;
-          nsv[t][0] = (t < nt) ? q[0] : 0;
-          nsv[t][1] = (t < nt) ? q[1] : 0;
+          const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+          const i2 q = ld2i(nsy + (size_t)(ib * 8 + fr) * np + jb * 8 + 2 * fk);
+          nsv[t][0] = q.x;
+          nsv[t][1] = q.y;
         }
       }
+      MCD_CLK(5);
       if (active) {
 #if defined(__CUDA_ARCH__)
         int offB[kTilesPerWarp];
 #pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = wt[4 + t] * 64;
+        for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = task.jb[t] * 64;
         const unsigned ax = (unsigned)__cvta_generic_to_shared(X) + (unsigned)(fk * ld + fr) * 8u;
         const unsigned ay = (unsigned)__cvta_generic_to_shared(Y) + (unsigned)(fk * ld + fr) * 8u;
         const int pitch4 = 4 * ld * 8, nk4 = np / 4;
@@ -915,7 +948,7 @@ struct Chain {
         }
 #else
         for (int t = 0; t < nt; ++t) {
-          const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
+          const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
           const int i = ib * 8 + fr;
           for (int e = 0; e < 2; ++e) {
             const int j = jb * 8 + 2 * fk + e;
@@ -926,36 +959,71 @@ struct Chain {
         }
 #endif
       }
-      // likelihood epilogue: this lane owns G[i][j], G[i][j+1]; inside diagonal tiles only i <= j
+      MCD_CLK(6);
+      // likelihood epilogue: this lane owns G[i][j], G[i][j+1]; inside diagonal tiles only i <= j.
+      // Branch-free over the 16 entries (weight 0 for padding / lower-triangle / empty pairs, argument 1
+      // for entries below the clip) so that the 16 logarithms interleave instead of running as 16
+      // dependent chains; the rare clipped entries are redone exactly afterwards.
       if (cnt && nt > 0) {
+        const double gmin = s.sc->gmin;
         double part = 0.0;
+        bool rare = false;
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
-          if (t < nt) {
-            const int ib = (t < na) ? rowA : rowB, jb = wt[4 + t];
+          const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+          const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool valid = (t < nt) && !(ib == jb && j + e < i);
+            const double g = c[t][e];
+            const bool above = g >= gmin;
+            const int ns = valid ? nsv[t][e] : 0;
+            rare |= (ns != 0) && !above;
+            part += (double)(above ? ns : 0) * fast_log(above ? g : 1.0);
+          }
+        }
+        if (rare) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const bool valid = (t < nt) && !(ib == jb && j + e < i);
+              if (valid && nsv[t][e] != 0 && !(c[t][e] >= gmin))
+                part += pair_term_clipped(c[t][e], nsv[t][e], i, j + e, cnt, P.np, P.clip, s.ea, s.eb, s.hv);
+            }
+          }
+        }
+        s.part[tid] += part;
+        if (Pl) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
             const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int jj = j + e;
-              if (ib == jb && jj < i) continue;
-              part += pair_term(c[t][e], nsv[t][e], i, jj, cnt);
-              if (Pl && i < n && jj < n) {
+              if (t < nt && !(ib == jb && jj < i) && i < n && jj < n) {
                 Pl[(size_t)i * n + jj] = s.ea[i] * c[t][e] * s.eb[jj];
                 Pl[(size_t)jj * n + i] = s.ea[jj] * c[t][e] * s.eb[i];
               }
             }
           }
         }
-        s.part[tid] += part;
       }
+      MCD_CLK(7);
       double* r = ex.regs(tid);
 #pragma unroll
       for (int t = 0; t < kTilesPerWarp; ++t) { r[2 * t] = c[t][0]; r[2 * t + 1] = c[t][1]; }
-      if (store == 1) dmma_store(D, warp, lane, ntasks, r);
+      if (store == 1) dmma_store(D, task, lane, r);
+      MCD_CLK(8);
     });
+    MCD_CLK(9);
     if (store == 2) {
-      ex.par([&](int tid) { dmma_store(D, tid >> 5, tid & 31, ntasks, ex.regs(tid)); });
+      ex.par([&](int tid) { dmma_store(D, load_task(tid >> 5, ntasks), tid & 31, ex.regs(tid)); });
     }
+    MCD_CLK(10);
   }
 
   // Taylor order of the squaring engines.  T_m(x) = e^x (1 - x^(m+1)/(m+1)! ...) per eigenmode, and the
@@ -984,49 +1052,72 @@ struct Chain {
     const int n = P.n, np = P.np, ld = P.ld;
     const double rho = t * gersh;
     if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
+    // s = smallest number of halvings with rho / 2^s <= 1
     int nsq = 0;
-    for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
+    if (rho > 1.0) {
+      int ex2;
+      const double fr2 = frexp(rho, &ex2);   // rho = fr2 2^ex2, fr2 in [0.5, 1)
+      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
+    }
     const double h = ldexp(t, -nsq);
-    const int m = taylor_order(nsq, taylor_m);
+    const int m = (taylor_m > 0) ? (taylor_m < 31 ? taylor_m : 31) : s.tord[nsq];   // rho < 1e9: nsq <= 30
     double* A = s.XT;
     double* B = s.B2;
+    MCD_CLK(16);
     // ---- T_m(hS) by Horner:  H <- I + (hS H)/k, k = m..1, ping-pong ----
-    // H is banded (half-width t after t steps): only the band is touched.  A row is shared by
+    // H is banded (half-width tt after tt steps): only the band is touched.  A row is shared by
     // `tpr` consecutive threads that walk its band with stride tpr (contiguous columns across
-    // lanes); the three coefficients of the row stay in registers for the whole pass.
-    ex.par([&](int tid) {
-      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(A + e, 0.0, 0.0); st2(B + e, 0.0, 0.0); }
-    });
+    // lanes), four independent elements at a time: these scalar phases are latency bound (phase
+    // clocks: ~0.3 instructions per cycle and SM sub-partition), so the loads of a chunk are issued
+    // together, and the thread -> (row, slot) map and the pass factors h/k come from tables.
+    // (A compact band layout with a final scatter was measured 1.3 % slower: profiles/r01_summary.md.)
+    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
     double* src = A;
     double* dst = B;
     ex.par([&](int tid) {
+      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(A + e, 0.0, 0.0); st2(B + e, 0.0, 0.0); }
+      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);   // no reduction runs before the passes end
+    });
+    ex.par([&](int tid) {
       for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
     });
-    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
-    const int rows_per_pass = Exec::nthr() / tpr;
+    MCD_CLK(3);
     for (int tt = 1; tt <= m; ++tt) {
-      const double f = h / (double)(m - tt + 1);
       const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
       const bool full = (width == n);
       ex.par([&](int tid) {
-        const int r = tid % tpr;
-        for (int i = tid / tpr; i < n; i += rows_per_pass) {
+        const int i = s.hrow[tid], r = s.hrem[tid];
+        if (i < n) {
+          const double f = s.red[tt];
           const int im = (i == 0) ? n - 1 : i - 1;
           const int ip = (i == n - 1) ? 0 : i + 1;
           const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.b[i];
-          const double* s0 = src + i * ld;
-          const double* sm = src + im * ld;
-          const double* sp = src + ip * ld;
-          double* d0 = dst + i * ld;
-          for (int dd = r; dd < width; dd += tpr) {
-            int j;
-            if (full) j = dd;
-            else {
-              j = i - tt + dd;
-              if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
-              else if (j < 0 || j >= n) continue;
+          const double* MCD_RESTRICT s0 = src + i * ld;
+          const double* MCD_RESTRICT sm = src + im * ld;
+          const double* MCD_RESTRICT sp = src + ip * ld;
+          double* MCD_RESTRICT d0 = dst + i * ld;
+          for (int dd0 = r; dd0 < width; dd0 += 4 * tpr) {
+            int jq[4];
+            bool ok[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int dd = dd0 + q * tpr;
+              bool o = dd < width;
+              int j = dd;
+              if (!full) {
+                j = i - tt + dd;
+                if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
+                else o = o && j >= 0 && j < n;
+              }
+              ok[q] = o;
+              jq[q] = o ? j : i;
             }
-            d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
+            double x0[4], xm[4], xp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { x0[q] = s0[jq[q]]; xm[q] = sm[jq[q]]; xp[q] = sp[jq[q]]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (ok[q]) d0[jq[q]] = ((i == jq[q]) ? 1.0 : 0.0) + (ai * x0[q] + bm * xm[q] + bp * xp[q]);
           }
         }
       });
@@ -1034,6 +1125,7 @@ struct Chain {
     }
     // ---- G(t) = T^(2^s): out-of-place squarings (direct stores), the last one carries the
     //      likelihood epilogue of lag `epi` ----
+    MCD_CLK(4);
     double* G = src;      // current power
     double* O = dst;      // the other buffer
     const int* cnt_e = (epi >= 0) ? P.counts + (size_t)epi * np * np : nullptr;
@@ -1089,17 +1181,9 @@ struct Chain {
     const int n = P.n, np = P.np;
     const size_t nn = (size_t)n * n, slot_elems = (size_t)np * P.ld;
     build_S(v, w);
-    // Gershgorin bound of ||S||
-    const double gersh = ex.max([&](int tid) {
-      double m = 0.0;
-      for (int i = tid; i < n; i += Exec::nthr()) {
-        const int im = (i == 0) ? n - 1 : i - 1;
-        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
-        m = (r > m || r != r) ? r : m;
-      }
-      return m;
-    });
+    const double gersh = s.sc->gersh;   // Gershgorin bound of ||S||
     ex.par([&](int tid) { s.part[tid] = 0.0; });
+    MCD_CLK(2);
     int nsq = 0;
     bool bad = false;
     double* R = nullptr;   // running kernel G(t_i)
@@ -1156,7 +1240,9 @@ struct Chain {
       ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
       return nan("");
     }
-    return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
+    const double ll_total = s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
+    MCD_CLK(11);
+    return ll_total;
   }
 
   // Kernels G(lagt[l]) = exp(lagt[l] S) of the generator currently in s.a / s.b for every lag time,
@@ -1421,15 +1507,7 @@ struct Chain {
     double* buf[3] = {ws, ws + melems, ws + 2 * melems};
     double* slots = ws + 3 * melems;
     build_S(v, w);
-    const double gersh = ex.max([&](int tid) {
-      double m = 0.0;
-      for (int i = tid; i < n; i += Exec::nthr()) {
-        const int im = (i == 0) ? n - 1 : i - 1;
-        const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
-        m = (r > m || r != r) ? r : m;
-      }
-      return m;
-    });
+    const double gersh = s.sc->gersh;
     ex.par([&](int tid) { s.part[tid] = 0.0; });
     int nsq_total = 0;
     bool bad = false;
@@ -1656,6 +1734,7 @@ struct Chain {
       have_basis = 1;
     }
     long long since_refresh = 0;
+    MCD_CLK_BEGIN();
 
     for (int it = 0; it < nsteps; ++it) {
       // Two phases per step with ONE inlined likelihood evaluation site:
@@ -1712,6 +1791,7 @@ struct Chain {
             sc->do_t0 = (sc->t0_try > -0.5 * mp.min_lt) ? 1 : 0;  // lib/MCState.py:207
           }
         });
+        MCD_CLK(0);
         if (phase == 0) move = sc->move;
         if (phase == 0 && move == 0) continue;
         if (phase == 1 && !sc->do_t0) break;
@@ -1774,6 +1854,7 @@ struct Chain {
           mode = (move != 0 && sc->accepted && have_basis) ? 2 : (have_basis ? 0 : 1);
         }
 
+        MCD_CLK(1);
         int sw = 0;
         double ll_new;
         if constexpr (kBlocked) {
@@ -1824,6 +1905,7 @@ struct Chain {
           }
           if (phase == 0) sc->ll_try = lt;
         });
+        MCD_CLK(12);
         // ---- commit ----
         if (phase == 0 && sc->accepted) {
           const int idx = sc->idx;
@@ -1883,7 +1965,9 @@ struct Chain {
         }
         sc->step = j;
       });
+      MCD_CLK(13);
     }
+    MCD_CLK_END();
     // ---- store chain state ----
     ex.par([&](int tid) {
       for (int i = tid; i < n; i += Exec::nthr()) io.v[chain * n + i] = s.v[i];

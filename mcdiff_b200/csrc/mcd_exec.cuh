@@ -14,10 +14,47 @@
 #define MCD_HD __device__ __forceinline__
 #define MCD_HOSTDEV __host__ __device__ inline
 #define MCD_NOINLINE __device__ __noinline__
+#define MCD_RESTRICT __restrict__
 #else
 #define MCD_HD inline
 #define MCD_HOSTDEV inline
 #define MCD_NOINLINE inline
+#define MCD_RESTRICT __restrict__
+#endif
+
+// Optional phase clocks (-DMCD_PHASE_CLOCK, profiles/prof_phases.py): thread 0 of CTA 0 adds the cycles
+// since its previous stamp to g_phase_clk[id].  Compiled out of the product library.
+#if defined(MCD_PHASE_CLOCK) && defined(__CUDACC__)
+namespace mcd {
+__device__ long long g_phase_clk[32];
+__shared__ long long s_phase_clk[33];   // [32] = previous stamp; shared memory keeps a stamp at ~2 x 30 cycles
+}
+#endif
+#if defined(MCD_PHASE_CLOCK) && defined(__CUDA_ARCH__)
+#define MCD_CLK(id)                                                             \
+  do {                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {                                  \
+      const long long t_ = clock64();                                           \
+      mcd::s_phase_clk[id] += t_ - mcd::s_phase_clk[32];                        \
+      mcd::s_phase_clk[32] = clock64();                                         \
+    }                                                                           \
+  } while (0)
+#define MCD_CLK_BEGIN()                                                         \
+  do {                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {                                  \
+      for (int q_ = 0; q_ < 32; ++q_) mcd::s_phase_clk[q_] = 0;                 \
+      mcd::s_phase_clk[32] = clock64();                                         \
+    }                                                                           \
+  } while (0)
+#define MCD_CLK_END()                                                           \
+  do {                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                                    \
+      for (int q_ = 0; q_ < 32; ++q_) mcd::g_phase_clk[q_] += mcd::s_phase_clk[q_]; \
+  } while (0)
+#else
+#define MCD_CLK(id) do { } while (0)
+#define MCD_CLK_BEGIN() do { } while (0)
+#define MCD_CLK_END() do { } while (0)
 #endif
 
 namespace mcd {
@@ -34,6 +71,13 @@ struct d2 {
 struct i4 {
   int x, y, z, w;
 };
+struct i2 {
+  int x, y;
+};
+// four maxima (NaN-propagating) and one sum reduced over the CTA in one go (Exec::max4sum)
+struct r5 {
+  double m0, m1, m2, m3, sum;
+};
 
 // max that propagates NaN (fmax would drop it): non-finite profiles must surface as NaN
 MCD_HD double nanmax(double a, double b) { return (a != a || a > b) ? a : ((b != b) ? b : (a > b ? a : b)); }
@@ -44,6 +88,14 @@ MCD_HD d2 ld2(const double* p) {
   return d2{t.x, t.y};
 #else
   return d2{p[0], p[1]};
+#endif
+}
+MCD_HD i2 ld2i(const int* p) {   // 8-byte aligned pair of ints
+#if defined(__CUDA_ARCH__)
+  int2 t = *reinterpret_cast<const int2*>(p);
+  return i2{t.x, t.y};
+#else
+  return i2{p[0], p[1]};
 #endif
 }
 MCD_HD void st2(double* p, double a, double b) {
@@ -57,6 +109,16 @@ MCD_HD void st2(double* p, double a, double b) {
 MCD_HD i4 ld4i(const int* p) {
 #if defined(__CUDA_ARCH__)
   int4 t = __ldg(reinterpret_cast<const int4*>(p));
+  return i4{t.x, t.y, t.z, t.w};
+#else
+  return i4{p[0], p[1], p[2], p[3]};
+#endif
+}
+
+// 16-byte aligned quadruple of ints from shared (or any non-constant) memory
+MCD_HD i4 lds4i(const int* p) {
+#if defined(__CUDA_ARCH__)
+  int4 t = *reinterpret_cast<const int4*>(p);
   return i4{t.x, t.y, t.z, t.w};
 #else
   return i4{p[0], p[1], p[2], p[3]};
@@ -111,6 +173,40 @@ struct DeviceExec {
     __syncthreads();
     return t;
   }
+  // Four maxima and a sum with ONE pair of barriers (a reduction costs two barriers and a 5-step shuffle
+  // tree whatever it reduces; the five trees interleave).  scratch: 5 * kThreads / 32 doubles.
+  // The sum has the same shape as sum(): shuffle tree per warp, then warp order.
+  template <class F>
+  __device__ __forceinline__ r5 max4sum(double* scratch, F f) {
+    r5 v = f(tid);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v.m0 = nanmax(v.m0, __shfl_xor_sync(0xffffffffu, v.m0, o));
+      v.m1 = nanmax(v.m1, __shfl_xor_sync(0xffffffffu, v.m1, o));
+      v.m2 = nanmax(v.m2, __shfl_xor_sync(0xffffffffu, v.m2, o));
+      v.m3 = nanmax(v.m3, __shfl_xor_sync(0xffffffffu, v.m3, o));
+      v.sum += __shfl_xor_sync(0xffffffffu, v.sum, o);
+    }
+    constexpr int nw = kThreads / 32;
+    if ((tid & 31) == 0) {
+      const int w = tid >> 5;
+      scratch[w] = v.m0; scratch[nw + w] = v.m1; scratch[2 * nw + w] = v.m2; scratch[3 * nw + w] = v.m3;
+      scratch[4 * nw + w] = v.sum;
+    }
+    __syncthreads();
+    r5 t{scratch[0], scratch[nw], scratch[2 * nw], scratch[3 * nw], 0.0};
+#pragma unroll
+    for (int w = 1; w < nw; ++w) {
+      t.m0 = nanmax(t.m0, scratch[w]);
+      t.m1 = nanmax(t.m1, scratch[nw + w]);
+      t.m2 = nanmax(t.m2, scratch[2 * nw + w]);
+      t.m3 = nanmax(t.m3, scratch[3 * nw + w]);
+    }
+#pragma unroll
+    for (int w = 0; w < nw; ++w) t.sum += scratch[4 * nw + w];
+    __syncthreads();
+    return t;
+  }
 };
 #endif
 
@@ -151,6 +247,17 @@ struct HostExec {
     double m = f(0);
     for (int t = 1; t < kThreads; ++t) m = nanmax(m, f(t));
     return m;
+  }
+  template <class F>
+  r5 max4sum(double*, F f) {
+    r5 out = f(0);
+    for (int t = 1; t < kThreads; ++t) {
+      const r5 x = f(t);
+      out.m0 = nanmax(out.m0, x.m0); out.m1 = nanmax(out.m1, x.m1); out.m2 = nanmax(out.m2, x.m2);
+      out.m3 = nanmax(out.m3, x.m3);
+    }
+    out.sum = sum([&](int t) { return f(t).sum; });
+    return out;
   }
 };
 #endif

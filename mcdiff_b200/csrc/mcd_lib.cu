@@ -519,6 +519,17 @@ int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t 
   return (int)cudaGetLastError();
 }
 
+#if defined(MCD_PHASE_CLOCK)
+// debug build only (profiles/prof_phases.py): read and reset the phase clocks of CTA 0
+int mcd_debug_phase_clocks(long long* out32) {
+  long long z[32] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, mcd::g_phase_clk, sizeof(z));
+  cudaMemcpyToSymbol(mcd::g_phase_clk, z, sizeof(z));
+  return (int)cudaGetLastError();
+}
+#endif
+
 int mcd_fp64_peak(mcd_handle* h, double* tflops) {
   if (!h || !tflops) return MCD_E_ARG;
   CUDA_TRY(cudaSetDevice(h->device));
