@@ -32,7 +32,7 @@ MC_PER_LAUNCH = 200
 NCOS_F, NCOS_D = 10, 6           # the reference's own example model (examples/example-HexdWat-run1.sh)
 DV = DW = 0.05
 NMC_UPDATE = 1000.0
-NCU_DRAM_BYTES_PER_LAUNCH = 4115968 + 7168
+NCU_DRAM_BYTES_PER_LAUNCH = 3954944 + 56320
 METRIC = "MC steps/sec (all chains, 100 bins x 4 lags)"
 UNIT = "MC steps/s"
 
@@ -322,7 +322,7 @@ def run_gpu(args):
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this configuration
-                     # (ncu --set full, profiles/r01_ncu_full_mc_run_bench_launch.csv): 4.12 MB
+                     # (ncu --set full, profiles/r01_ncu_full_mc_run_final.csv): 4.0 MB
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (nch, MC_PER_LAUNCH) == (1024, 200) else None,
                      "traffic_unit": "bytes of DRAM traffic per launch (ncu); the kernel is not HBM bound",
                      "peak_source": "measured here by mcd_fp64_peak (dense DFMA loop); MEASURED_PEAKS.json has no FP64 "

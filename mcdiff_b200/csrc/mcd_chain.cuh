@@ -905,11 +905,13 @@ struct Chain {
                            int store) {
     const int n = P.n, np = P.np, ld = P.ld;
     const int ntasks = s.sc->mma_tasks;
+    MCD_CLK(17);
     ex.par([&](int tid) {
       const int warp = tid >> 5, lane = tid & 31;
       const WarpTask task = load_task(warp, ntasks);
       const bool active = warp < ntasks;
       const int nt = task.nt, na = task.na, rowA = task.rowA, rowB = task.rowB;
+      MCD_CLK(18);
       double c[kTilesPerWarp][2];
 #pragma unroll
       for (int t = 0; t < kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
@@ -1409,24 +1411,49 @@ struct Chain {
           }
 #endif
         }
-        double part = 0.0;
+        // likelihood epilogue, branch-free over the 16 entries like dmma_product (clipped entries redone after)
+        if (epi) {
+          const double gmin = s.sc->gmin;
+          double part = 0.0;
+          bool rare = false;
 #pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) {
-          if (t < nt) {
+          for (int t = 0; t < kTilesPerWarp; ++t) {
             const int ib = (t < na) ? rowA : rowB, jb = jbs[t];
-            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
-            if (epi) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gi = i_off + ib * 8 + fr, gj = j_off + jb * 8 + 2 * fk + e;
+              const bool valid = (t < nt) && !(sym && ib == jb && gj < gi);
+              const double g = c[t][e];
+              const bool above = g >= gmin;
+              const int ns = valid ? nsv[t][e] : 0;
+              rare |= (ns != 0) && !above;
+              part += (double)(above ? ns : 0) * fast_log(above ? g : 1.0);
+            }
+          }
+          if (rare || Pl) {
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const int ib = (t < na) ? rowA : rowB, jb = jbs[t];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int gi = i_off + i, gj = j_off + j + e;
-                if (sym && ib == jb && gj < gi) continue;
-                part += pair_term(c[t][e], nsv[t][e], gi, gj, cnt);
+                const int gi = i_off + ib * 8 + fr, gj = j_off + jb * 8 + 2 * fk + e;
+                if (!(t < nt) || (sym && ib == jb && gj < gi)) continue;
+                if (nsv[t][e] != 0 && !(c[t][e] >= gmin))
+                  part += pair_term_clipped(c[t][e], nsv[t][e], gi, gj, cnt, P.np, P.clip, s.ea, s.eb, s.hv);
                 if (Pl && gi < n && gj < n) {
                   Pl[(size_t)gi * n + gj] = s.ea[gi] * c[t][e] * s.eb[gj];
                   Pl[(size_t)gj * n + gi] = s.ea[gj] * c[t][e] * s.eb[gi];
                 }
               }
             }
+          }
+          s.part[tid] += part;
+        }
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          if (t < nt) {
+            const int ib = (t < na) ? rowA : rowB, jb = jbs[t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
             st2(D + (size_t)i * ldg + j, c[t][0], c[t][1]);
             if (fin) {
               if (!sym) {
@@ -1439,7 +1466,6 @@ struct Chain {
             }
           }
         }
-        if (epi) s.part[tid] += part;
       });
     }
   }
