@@ -474,8 +474,9 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
   const size_t per_cta = rad_workspace_doubles(R) * sizeof(double);
   int rc = ensure_gws(h, (size_t)grid * per_cta);
   if (rc != MCD_OK) return rc;
-  const size_t smem = rad_smem_bytes(R);
-  if (smem > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
+  const size_t smem = rad_smem_bytes(R, R.nbatch);
   CUDA_TRY(cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mcd_rad_loglike_kernel<<<grid, kThreads, smem, st>>>(R, B, wrad, out_ll, out_P, status, h->gws);
   h->launches++;
@@ -507,8 +508,9 @@ int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t 
   if (prc != MCD_OK) return prc;
   int rc = ensure_gws(h, (size_t)nchains * rad_workspace_doubles(R) * sizeof(double));
   if (rc != MCD_OK) return rc;
-  const size_t smem = rad_smem_bytes(R);
-  if (smem > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
+  R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
+  const size_t smem = rad_smem_bytes(R, R.nbatch);
   RadMcParams mp;
   RadChainIO cio;
   std::memcpy(&mp, params, sizeof(mp));

@@ -24,19 +24,30 @@ struct RadProblem {
   const double* bessels;   // [lmax][dim_rad]
   const double* b0zeros;   // [lmax]
   double clip;
+  int nbatch;              // Bessel terms whose work matrices fit in shared memory side by side (>= 1)
+  int reserved;
   LagPlan plan;            // squaring-engine route to the lag times (plan.ok == 0: eigen fallback)
 };
 
 constexpr int kMaxBessel = 64;
+constexpr int kMaxRadBatch = 6;   // Bessel terms advanced in lockstep by the squaring route
 
 MCD_HOSTDEV size_t rad_workspace_doubles(const RadProblem& R) {
   const size_t eig = (size_t)R.lmax * R.np * R.ld + (size_t)R.lmax * R.np;
-  const size_t sq = ((size_t)R.nlag * R.lmax + kMaxSlots) * R.np * R.ld;
+  const size_t sq = ((size_t)R.nlag * R.lmax + (size_t)kMaxSlots * kMaxRadBatch) * R.np * R.ld;
   return eig > sq ? eig : sq;
 }
-MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R) {
-  return smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) + ((size_t)R.np + (size_t)R.lmax * R.np) * 8 +
-         (((size_t)R.n * (R.n + 1) + 15) & ~(size_t)15);   // + pair table
+// shared memory: nbatch pairs of work matrices, the chain vectors, a0[np], elm[lmax][np] (eigen fallback),
+// exp(wrad)[np], the batch diagonals [nbatch][np], the pair table
+MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R, int nbatch) {
+  return (size_t)nbatch * smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) +
+         ((size_t)2 * R.np + (size_t)R.lmax * R.np + (size_t)nbatch * R.np) * 8 +
+         (((size_t)R.n * (R.n + 1) + 15) & ~(size_t)15);
+}
+MCD_HOSTDEV int rad_pick_batch(const RadProblem& R, size_t smem_cap) {
+  int nb = 1;
+  while (nb < kMaxRadBatch && nb < R.lmax && rad_smem_bytes(R, nb + 1) <= smem_cap) ++nb;
+  return nb;
 }
 
 // Monte-Carlo schedule and per-chain state of the radial loop (lib/mc.py:29-30,
@@ -83,6 +94,8 @@ struct RadCtx {
   double* ws_x;    // squaring: [lmax][nlag][np][ld] kernels; eigen: [lmax][np][ld] eigenvectors (global, L2 resident)
   double* ws_lam;  // [lmax][np]
   const unsigned char* ptab;  // (i, j) of the pairs i <= j, row-major
+  double* ewr;     // [np] exp(wrad)
+  double* ab;      // [nbatch][np] diagonals of the Bessel terms of the current batch
 
   // log(max(p, clip)), lib/twod.py:29; the table-based logarithm needs a positive normal argument
   __device__ __forceinline__ double clipped_log(double p) const {
@@ -90,37 +103,234 @@ struct RadCtx {
     return (x >= 1.0e-300) ? ch.fast_log(x) : log(x);
   }
 
-  // Squaring route: kernels of all lag times per Bessel term -> workspace [nlag][lmax][np][ld]
-  // (+ the plan's slots behind it), then the Bessel sums and the logarithms per pair.
+  // ---- batched squaring route ------------------------------------------------------------
+  // The work matrices of a radial problem are small (n ~ 30-60: one product keeps only 2-4 of the 12
+  // warps busy and every phase costs a barrier), so NB Bessel terms advance in LOCKSTEP: their work
+  // matrices sit side by side in two shared-memory banks, a Horner pass / a product handles all of
+  // them at once (warp w -> term w / T1, warp task w % T1), and the squaring count is the batch
+  // maximum (a smaller step h only makes the Taylor part more accurate).  S_m differs from S only in
+  // its diagonal (ab).  Workspace layout [nlag][lmax][np][ld], the plan's slots (NB matrices each) behind.
+
+  // D_b <- X_b Y_b for the nb terms of the batch (banks X, Y, D: nb matrices each, stride me)
+  __device__ __forceinline__ void batch_product(const double* X, const double* Y, double* D, int nb, int T1, int store) {
+    const int np = R.np, ld = R.ld;
+    const size_t me = (size_t)np * ld;
+    using CH = Chain<DeviceExec>;
+    ex.par([&](int tid) {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int b = warp / T1, tsk = warp - b * T1;
+      const bool active = b < nb;
+      const CH::WarpTask task = ch.load_task(tsk, active ? T1 : 0);
+      double c[CH::kTilesPerWarp][2];
+#pragma unroll
+      for (int t = 0; t < CH::kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+      const int fr = lane >> 2, fk = lane & 3;
+#if defined(__CUDA_ARCH__)
+      if (active) {
+        int offB[CH::kTilesPerWarp];
+#pragma unroll
+        for (int t = 0; t < CH::kTilesPerWarp; ++t) offB[t] = task.jb[t] * 64;
+        const unsigned ax = (unsigned)__cvta_generic_to_shared(X + b * me) + (unsigned)(fk * ld + fr) * 8u;
+        const unsigned ay = (unsigned)__cvta_generic_to_shared(Y + b * me) + (unsigned)(fk * ld + fr) * 8u;
+        const int pitch4 = 4 * ld * 8, nk4 = np / 4;
+        switch (task.na) {
+          case 1: CH::mma_loop<1>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 2: CH::mma_loop<2>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 3: CH::mma_loop<3>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 4: CH::mma_loop<4>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 5: CH::mma_loop<5>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 6: CH::mma_loop<6>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          case 7: CH::mma_loop<7>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+          default: CH::mma_loop<8>(ax, ay, pitch4, nk4, task.rowA * 64, task.rowB * 64, offB, c); break;
+        }
+      }
+#endif
+      double* r = ex.regs(tid);
+#pragma unroll
+      for (int t = 0; t < CH::kTilesPerWarp; ++t) { r[2 * t] = c[t][0]; r[2 * t + 1] = c[t][1]; }
+      if (store == 1 && active) ch.dmma_store(D + b * me, task, lane, r);
+    });
+    if (store == 2) {
+      ex.par([&](int tid) {
+        const int warp = tid >> 5;
+        const int b = warp / T1, tsk = warp - b * T1;
+        if (b < nb) ch.dmma_store(D + b * me, ch.load_task(tsk, T1), tid & 31, ex.regs(tid));
+      });
+    }
+  }
+
+  __device__ __forceinline__ void batch_copy(double* dst, const double* src, int nb) {
+    const int total = nb * R.np * R.ld;
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < total; e += 2 * kThreads) {
+        const d2 x = ld2(src + e);
+        st2(dst + e, x.x, x.y);
+      }
+    });
+  }
+
+  // exp(t S_b) for the nb terms of the batch: Taylor/Horner + squarings.  bank0 / bank1: NB matrices
+  // each.  Returns the bank holding the results (*other: the second one), nullptr for an absurd scale.
+  __device__ __forceinline__ double* batch_chain(double t, double gersh, int nb, int NB, int T1, double* bank0,
+                                                 double* bank1, double** other) {
+    const int n = R.n, np = R.np, ld = R.ld;
+    const size_t me = (size_t)np * ld;
+    const double rho = t * gersh;
+    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
+    int nsq = 0;
+    if (rho > 1.0) {
+      int ex2;
+      const double fr2 = frexp(rho, &ex2);
+      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
+    }
+    const double h = ldexp(t, -nsq);
+    const int m = s.tord[nsq];
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < (int)(2 * NB * me); e += 2 * kThreads) st2(bank0 + e, 0.0, 0.0);   // both banks (contiguous)
+      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);
+    });
+    ex.par([&](int tid) {
+      for (int e = tid; e < nb * n; e += kThreads) {
+        const int b = e / n, i = e - b * n;
+        bank0[b * me + i * ld + i] = 1.0;
+      }
+    });
+    double* src = bank0;
+    double* dst = bank1;
+    const int tpr = (kThreads / n > 1) ? kThreads / n : 1;
+    for (int tt = 1; tt <= m; ++tt) {
+      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
+      const bool full = (width == n);
+      ex.par([&](int tid) {
+        const int i = s.hrow[tid], r = s.hrem[tid];
+        if (i < n) {
+          const double f = s.red[tt];
+          const int im = (i == 0) ? n - 1 : i - 1;
+          const int ip = (i == n - 1) ? 0 : i + 1;
+          const double bm = f * s.b[im], bp = f * s.b[i];
+          for (int dd0 = r; dd0 < width; dd0 += 4 * tpr) {
+            int jq[4];
+            bool ok[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int dd = dd0 + q * tpr;
+              bool o = dd < width;
+              int j = dd;
+              if (!full) {
+                j = i - tt + dd;
+                if (R.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
+                else o = o && j >= 0 && j < n;
+              }
+              ok[q] = o;
+              jq[q] = o ? j : i;
+            }
+            for (int b = 0; b < nb; ++b) {
+              const double ai = f * ab[b * np + i];
+              const double* MCD_RESTRICT s0 = src + b * me + i * ld;
+              const double* MCD_RESTRICT sm = src + b * me + im * ld;
+              const double* MCD_RESTRICT sp = src + b * me + ip * ld;
+              double* MCD_RESTRICT d0 = dst + b * me + i * ld;
+              double x0[4], xm[4], xp[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { x0[q] = s0[jq[q]]; xm[q] = sm[jq[q]]; xp[q] = sp[jq[q]]; }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (ok[q]) d0[jq[q]] = ((i == jq[q]) ? 1.0 : 0.0) + (ai * x0[q] + bm * xm[q] + bp * xp[q]);
+            }
+          }
+        }
+      });
+      double* tmp = src; src = dst; dst = tmp;
+    }
+    double* G = src;
+    double* O = dst;
+    for (int q = 0; q < nsq; ++q) {
+      batch_product(G, G, O, nb, T1, 1);
+      double* tmp = G; G = O; O = tmp;
+    }
+    *other = O;
+    return G;
+  }
+
+  // Squaring route: kernels of all lag times per Bessel term -> workspace, then the Bessel sums and the
+  // logarithms per pair.
   __device__ __forceinline__ double loglike_sq(const double* wrad_vec, double* Pb, int* bad_out) {
     const int n = R.n, np = R.np, ld = R.ld, lmax = R.lmax, dim_rad = R.dim_rad;
     const double rmax = (double)dim_rad;
     const size_t me = (size_t)np * ld;
+    const LagPlan& pl = R.plan;
+    const int T1 = s.sc->mma_tasks;
+    int NB = R.nbatch;
+    if (NB * T1 > kThreads / 32) NB = (kThreads / 32) / T1;
+    double* bank0 = s.XT;
+    double* bank1 = s.XT + (size_t)NB * me;
     double* slots = ws_x + (size_t)R.nlag * lmax * me;
-    const bool use_mma = ch.dmma_ok();
+    const bool fast = pl.fast != 0;
     int bad = 0;
-    for (int m = 0; m < lmax && !bad; ++m) {
-      const double z = R.b0zeros[m];
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += kThreads) ewr[i] = (i < n) ? exp(wrad_vec[i]) : 0.0;
+    });
+    for (int m0 = 0; m0 < lmax && !bad; m0 += NB) {
+      const int nb = (lmax - m0 < NB) ? lmax - m0 : NB;
       ex.par([&](int tid) {
-        for (int i = tid; i < np; i += kThreads)
-          s.a[i] = (i < n) ? a0[i] - exp(wrad_vec[i]) * z * z / (rmax * rmax) : 0.0;  // lib/twod.py:113-117
+        for (int e = tid; e < nb * np; e += kThreads) {
+          const int b = e / np, i = e - b * np;
+          const double z = R.b0zeros[m0 + b];
+          ab[e] = (i < n) ? a0[i] - ewr[i] * z * z / (rmax * rmax) : 0.0;  // lib/twod.py:113-117
+        }
       });
       const double gersh = ex.max([&](int tid) {
         double mx = 0.0;
-        for (int i = tid; i < n; i += kThreads) {
+        for (int e = tid; e < nb * n; e += kThreads) {
+          const int b = e / n, i = e - b * n;
           const int im = (i == 0) ? n - 1 : i - 1;
-          const double r = fabs(s.a[i]) + s.b[im] + s.b[i];
+          const double r = fabs(ab[b * np + i]) + s.b[im] + s.b[i];
           mx = (r > mx || r != r) ? r : mx;
         }
         return mx;
       });
-      // workspace layout [lmax][nlag][np][ld]: kernels_sq writes the nlag kernels of term m contiguously
-      if (!ch.kernels_sq(R.lagtimes, R.plan, slots, ws_x + (size_t)m * R.nlag * me, gersh, use_mma)) bad = 1;
+      // ---- LagPlan walk (same as Chain::kernels_sq) on the whole batch ----
+      double* Rk = nullptr;
+      double* O = nullptr;
+      for (int c = 0; c < pl.nchain && !bad; ++c) {
+        const double t = R.lagtimes[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? R.lagtimes[pl.chain_b[c]] : 0.0);
+        double* other = nullptr;
+        MCD_CLK(22);
+        double* G = batch_chain(t, gersh, nb, NB, T1, bank0, bank1, &other);
+        MCD_CLK(23);
+        if (!G) { bad = 1; break; }
+        if (!fast && pl.chain_slot[c] >= 0) batch_copy(slots + (size_t)pl.chain_slot[c] * NB * me, G, nb);
+        Rk = G;
+        O = other;
+      }
+      if (bad) break;
+      batch_copy(ws_x + ((size_t)pl.order[0] * lmax + m0) * me, Rk, nb);
+      double* G0 = Rk;
+      int in_O = -1;
+      for (int i = 1; i < R.nlag; ++i) {
+        const int l = pl.order[i];
+        const double* res = Rk;
+        if (fast || pl.op_slot[i] >= 0) {
+          if (fast) {
+            batch_product((i == 1) ? G0 : O, G0, O, nb, T1, (i == 1) ? 1 : 2);
+            res = O;
+          } else {
+            if (in_O != pl.op_slot[i]) {
+              batch_copy(O, slots + (size_t)pl.op_slot[i] * NB * me, nb);
+              in_O = pl.op_slot[i];
+            }
+            batch_product(Rk, O, Rk, nb, T1, 2);
+          }
+        }
+        batch_copy(ws_x + ((size_t)l * lmax + m0) * me, res, nb);
+        if (!fast && pl.park[i] >= 0) batch_copy(slots + (size_t)pl.park[i] * NB * me, Rk, nb);
+      }
     }
     if (bad) {
       if (bad_out) *bad_out = 1;
       return nan("");
     }
+    MCD_CLK(20);
     // ---- Bessel sums + logarithms.  The pairs i <= j are taken in chunks of CH: the lmax kernel
     //      entries of every pair of the chunk are staged in shared memory (the work matrices are free
     //      now), then thread (p, kg) handles the radial bins k = kg, kg + KG, ... of pair p ----
@@ -137,29 +347,60 @@ struct RadCtx {
             const int m = e / CH, p = e - m * CH;
             if (c0 + p < npairs) {
               const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
-              gs[e] = ws_x[((size_t)m * R.nlag + l) * me + (size_t)i * ld + j];
+              gs[e] = ws_x[((size_t)l * lmax + m) * me + (size_t)i * ld + j];
             }
           }
         });
+        // thread (p, kg): four radial bins at a time -- four independent Bessel sums, their count loads
+        // issued up front, and branch-free logarithms (this pass is latency bound like every scalar phase).
+        // P_ij = s_ij p_k and P_ji = s_ji p_k share ONE logarithm: log P_ij = log p_k + (v_j - v_i)/2,
+        // log P_ji = log p_k - (v_j - v_i)/2, each replaced by log(clip) when the entry is below the clip
+        // (lib/twod.py:29).
         ex.par([&](int tid) {
           const int kg = tid / CH, p = tid - kg * CH;
           if (kg < KG && c0 + p < npairs) {
             const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
             const double sij = s.ea[i] * s.eb[j], sji = s.ea[j] * s.eb[i];
+            const double dh = s.hv[j] - s.hv[i];
+            const double wji = (i != j) ? 1.0 : 0.0;
+            const double clip = R.clip, logclip = log(R.clip);
+            const size_t oij = (size_t)i * n + j, oji = (size_t)j * n + i;
             double part = 0.0;
-            for (int k = kg; k < dim_rad; k += KG) {
-              double pk = 0.0;
-              for (int m = 0; m < lmax; ++m) pk = fma(R.bessels[(size_t)m * dim_rad + k], gs[m * CH + p], pk);  // lib/twod.py:125-126
-              const size_t base = (((size_t)l * dim_rad + k) * n) * n;
-              const double pij = sij * pk;
-              const double nij = R.counts[base + (size_t)i * n + j];
-              if (nij != 0.0) part += nij * clipped_log(pij);
-              if (Pb) Pb[base + (size_t)i * n + j] = pij;
-              if (i != j) {
-                const double pji = sji * pk;
-                const double nji = R.counts[base + (size_t)j * n + i];
-                if (nji != 0.0) part += nji * clipped_log(pji);
-                if (Pb) Pb[base + (size_t)j * n + i] = pji;
+            for (int kb = kg; kb < dim_rad; kb += 4 * KG) {
+              int kk[4];
+              double wq[4], nij[4], nji[4], pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int k = kb + q * KG;
+                wq[q] = (k < dim_rad) ? 1.0 : 0.0;
+                kk[q] = (k < dim_rad) ? k : kg;
+                const size_t base = (((size_t)l * dim_rad + kk[q]) * n) * n;
+                nij[q] = R.counts[base + oij];
+                nji[q] = R.counts[base + oji];
+                pk[q] = 0.0;
+              }
+              for (int m = 0; m < lmax; ++m) {
+                const double g = gs[m * CH + p];
+                const double* brow = R.bessels + (size_t)m * dim_rad;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pk[q] = fma(brow[kk[q]], g, pk[q]);  // lib/twod.py:125-126
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const double pij = sij * pk[q], pji = sji * pk[q];
+                const double lp = ch.fast_log(fmax(pk[q], 1.0e-300));
+                const double lij = (pij >= clip) ? lp + dh : logclip;
+                const double lji = (pji >= clip) ? lp - dh : logclip;
+                part += wq[q] * (nij[q] * lij + wji * (nji[q] * lji));
+              }
+              if (Pb) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (wq[q] != 0.0) {
+                    const size_t base = (((size_t)l * dim_rad + kk[q]) * n) * n;
+                    Pb[base + oij] = sij * pk[q];
+                    Pb[base + oji] = sji * pk[q];
+                  }
               }
             }
             ex.regs(tid)[0] += part;
@@ -168,12 +409,13 @@ struct RadCtx {
       }
     }
     const double ll = ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+    MCD_CLK(21);
     if (bad_out) *bad_out = 0;
     return ll;
   }
 
   __device__ __forceinline__ double loglike(const double* wrad_vec, double* Pb, int* bad_out) {
-    if (R.plan.ok) return loglike_sq(wrad_vec, Pb, bad_out);
+    if (R.plan.ok && ch.dmma_ok()) return loglike_sq(wrad_vec, Pb, bad_out);
     return loglike_eig(wrad_vec, Pb, bad_out);
   }
 
@@ -256,11 +498,13 @@ struct RadCtx {
   P.ncosF = 0; P.ncosD = 0; P.lagtimes = R.lagtimes; P.counts = nullptr; P.nsym = nullptr; P.rvec = nullptr;     \
   P.v_basis = nullptr; P.w_basis = nullptr; P.svecs = nullptr; P.spring_k = 0.0; P.clip = R.clip;                \
   P.nbk = R.np; P.lds = R.ld; P.blocked = 0;                                                                    \
-  const size_t mat_bytes = smem_matrix_bytes(R.np, R.ld);                                                       \
+  const size_t mat_bytes = (size_t)R.nbatch * smem_matrix_bytes(R.np, R.ld);                                    \
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);                                 \
   double* a0 = reinterpret_cast<double*>(smem_raw + mat_bytes + smem_vectors_bytes(R.np));                       \
   double* elm = a0 + R.np;                                                                                      \
-  unsigned char* ptab = reinterpret_cast<unsigned char*>(elm + (size_t)R.lmax * R.np);                          \
+  double* ewr = elm + (size_t)R.lmax * R.np;                                                                    \
+  double* ab = ewr + R.np;                                                                                      \
+  unsigned char* ptab = reinterpret_cast<unsigned char*>(ab + (size_t)R.nbatch * R.np);                         \
   DeviceExec ex(s.red);                                                                                         \
   Chain<DeviceExec> ch(ex, P, s);                                                                               \
   ch.build_tables();                                                                                            \
@@ -282,7 +526,7 @@ struct RadCtx {
       for (int j = i; j < n; ++j) { ptab[2 * (row0 + j - i)] = (unsigned char)i; ptab[2 * (row0 + j - i) + 1] = (unsigned char)j; } \
     }                                                                                                           \
   });                                                                                                           \
-  RadCtx ctx{R, ex, ch, s, a0, elm, ws_x, ws_lam, ptab};
+  RadCtx ctx{R, ex, ch, s, a0, elm, ws_x, ws_lam, ptab, ewr, ab};
 
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, double* __restrict__ out_ll,
@@ -327,6 +571,7 @@ mcd_rad_mc_run_kernel(RadProblem R, RadMcParams mp, RadChainIO io, int nsteps, d
       sc->nsamp = 0;
     }
   });
+  MCD_CLK_BEGIN();
   for (int it = 0; it < nsteps; ++it) {
     ex.single([&]() {   // proposal: lib/MCState.py:308-317
       const long long imc = sc->step;
@@ -427,7 +672,9 @@ mcd_rad_mc_run_kernel(RadProblem R, RadMcParams mp, RadChainIO io, int nsteps, d
       }
       sc->step = j;
     });
+    MCD_CLK(24);
   }
+  MCD_CLK_END();
   ex.par([&](int tid) {
     for (int i = tid; i < n; i += kThreads) io.wrad[chain * n + i] = wcur[i];
     for (int c = tid; c < ncos; c += kThreads) io.wcoef[chain * ncos + c] = ccur[c];

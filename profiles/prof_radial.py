@@ -33,3 +33,16 @@ print("radial n=%d dim_rad=%d lmax=%d L=%d: %d chains x %d steps in %.3f s -> %.
           n, dim_rad, lmax, L, nch, nsteps, el, nch * nsteps / el, 1e3 * el / nsteps / max(1.0, nch / 148.0), t_init,
           abs(ll0[0] - ref) / abs(ref), t_cpu, nch * nsteps / el * t_cpu, st["counters"][:, 0].mean() / (nsteps + 2),
           st["counters"][:, 3].any()))
+
+if hasattr(eng.lib, "mcd_debug_phase_clocks"):      # -DMCD_PHASE_CLOCK build (MCDIFF_B200_LIB=...)
+    import ctypes as C
+    out = (C.c_longlong * 32)()
+    eng.lib.mcd_debug_phase_clocks(out)             # reset
+    ch.run(nsteps, num_mc_update=100, seed=1); torch.cuda.synchronize()
+    eng.lib.mcd_debug_phase_clocks(out)
+    names = {20: "lag products, copies to the workspace", 21: "Bessel sums + logarithms", 22: "batch diagonals, Gershgorin",
+             23: "Taylor/Horner + squarings of the batch", 24: "proposal, Metropolis, records"}
+    tot = float(sum(out))
+    print("cycles per MC step (CTA 0): %.0f" % (tot / nsteps))
+    for i in sorted(names):
+        print("%2d %-42s %9.0f cycles/step %5.1f %%" % (i, names[i], out[i] / nsteps, 100.0 * out[i] / tot))
