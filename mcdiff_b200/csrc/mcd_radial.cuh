@@ -252,6 +252,127 @@ struct RadCtx {
     return G;
   }
 
+  // Bessel sums on the FP64 tensor cores.  For a chunk of 96 pairs (one 8-pair tile per warp)
+  //   P[k][pair] = sum_m bessels[m][k] G_m[pair]          (lib/twod.py:125-126)
+  // is a (dim_rad x lmax) x (lmax x 96) product: A = bessels^T (fragments straight from L1), B = the
+  // kernel entries staged in shared memory (pitch 100: conflict-free fragment loads), one m8n8k4 per
+  // (8 radial bins, 8 pairs, 4 terms).  A lane ends up with 2 pairs x (dim_rad / 8) bins; their count
+  // loads are issued before the MMAs and the logarithms are branch-free (one per pair and bin:
+  // log P_ij = log p + (v_j - v_i)/2, log P_ji = log p - (v_j - v_i)/2, clip as lib/twod.py:29).
+  // Returns false (nothing done) when the shapes do not fit; the vector-pipe version below then runs.
+  static constexpr int kBinGroup = 6;   // radial-bin tiles (8 bins each) accumulated at a time
+  __device__ __forceinline__ bool bessel_sums_mma(double* Pb, int NB) {
+    const int n = R.n, np = R.np, ld = R.ld, lmax = R.lmax, dim_rad = R.dim_rad;
+    const size_t me = (size_t)np * ld;
+    constexpr int nwarp = kThreads / 32, CHT = 8 * nwarp, CHP = CHT + 4;
+    const int lpad = (lmax + 3) & ~3, mt = (dim_rad + 7) / 8;
+    if ((size_t)lpad * CHP > 2 * (size_t)NB * me) return false;
+    const int npairs = n * (n + 1) / 2;
+    double* gs = s.XT;   // [lpad][CHP]
+    const double clip = R.clip, logclip = log(R.clip);
+    for (int l = 0; l < R.nlag; ++l) {
+      for (int c0 = 0; c0 < npairs; c0 += CHT) {
+        ex.par([&](int tid) {
+          for (int e = tid; e < CHT * lpad; e += kThreads) {
+            const int m = e / CHT, p = e - m * CHT;
+            double g = 0.0;
+            if (m < lmax && c0 + p < npairs) {
+              const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
+              g = ws_x[((size_t)l * lmax + m) * me + (size_t)i * ld + j];
+            }
+            gs[m * CHP + p] = g;
+          }
+        });
+        ex.par([&](int tid) {
+          const int warp = tid >> 5, lane = tid & 31;
+          const int fr = lane >> 2, fk = lane & 3;
+          // this lane's two pairs and their count rows
+          int pi[2], pj[2];
+          double wv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int pr = c0 + 8 * warp + 2 * fk + e;
+            const bool okp = pr < npairs;
+            wv[e] = okp ? 1.0 : 0.0;
+            pi[e] = okp ? ptab[2 * pr] : 0;
+            pj[e] = okp ? ptab[2 * pr + 1] : 0;
+          }
+          double sij[2], sji[2], dh[2], wji[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            sij[e] = s.ea[pi[e]] * s.eb[pj[e]];
+            sji[e] = s.ea[pj[e]] * s.eb[pi[e]];
+            dh[e] = s.hv[pj[e]] - s.hv[pi[e]];
+            wji[e] = (pi[e] != pj[e]) ? wv[e] : 0.0;
+          }
+          double part = 0.0;
+          // bin tiles in groups of kBinGroup (registers: 3 x 2 x kBinGroup doubles per lane)
+          for (int t0 = 0; t0 < mt; t0 += kBinGroup) {
+            double nij[kBinGroup][2], nji[kBinGroup][2], c[kBinGroup][2];
+#pragma unroll
+            for (int t = 0; t < kBinGroup; ++t) {
+              c[t][0] = 0.0; c[t][1] = 0.0;
+              const int kb = 8 * (t0 + t) + fr;
+              const int kc = (kb < dim_rad) ? kb : dim_rad - 1;
+              const size_t base = (((size_t)l * dim_rad + kc) * n) * n;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                nij[t][e] = R.counts[base + (size_t)pi[e] * n + pj[e]];
+                nji[t][e] = R.counts[base + (size_t)pj[e] * n + pi[e]];
+              }
+            }
+#if defined(__CUDA_ARCH__)
+            const unsigned gb = (unsigned)__cvta_generic_to_shared(gs) + (unsigned)(fk * CHP + 8 * warp + fr) * 8u;
+            for (int k4 = 0; k4 < lpad / 4; ++k4) {
+              const double bfrag = Chain<DeviceExec>::lds64(gb + (unsigned)(k4 * 4 * CHP) * 8u);
+              const int term = 4 * k4 + fk;
+              const double* brow = R.bessels + (size_t)((term < lmax) ? term : lmax - 1) * dim_rad;
+#pragma unroll
+              for (int t = 0; t < kBinGroup; ++t) {
+                const int kb = 8 * (t0 + t) + fr;
+                const double afrag = __ldg(brow + ((kb < dim_rad) ? kb : dim_rad - 1));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[t][0]), "+d"(c[t][1])
+                             : "d"(afrag), "d"(bfrag));
+              }
+            }
+#endif
+#pragma unroll
+            for (int t = 0; t < kBinGroup; ++t) {
+              const double wk = (8 * (t0 + t) + fr < dim_rad) ? 1.0 : 0.0;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const double pk = c[t][e];
+                const double pij = sij[e] * pk, pji = sji[e] * pk;
+                const double lp = ch.fast_log(fmax(pk, 1.0e-300));
+                const double lij = (pij >= clip) ? lp + dh[e] : logclip;
+                const double lji = (pji >= clip) ? lp - dh[e] : logclip;
+                part += wk * (wv[e] * (nij[t][e] * lij) + wji[e] * (nji[t][e] * lji));
+              }
+            }
+            if (Pb) {
+#pragma unroll
+              for (int t = 0; t < kBinGroup; ++t) {
+                const int kb = 8 * (t0 + t) + fr;
+                if (kb < dim_rad) {
+                  const size_t base = (((size_t)l * dim_rad + kb) * n) * n;
+#pragma unroll
+                  for (int e = 0; e < 2; ++e)
+                    if (wv[e] != 0.0) {
+                      Pb[base + (size_t)pi[e] * n + pj[e]] = sij[e] * c[t][e];
+                      Pb[base + (size_t)pj[e] * n + pi[e]] = sji[e] * c[t][e];
+                    }
+                }
+              }
+            }
+          }
+          ex.regs(tid)[0] += part;
+        });
+      }
+    }
+    return true;
+  }
+
   // Squaring route: kernels of all lag times per Bessel term -> workspace, then the Bessel sums and the
   // logarithms per pair.
   __device__ __forceinline__ double loglike_sq(const double* wrad_vec, double* Pb, int* bad_out) {
@@ -336,6 +457,12 @@ struct RadCtx {
     //      now), then thread (p, kg) handles the radial bins k = kg, kg + KG, ... of pair p ----
     ex.par([&](int tid) { ex.regs(tid)[0] = 0.0; });
     const int npairs = n * (n + 1) / 2;
+    if (bessel_sums_mma(Pb, NB)) {
+      const double llm = ex.sum([&](int tid) { return ex.regs(tid)[0]; });
+      MCD_CLK(21);
+      if (bad_out) *bad_out = 0;
+      return llm;
+    }
     int CH = (int)((2 * me) / (size_t)lmax);
     CH = CH >= 128 ? 128 : (CH >= 64 ? 64 : (CH >= 32 ? 32 : CH));
     const int KG = kThreads / CH;
