@@ -1332,6 +1332,7 @@ struct Chain {
       }
 #endif
     });
+    MCD_CLK(25);
   }
 
   // One block: D (+)= A^T B.  sym: diagonal block (upper tiles, mirrored inside the block on the final
@@ -1380,6 +1381,7 @@ struct Chain {
             nsv[t][0] = qn[0]; nsv[t][1] = qn[1];
           }
         }
+        MCD_CLK(5);
         if (active) {
 #if defined(__CUDA_ARCH__)
           int offB[kTilesPerWarp];
@@ -1411,6 +1413,7 @@ struct Chain {
           }
 #endif
         }
+        MCD_CLK(6);
         // likelihood epilogue, branch-free over the 16 entries like dmma_product (clipped entries redone after)
         if (epi) {
           const double gmin = s.sc->gmin;
@@ -1449,6 +1452,7 @@ struct Chain {
           }
           s.part[tid] += part;
         }
+        MCD_CLK(7);
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
           if (t < nt) {
@@ -1466,7 +1470,9 @@ struct Chain {
             }
           }
         }
+        MCD_CLK(8);
       });
+      MCD_CLK(9);
     }
   }
 
@@ -1535,6 +1541,7 @@ struct Chain {
     build_S(v, w);
     const double gersh = s.sc->gersh;
     ex.par([&](int tid) { s.part[tid] = 0.0; });
+    MCD_CLK(2);
     int nsq_total = 0;
     bool bad = false;
     const int l0 = pl.order[0];
@@ -1628,6 +1635,7 @@ struct Chain {
         double* tmp = src; src = dst; dst = tmp;
       }
       }
+      MCD_CLK(4);
       double* G = src;
       double* O = dst;
       const int* cnt_e = is_first_lag ? P.counts + (size_t)l0 * np * np : nullptr;

@@ -26,3 +26,18 @@ t = time.time(); ch.run(nsteps, mp); torch.cuda.synchronize(); el = time.time() 
 st = ch.host_state()
 print("method %d" % mp.method, "n=200 L=8: %d chains x %d steps in %.3f s -> %.1f MC steps/s, %.2f ms per step per wave, sweeps/step %.2f, status %s, in_smem %s squaring_ok %s" % (
     nch, nsteps, el, nch * nsteps / el, 1e3 * el / nsteps, st["counters"][:, 7].sum() / st["counters"][:, 5].sum(), st["counters"][:, 6].any(), prob.in_smem, prob.squaring_ok))
+
+if hasattr(eng.lib, "mcd_debug_phase_clocks"):      # -DMCD_PHASE_CLOCK build (MCDIFF_B200_LIB=...)
+    import ctypes as C
+    out = (C.c_longlong * 32)()
+    eng.lib.mcd_debug_phase_clocks(out)
+    ch.run(nsteps, mp); torch.cuda.synchronize()
+    eng.lib.mcd_debug_phase_clocks(out)
+    names = {0: "proposal", 1: "trial profile", 2: "build_S + reductions", 4: "Taylor/Horner (band, shared memory) + expansion",
+             25: "panel staging (cp.async)", 5: "block prologue (task, partial sums, counts)", 6: "m8n8k4 k loop",
+             7: "likelihood epilogue", 8: "result stores (+ transpose)", 9: "barrier wait after block", 11: "final reduction",
+             12: "Metropolis", 13: "commit, records"}
+    tot = float(sum(out))
+    print("cycles per MC step (CTA 0): %.0f" % (tot / nsteps))
+    for i in sorted(names):
+        print("%2d %-50s %9.0f cycles/step %5.1f %%" % (i, names[i], out[i] / nsteps, 100.0 * out[i] / tot))
