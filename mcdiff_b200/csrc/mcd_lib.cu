@@ -472,8 +472,14 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
   if (prc != MCD_OK) return prc;
   const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
   const size_t per_cta = rad_workspace_doubles(R) * sizeof(double);
-  int rc = ensure_gws(h, (size_t)grid * per_cta);
+  int rc = ensure_gws(h, (size_t)grid * per_cta + rad_pcounts_doubles(R) * sizeof(double));
   if (rc != MCD_OK) return rc;
+  {   // pair-major copy of the counts behind the per-CTA workspaces (stream ordered before the main kernel)
+    double* pc = h->gws + (size_t)grid * rad_workspace_doubles(R);
+    mcd_rad_pair_counts_kernel<<<2 * h->sm_count, 256, 0, st>>>(counts, pc, nlag, dim_rad, n);
+    h->launches++;
+    R.pcounts = pc;
+  }
   if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
   R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
   const size_t smem = rad_smem_bytes(R, R.nbatch);
@@ -506,8 +512,14 @@ int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t 
   R.clip = clip;
   int prc = rad_plan(R, st);
   if (prc != MCD_OK) return prc;
-  int rc = ensure_gws(h, (size_t)nchains * rad_workspace_doubles(R) * sizeof(double));
+  int rc = ensure_gws(h, ((size_t)nchains * rad_workspace_doubles(R) + rad_pcounts_doubles(R)) * sizeof(double));
   if (rc != MCD_OK) return rc;
+  {
+    double* pc = h->gws + (size_t)nchains * rad_workspace_doubles(R);
+    mcd_rad_pair_counts_kernel<<<2 * h->sm_count, 256, 0, st>>>(counts, pc, nlag, dim_rad, n);
+    h->launches++;
+    R.pcounts = pc;
+  }
   if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
   R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
   const size_t smem = rad_smem_bytes(R, R.nbatch);

@@ -21,6 +21,7 @@ struct RadProblem {
   const double* w;         // [dim_w]
   const double* lagtimes;  // [nlag]
   const double* counts;    // [nlag][dim_rad][n][n]
+  const double* pcounts;   // [nlag][dim_rad][rad_pairs_padded(n)][2] = {N_ij, N_ji (0 when i == j)} per pair i <= j (library scratch)
   const double* bessels;   // [lmax][dim_rad]
   const double* b0zeros;   // [lmax]
   double clip;
@@ -43,6 +44,11 @@ MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R, int nbatch) {
   return (size_t)nbatch * smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) +
          ((size_t)2 * R.np + (size_t)R.lmax * R.np + (size_t)nbatch * R.np) * 8 +
          (((size_t)R.n * (R.n + 1) + 15) & ~(size_t)15);
+}
+// pairs i <= j, padded so that the two-pair (32-byte) loads of the Bessel-sum epilogue stay in bounds
+MCD_HOSTDEV size_t rad_pairs_padded(int n) { return (((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1) + 2; }
+MCD_HOSTDEV size_t rad_pcounts_doubles(const RadProblem& R) {
+  return (size_t)R.nlag * R.dim_rad * rad_pairs_padded(R.n) * 2;
 }
 MCD_HOSTDEV int rad_pick_batch(const RadProblem& R, size_t smem_cap) {
   int nb = 1;
@@ -309,17 +315,18 @@ struct RadCtx {
           // bin tiles in groups of kBinGroup (registers: 3 x 2 x kBinGroup doubles per lane)
           for (int t0 = 0; t0 < mt; t0 += kBinGroup) {
             double nij[kBinGroup][2], nji[kBinGroup][2], c[kBinGroup][2];
+            // counts of this lane's two pairs: one 32-byte piece of the pair-major copy per radial bin
+            const size_t npp = rad_pairs_padded(n);
+            const size_t pr0 = (size_t)(c0 + 8 * warp + 2 * fk);
+            const size_t prc = (pr0 + 2 <= npp) ? pr0 : npp - 2;
 #pragma unroll
             for (int t = 0; t < kBinGroup; ++t) {
               c[t][0] = 0.0; c[t][1] = 0.0;
               const int kb = 8 * (t0 + t) + fr;
               const int kc = (kb < dim_rad) ? kb : dim_rad - 1;
-              const size_t base = (((size_t)l * dim_rad + kc) * n) * n;
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                nij[t][e] = R.counts[base + (size_t)pi[e] * n + pj[e]];
-                nji[t][e] = R.counts[base + (size_t)pj[e] * n + pi[e]];
-              }
+              const double* q = R.pcounts + (((size_t)l * dim_rad + kc) * npp + prc) * 2;
+              const d2 x0 = ld2(q), x1 = ld2(q + 2);
+              nij[t][0] = x0.x; nji[t][0] = x0.y; nij[t][1] = x1.x; nji[t][1] = x1.y;
             }
 #if defined(__CUDA_ARCH__)
             const unsigned gb = (unsigned)__cvta_generic_to_shared(gs) + (unsigned)(fk * CHP + 8 * warp + fr) * 8u;
@@ -617,6 +624,26 @@ struct RadCtx {
     return bad ? nan("") : ll;
   }
 };
+
+// pair-major copy of the radial counts (see RadProblem::pcounts)
+__global__ void mcd_rad_pair_counts_kernel(const double* __restrict__ counts, double* __restrict__ out, int L, int dim_rad,
+                                           int n) {
+  const size_t npp = rad_pairs_padded(n);
+  const size_t planes = (size_t)L * dim_rad;
+  for (size_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const double* src = counts + pl * n * n;
+    double* dst = out + pl * npp * 2;
+    const int npairs = n * (n + 1) / 2;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (j < i) continue;
+      const int p = i * n - i * (i - 1) / 2 + (j - i);
+      dst[2 * p] = src[(size_t)i * n + j];
+      dst[2 * p + 1] = (i != j) ? src[(size_t)j * n + i] : 0.0;
+    }
+    for (size_t e = (size_t)2 * npairs + threadIdx.x; e < 2 * npp; e += blockDim.x) dst[e] = 0.0;
+  }
+}
 
 #define MCD_RAD_SETUP()                                                                                         \
   extern __shared__ __align__(16) unsigned char smem_raw[];                                                     \
