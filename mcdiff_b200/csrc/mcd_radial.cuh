@@ -278,15 +278,25 @@ struct RadCtx {
     const double clip = R.clip, logclip = log(R.clip);
     for (int l = 0; l < R.nlag; ++l) {
       for (int c0 = 0; c0 < npairs; c0 += CHT) {
-        ex.par([&](int tid) {
-          for (int e = tid; e < CHT * lpad; e += kThreads) {
-            const int m = e / CHT, p = e - m * CHT;
-            double g = 0.0;
-            if (m < lmax && c0 + p < npairs) {
-              const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
-              g = ws_x[((size_t)l * lmax + m) * me + (size_t)i * ld + j];
+        ex.par([&](int tid) {   // staging: eight independent L2 loads in flight per thread
+          for (int e0 = tid; e0 < CHT * lpad; e0 += 8 * kThreads) {
+            double g[8];
+            int dst[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int e = e0 + q * kThreads;
+              const int m = e / CHT, p = e - m * CHT;
+              const bool inr = e < CHT * lpad;
+              const bool live = inr && m < lmax && c0 + p < npairs;
+              const int pr = live ? c0 + p : 0;
+              const int i = ptab[2 * pr], j = ptab[2 * pr + 1];
+              const double x = ws_x[((size_t)l * lmax + (live ? m : 0)) * me + (size_t)i * ld + j];
+              g[q] = live ? x : 0.0;
+              dst[q] = inr ? m * CHP + p : -1;
             }
-            gs[m * CHP + p] = g;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (dst[q] >= 0) gs[dst[q]] = g[q];
           }
         });
         ex.par([&](int tid) {
