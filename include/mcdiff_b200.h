@@ -58,7 +58,10 @@ enum {
  *             GEMMs on shared-memory operands.  Lag times are visited in ascending order,
  *             G(t_i) = G(t_{i-1}) G(t_i - t_{i-1}); every distinct operand is an earlier G(t_j) or gets its
  *             own squaring chain (at most 8), so arithmetic progressions (10,20,30,40 / a single lag) need
- *             one chain, time-offset moves (--t0) two.  Needs n <= 104 (work matrices in shared memory). */
+ *             one chain, time-offset moves (--t0) two.  n <= 104: work matrices in shared memory;
+ *             104 < n <= 208: blocked (matrices in a per-chain global workspace, 2 x 2 block products
+ *             through shared-memory operand panels; tensor-core products only, no SQUARING_DFMA);
+ *             larger n: EIGEN only. */
 enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2,
        MCD_METHOD_SQUARING_DFMA = 3 /* same algorithm, products on the FP64 vector pipe (A/B reference) */ };
 
@@ -93,7 +96,8 @@ typedef struct {
   int32_t refresh_every; /* cold eigen re-solve period (0 = never); 512 is a good default */
   int32_t use_tape;      /* 1: proposals and uniforms come from tape_u / tape_idx */
   int32_t method;        /* MCD_METHOD_*: propagator engine (AUTO picks SQUARING when it applies) */
-  int32_t taylor_m;      /* Taylor order of the squaring engine, 0 = default (20) */
+  int32_t taylor_m;      /* Taylor order of the squaring engine, 0 = adaptive (smallest order with a
+                            truncation error <= 1e-17 after the squarings, 6..24); values > 31 are clamped */
   uint64_t seed;         /* Philox4x32-10 key */
   int64_t chain_offset;  /* global index of chain 0 (chains shard over GPUs) */
   int64_t tape_stride;   /* 0: one tape for all chains, else per-chain stride (in steps) */

@@ -71,9 +71,52 @@ __global__ void __launch_bounds__(T, 1) bench(double* out, long long* cyc, int r
           dst[i * ld + j] = ((i == j) ? 1.0 : 0.0) + f * (a[i] * src[i * ld + j] + b[im] * src[im * ld + j] + b[i] * src[ip * ld + j]);
         }
       } else if (V == 2) {   // empty pass (barrier only)
+      } else if (V == 3) {   // two Horner steps per pass: H <- I + f1 S + f1 f2 S^2 H  (pentadiagonal), every second tt
+        if (tt & 1) {
+          const int i = hrow[tid], r = hrem[tid];
+          const int w2 = (tt + 1 <= M) ? tt + 1 : tt;      // half-width after this pass
+          const int width2 = 2 * w2 + 1;
+          if (i < n) {
+            const double f1 = fac[tt], f2 = fac[tt + 1];
+            const int im = (i == 0) ? n - 1 : i - 1, ip = (i == n - 1) ? 0 : i + 1;
+            const int im2 = (im == 0) ? n - 1 : im - 1, ip2 = (ip == n - 1) ? 0 : ip + 1;
+            const double ai = a[i], am = a[im], ap = a[ip], bi = b[i], bm = b[im], bm2 = b[im2], bp = b[ip];
+            const double g = f1 * f2;
+            const double cm2 = g * bm2 * bm, cm1 = g * bm * (am + ai), c0 = g * (ai * ai + bm * bm + bi * bi),
+                         cp1 = g * bi * (ai + ap), cp2 = g * bi * bp;
+            const double sa = f1 * ai, sbm = f1 * bm, sbp = f1 * bi;
+            const double* __restrict__ r0 = src + i * ld;
+            const double* __restrict__ r1 = src + im * ld;
+            const double* __restrict__ r2 = src + ip * ld;
+            const double* __restrict__ r3 = src + im2 * ld;
+            const double* __restrict__ r4 = src + ip2 * ld;
+            double* __restrict__ d0 = dst + i * ld;
+            for (int dd0 = r; dd0 < width2; dd0 += 4 * tpr) {
+              int jq[4]; bool ok[4]; double lin[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int dd = dd0 + q * tpr;
+                const bool o = dd < width2;
+                const int off = dd - w2;               // column offset j - i
+                int j = i + off;
+                if (j < 0) j += n; else if (j >= n) j -= n;
+                ok[q] = o; jq[q] = o ? j : i;
+                lin[q] = (off == 0) ? 1.0 + sa : ((off == -1) ? sbm : ((off == 1) ? sbp : 0.0));
+              }
+              double x0[4], x1[4], x2[4], x3[4], x4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { x0[q] = r0[jq[q]]; x1[q] = r1[jq[q]]; x2[q] = r2[jq[q]]; x3[q] = r3[jq[q]]; x4[q] = r4[jq[q]]; }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (ok[q]) d0[jq[q]] = lin[q] + (c0 * x0[q] + cm1 * x1[q] + cp1 * x2[q] + cm2 * x3[q] + cp2 * x4[q]);
+            }
+          }
+        }
       }
-      __syncthreads();
-      double* tmp = src; src = dst; dst = tmp;
+      if (V != 3 || (tt & 1)) {
+        __syncthreads();
+        double* tmp = src; src = dst; dst = tmp;
+      }
     }
     tot += clock64() - t0;
   }
@@ -105,5 +148,6 @@ int main() {
   run<2>("barrier only", out, cyc);
   run<0>("library walk (row slots, chunks of 4)", out, cyc);
   run<1>("flat elements, e / width", out, cyc);
+  run<3>("two steps per pass (pentadiagonal)", out, cyc);
   return 0;
 }
