@@ -148,8 +148,9 @@ int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, in
 /* log L of B profiles: out_ll[b] = sum_l sum_ij counts[l,i,j] log(max(P_l[i,j], clip)) with
  * P_l = expm(lag_l R(v_b, w_b)).  lagtimes == NULL uses the problem's lag times, otherwise
  * [B][nlag] per-profile lag times (time-offset moves).  out_P (optional) receives
- * [B][nlag][n][n] propagators, status (optional) [B] status bits.  method: MCD_METHOD_AUTO = EIGEN here
- * (the batched call is also the independent cross-check of the squaring engine).
+ * [B][nlag][n][n] propagators, status (optional) [B] status bits.  method: MCD_METHOD_AUTO = SQUARING when
+ * it applies to the problem and no per-profile lag times are given (componentwise accurate), else EIGEN;
+ * an explicit MCD_METHOD_EIGEN is the independent cross-check of the squaring engine.
  * Replaces log_like_lag, lib/utils.py:355-368. */
 int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
                       const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,

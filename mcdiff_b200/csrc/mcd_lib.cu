@@ -356,7 +356,7 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
                       const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
                       void* stream) {
   if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
-  if (method == MCD_METHOD_AUTO) method = MCD_METHOD_EIGEN;
+  if (method == MCD_METHOD_AUTO) method = (p->squaring_ok && !lagtimes) ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (method < MCD_METHOD_EIGEN || method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
   if (method >= MCD_METHOD_SQUARING && (!p->squaring_ok || lagtimes)) return MCD_E_UNSUPPORTED;
   if (B == 0) return MCD_OK;
