@@ -76,7 +76,9 @@ typedef struct {
   int32_t nlag;     /* number of lag times / count matrices (<= 64) */
   int32_t ncosF;    /* 0: per-bin F moves, >0: v = v_basis . v_coeff  (<= 64) */
   int32_t ncosD;    /* 0: per-bin ln D moves, >0: w = w_basis . w_coeff (<= 64) */
-  int32_t reserved;
+  int32_t use_pull; /* 1: constant pulling force (--pull): generator of init_rate_matrix_pbc_pull,
+                       lib/utils.py:133-183 -- not symmetrisable, runs on the general squaring engine;
+                       needs pbc, n <= 104 and a lag set with a LagPlan (else MCD_E_UNSUPPORTED) */
   const double* lagtimes;  /* [nlag]                       device */
   const int32_t* counts;   /* [nlag][n][n]                 device */
   const double* v_basis;   /* [n][ncosF] or NULL           device (lib/model.py:93-96) */
@@ -84,6 +86,7 @@ typedef struct {
   const double* string_vecs; /* [dim_w][dim_w] or NULL     device (lib/utils.py:294-305) */
   double spring_k;         /* -k option; <= 0 disables     (lib/MCState.py:121-124,287-289) */
   double clip;             /* lower bound of P before log: 1e-10 (lib/utils.py:317) */
+  double pull;             /* dF between neighbouring bins = -pull * dz (lib/MCState.py:65-67); read when use_pull */
 } mcd_problem_desc;
 
 /* Monte-Carlo schedule: what MCState.set_MC_params holds (lib/MCState.py:29-61). */

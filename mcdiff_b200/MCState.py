@@ -74,11 +74,14 @@ class MCState:
     # ---- lib/MCState.py:63-99 ------------------------------------------------------------
     def set_model(self, model, data, ncosF, ncosD, ncosDrad, pull):
         self.data = data
+        # pull (kBT/angstrom) -> dF (kBT) between bins, lib/MCState.py:65-69.  The generator is then not
+        # symmetrisable; the library runs it on the general squaring engine (pbc only, as the reference:
+        # lib/utils.py:49-53 has no non-periodic pull variant).
         self.pull = None if pull is None else -pull * self.data.dz
-        if self.pull is not None:
-            raise NotImplementedError(
-                "--pull makes the generator non-symmetrisable (complex spectrum); the CUDA engines of this "
-                "build cover the symmetric cases only. Run the reference for --pull.")
+        if self.pull is not None and not self.pbc:
+            raise NotImplementedError("pull without pbc (lib/utils.py:49-53)")
+        if self.pull is not None and self.do_radial:
+            raise NotImplementedError("--pull together with the radial model (--rad) is not supported by this build")
         if self.do_radial:
             if model == "RadCosinusModel":
                 self.model = RadCosinusModel(self.data, self.D0, ncosF, ncosD, 0, ncosDrad)
@@ -185,7 +188,7 @@ class MCState:
         self.problem = DeviceProblem(self.engine, counts.astype(np.int64), self.data.list_lt, self.pbc,
                                      v_basis=m.v_basis if m.ncosF > 0 else None,
                                      w_basis=m.w_basis if m.ncosD > 0 else None,
-                                     spring_k=self.k if self.k > 0 else -1.0, string_vecs=svecs)
+                                     spring_k=self.k if self.k > 0 else -1.0, string_vecs=svecs, pull=self.pull)
         self.chains = ChainBatch(self.problem, self.nchains)
         v = np.tile(m.v, (self.nchains, 1))
         w = np.tile(m.w, (self.nchains, 1))

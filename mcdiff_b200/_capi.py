@@ -24,9 +24,9 @@ c_dp = C.c_void_p  # device (or, for the test emulator, host) pointers are passe
 class ProblemDesc(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("pbc", C.c_int32), ("nlag", C.c_int32), ("ncosF", C.c_int32),
-        ("ncosD", C.c_int32), ("reserved", C.c_int32),
+        ("ncosD", C.c_int32), ("use_pull", C.c_int32),
         ("lagtimes", c_dp), ("counts", c_dp), ("v_basis", c_dp), ("w_basis", c_dp),
-        ("string_vecs", c_dp), ("spring_k", C.c_double), ("clip", C.c_double),
+        ("string_vecs", c_dp), ("spring_k", C.c_double), ("clip", C.c_double), ("pull", C.c_double),
     ]
 
 

@@ -47,7 +47,7 @@ def build_parser():
     p.add_option("--reduction", dest="reduction", default=False, action="store_true",
                  help="delete zero rows/columns of the transition matrix before the Monte Carlo")
     p.add_option("--pull", dest="pull", default=None, type="float", metavar="PULL",
-                 help="Constant external force in kBT/Angstrom (not supported by the CUDA engines)")
+                 help="Constant external force in kBT/Angstrom (periodic profiles; general squaring engine)")
     # ---- additions ----
     p.add_option("--nchains", dest="nchains", default=1, type="int",
                  help="number of independent chains (all GPUs together)")

@@ -55,6 +55,9 @@ struct Problem {
   double spring_k;
   double clip;
   LagPlan plan[2];         // [0]: lag times as given, [1]: lag times shifted by a time offset (--t0)
+  double pull;             // dF per bin of a constant pulling force (lib/utils.py:133-183), used when use_pull
+  int use_pull;            // 1: non-reversible generator -> general (non-symmetric) squaring engine
+  int reserved;
 };
 
 MCD_HOSTDEV bool plan_close(double a, double b) { return fabs(a - b) <= 1e-12 * fabs(b); }
@@ -299,8 +302,13 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
 }
 
 // ---------------------------------------------------------------------------------------
-template <class Exec, bool kBlocked = false>
+// kMode: 0 = symmetric engines (eigen / squaring in shared memory), 1 = blocked squaring engine
+// (104 < n <= 208), 2 = general engine for the non-reversible --pull generator.  The mode is a template
+// parameter so that every kernel only carries the code of its own likelihood evaluation.
+template <class Exec, int kMode = 0>
 struct Chain {
+  static constexpr bool kBlocked = (kMode == 1);
+  static constexpr bool kGeneral = (kMode == 2);
   Exec& ex;
   const Problem& P;
   Smem s;
@@ -1297,6 +1305,301 @@ struct Chain {
   }
 
   // ------------------------------------------------------------------------------------
+  // General (non-symmetric) squaring engine: --pull, lib/utils.py:133-183.
+  // A constant force on a periodic profile breaks detailed balance around the ring, so R cannot be
+  // symmetrised.  The engine works on R itself: P(t) = exp(tR) = (T_m(hR))^(2^s), all entries
+  // still non-negative (R is a generator), products are full n x n m8n8k4 products (A fragments
+  // read rows of X), and the likelihood is sum N_ij log max(P_ij, clip) entry by entry.
+  //   s.a = diagonal, s.b[k] = R[k+1][k] (rate k -> k+1), s.eb[k] = R[k][k+1] (rate k+1 -> k).
+  // Same LagPlan walk as evaluate_sq.  Warp task q: tile row q / ngrp, tile columns 8 (q % ngrp) ...;
+  // a round of 12 tasks completes whole rows, so an in-place product X <- X Y (register-staged,
+  // stored after the round's barrier) never overwrites rows a later round still reads.
+  // ------------------------------------------------------------------------------------
+  MCD_HD void build_R_pull(const double* v, const double* w) {
+    const int n = P.n, np = P.np;
+    const double dF = P.pull;
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += Exec::nthr()) {
+        double up = 0.0, dn = 0.0;
+        if (i < n - 1) {
+          const double dv = v[i + 1] - v[i] + dF;
+          up = exp(w[i] - 0.5 * dv);                    // R[i+1][i]
+          dn = exp(w[i] + 0.5 * dv);                    // R[i][i+1]
+        } else if (i == n - 1) {                        // the corner pair, exactly as lib/utils.py:172-173
+          up = exp(w[n - 1] - 0.5 * (v[0] - v[n - 1] + dF));   // R[0][n-1]
+          dn = exp(w[n - 1] - 0.5 * (v[0] - v[n - 1] - dF));   // R[n-1][0]
+        }
+        s.b[i] = up;
+        s.eb[i] = dn;
+        s.ea[i] = 1.0; s.hv[i] = 0.0;
+      }
+    });
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += Exec::nthr()) {
+        // column i: R[i-1][i] = eb[i-1] (down), R[i+1][i] = b[i] (up); lib/utils.py:175-181
+        const int im = (i == 0) ? n - 1 : i - 1;
+        s.a[i] = (i < n) ? -s.eb[im] - s.b[i] : 0.0;
+      }
+    });
+    const double amax = ex.max([&](int tid) {
+      double m = 0.0;
+      for (int i = tid; i < n; i += Exec::nthr()) {
+        const double r = fabs(s.a[i]);
+        m = (r > m || r != r) ? r : m;
+      }
+      return m;
+    });
+    ex.single([&]() {
+      s.sc->gersh = 2.0 * amax;      // ||R||_1: every column sums to zero
+      s.sc->scale = amax;
+      s.sc->gmin = P.clip;
+      s.sc->lin = 0.0;
+    });
+  }
+
+  // D <- X Y, full product.  cnt != nullptr: D is the propagator of a lag time, its likelihood terms are
+  // added to s.part.  store: 1 = D is a third buffer (direct stores), 2 = D aliases X (staged per round).
+  MCD_HD void gen_product(const double* X, const double* Y, double* D, const int* cnt, double* Pl, int store) {
+    const int n = P.n, np = P.np, ld = P.ld, nb8 = np / 8;
+    const int ngrp = (nb8 + kTilesPerWarp - 1) / kTilesPerWarp;
+    const int nwarp = Exec::nthr() / 32;
+    const int per_round = (nwarp / ngrp) * ngrp;       // whole rows per round
+    const int ntask = nb8 * ngrp;
+    const double clip = P.clip;
+    for (int base = 0; base < ntask; base += per_round) {
+      ex.par([&](int tid) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int q = base + warp;
+        const bool active = warp < per_round && q < ntask;
+        const int row = active ? q / ngrp : 0, grp = active ? q - row * ngrp : 0;
+        const int jb0 = grp * kTilesPerWarp;
+        const int nt = active ? ((nb8 - jb0 < kTilesPerWarp) ? nb8 - jb0 : kTilesPerWarp) : 0;
+        const int fr = lane >> 2, fk = lane & 3;
+        double c[kTilesPerWarp][2];
+        int nv[kTilesPerWarp][2];
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          c[t][0] = 0.0; c[t][1] = 0.0;
+          nv[t][0] = 0; nv[t][1] = 0;
+          if (cnt && active) {
+            const int jb = jb0 + ((t < nt) ? t : 0);
+            const i2 x = ld2i(cnt + (size_t)(row * 8 + fr) * np + jb * 8 + 2 * fk);
+            nv[t][0] = x.x; nv[t][1] = x.y;
+          }
+        }
+        if (active) {
+#if defined(__CUDA_ARCH__)
+          // A fragment: X[8 row + fr][k0 + fk] (rows of X), B fragments: Y[k0 + fk][8 jb + fr]
+          unsigned ax = (unsigned)__cvta_generic_to_shared(X) + (unsigned)((row * 8 + fr) * ld + fk) * 8u;
+          unsigned ay = (unsigned)__cvta_generic_to_shared(Y) + (unsigned)(fk * ld + fr) * 8u;
+          int offB[kTilesPerWarp];
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = (jb0 + ((t < nt) ? t : 0)) * 64;
+          const int pitch4 = 4 * ld * 8, nk4 = np / 4;
+#pragma unroll 2
+          for (int it = 0; it < nk4; ++it) {
+            const double a0 = lds64(ax);
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const double b = lds64(ay + offB[t]);
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(c[t][0]), "+d"(c[t][1])
+                           : "d"(a0), "d"(b));
+            }
+            ax += 32;
+            ay += pitch4;
+          }
+#else
+          for (int t = 0; t < nt; ++t) {
+            const int i = row * 8 + fr;
+            for (int e = 0; e < 2; ++e) {
+              const int j = (jb0 + t) * 8 + 2 * fk + e;
+              double acc = 0.0;
+              for (int k = 0; k < np; ++k) acc = fma(X[i * ld + k], Y[k * ld + j], acc);
+              c[t][e] = acc;
+            }
+          }
+#endif
+        }
+        if (cnt && nt > 0) {
+          double part = 0.0;
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ns = (t < nt) ? nv[t][e] : 0;
+              part += (double)ns * fast_log(fmax(c[t][e], clip));     // lib/utils.py:317-318
+            }
+          }
+          s.part[tid] += part;
+          if (Pl) {
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const int i = row * 8 + fr, j = (jb0 + t) * 8 + 2 * fk;
+              if (t < nt && i < n) {
+                if (j < n) Pl[(size_t)i * n + j] = c[t][0];
+                if (j + 1 < n) Pl[(size_t)i * n + j + 1] = c[t][1];
+              }
+            }
+          }
+        }
+        double* r = ex.regs(tid);
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) { r[2 * t] = c[t][0]; r[2 * t + 1] = c[t][1]; }
+        if (store == 1) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t)
+            if (t < nt) st2(D + (row * 8 + fr) * ld + (jb0 + t) * 8 + 2 * fk, r[2 * t], r[2 * t + 1]);
+        }
+      });
+      if (store == 2) {
+        ex.par([&](int tid) {
+          const int warp = tid >> 5, lane = tid & 31;
+          const int q = base + warp;
+          if (warp < per_round && q < ntask) {
+            const int row = q / ngrp, grp = q - row * ngrp;
+            const int jb0 = grp * kTilesPerWarp;
+            const int nt = (nb8 - jb0 < kTilesPerWarp) ? nb8 - jb0 : kTilesPerWarp;
+            const int fr = lane >> 2, fk = lane & 3;
+            const double* r = ex.regs(tid);
+            for (int t = 0; t < nt; ++t) st2(D + (row * 8 + fr) * ld + (jb0 + t) * 8 + 2 * fk, r[2 * t], r[2 * t + 1]);
+          }
+        });
+      }
+    }
+  }
+
+  // likelihood terms of a propagator that already sits in a buffer (general engine)
+  MCD_HD void gen_buffer_loglike(const double* G, const int* cnt, double* Pl) {
+    const int n = P.n, np = P.np, ld = P.ld;
+    const double clip = P.clip;
+    ex.par([&](int tid) {
+      double part = 0.0;
+      for (int e = tid; e < n * n; e += Exec::nthr()) {
+        const int i = e / n, j = e - i * n;
+        const double g = G[i * ld + j];
+        part += (double)cnt[(size_t)i * np + j] * fast_log(fmax(g, clip));
+        if (Pl) Pl[e] = g;
+      }
+      s.part[tid] += part;
+    });
+  }
+
+  // exp(t R) by Taylor + squarings (general engine); same contract as sq_chain
+  MCD_HD double* gen_chain(double t, double gersh, int taylor_m, int epi, double* Pout, double** other, int* nsq_out) {
+    const int n = P.n, np = P.np, ld = P.ld;
+    const double rho = t * gersh;
+    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
+    int nsq = 0;
+    if (rho > 1.0) {
+      int ex2;
+      const double fr2 = frexp(rho, &ex2);
+      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
+    }
+    const double h = ldexp(t, -nsq);
+    const int m = (taylor_m > 0) ? (taylor_m < 31 ? taylor_m : 31) : s.tord[nsq];
+    double* src = s.XT;
+    double* dst = s.B2;
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(src + e, 0.0, 0.0); st2(dst + e, 0.0, 0.0); }
+      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);
+    });
+    ex.par([&](int tid) {
+      for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
+    });
+    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
+    for (int tt = 1; tt <= m; ++tt) {     // (R H)[i][j] = a_i H[i][j] + R[i][i-1] H[i-1][j] + R[i][i+1] H[i+1][j]
+      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
+      const bool full = (width == n);
+      ex.par([&](int tid) {
+        const int i = s.hrow[tid], r = s.hrem[tid];
+        if (i < n) {
+          const double f = s.red[tt];
+          const int im = (i == 0) ? n - 1 : i - 1;
+          const int ip = (i == n - 1) ? 0 : i + 1;
+          const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.eb[i];
+          const double* MCD_RESTRICT s0 = src + i * ld;
+          const double* MCD_RESTRICT sm = src + im * ld;
+          const double* MCD_RESTRICT sp = src + ip * ld;
+          double* MCD_RESTRICT d0 = dst + i * ld;
+          for (int dd = r; dd < width; dd += tpr) {
+            int j = dd;
+            if (!full) {
+              j = i - tt + dd;
+              if (j < 0) j += n; else if (j >= n) j -= n;
+            }
+            d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
+          }
+        }
+      });
+      double* tmp = src; src = dst; dst = tmp;
+    }
+    double* G = src;
+    double* O = dst;
+    const int* cnt_e = (epi >= 0) ? P.counts + (size_t)epi * np * np : nullptr;
+    for (int q = 0; q < nsq; ++q) {
+      const bool last = (q + 1 == nsq);
+      gen_product(G, G, O, last ? cnt_e : nullptr, last ? Pout : nullptr, 1);
+      double* tmp = G; G = O; O = tmp;
+    }
+    if (nsq == 0 && epi >= 0) gen_buffer_loglike(G, cnt_e, Pout);
+    *other = O;
+    if (nsq_out) *nsq_out += nsq;
+    return G;
+  }
+
+  MCD_HD double evaluate_gen(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* slots,
+                             int taylor_m, double* Pout, int* squarings_out) {
+    const int n = P.n, np = P.np;
+    const size_t nn = (size_t)n * n, slot_elems = (size_t)np * P.ld;
+    build_R_pull(v, w);
+    const double gersh = s.sc->gersh;
+    ex.par([&](int tid) { s.part[tid] = 0.0; });
+    int nsq = 0;
+    bool bad = false;
+    double* R = nullptr;
+    double* O = nullptr;
+    const int l0 = pl.order[0];
+    const bool fast = pl.fast != 0;
+    for (int c = 0; c < pl.nchain && !bad; ++c) {
+      const bool is_first_lag = (c == pl.nchain - 1);
+      const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
+      double* other = nullptr;
+      double* G = gen_chain(t, gersh, taylor_m, is_first_lag ? l0 : -1,
+                            (is_first_lag && Pout) ? Pout + (size_t)l0 * nn : nullptr, &other, &nsq);
+      if (!G) { bad = true; break; }
+      if (!fast && pl.chain_slot[c] >= 0) copy_buffer(slots + (size_t)pl.chain_slot[c] * slot_elems, G);
+      R = G;
+      O = other;
+    }
+    double* G0 = R;
+    int in_O = -1;
+    for (int i = 1; i < P.nlag && !bad; ++i) {
+      const int l = pl.order[i];
+      const int* cnt = P.counts + (size_t)l * np * np;
+      double* Pl = Pout ? Pout + (size_t)l * nn : nullptr;
+      if (!fast && pl.op_slot[i] < 0) {
+        gen_buffer_loglike(R, cnt, Pl);
+      } else if (fast) {
+        gen_product((i == 1) ? G0 : O, G0, O, cnt, Pl, (i == 1) ? 1 : 2);   // G((i+1) t0) = G(i t0) G(t0)
+      } else {
+        if (in_O != pl.op_slot[i]) {
+          copy_buffer(O, slots + (size_t)pl.op_slot[i] * slot_elems);
+          in_O = pl.op_slot[i];
+        }
+        gen_product(R, O, R, cnt, Pl, 2);
+      }
+      if (!fast && pl.park[i] >= 0) copy_buffer(slots + (size_t)pl.park[i] * slot_elems, R);
+    }
+    if (squarings_out) *squarings_out = bad ? -1 : nsq;
+    if (bad) {
+      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      return nan("");
+    }
+    return ex.sum([&](int tid) { return s.part[tid]; });
+  }
+
+  // ------------------------------------------------------------------------------------
   // Blocked squaring engine (kBlocked, kMaxSmemBins < n <= 2 kMaxSmemBins).
   // The np x np matrices (np = 2 nbk) live in a per-CTA global workspace that stays in L2; a product
   //   C_IJ = sum_K X_KI^T Y_KJ      (I, J, K in {0, 1}; X, Y symmetric and commuting)
@@ -1760,7 +2063,7 @@ struct Chain {
       for (int l = tid; l < P.nlag; l += Exec::nthr()) s.lag[l] = P.lagtimes[l] + sc->timezero;
     });
     int have_basis = 0;
-    if (!kBlocked && io.basis && io.basis_valid[chain]) {
+    if (kMode == 0 && io.basis && io.basis_valid[chain]) {
       const double* src = io.basis + (size_t)chain * np * ld;
       ex.par([&](int tid) {
         for (int e = tid; e < np * ld; e += Exec::nthr()) s.XT[e] = src[e];
@@ -1893,6 +2196,8 @@ struct Chain {
         double ll_new;
         if constexpr (kBlocked) {
           ll_new = evaluate_blk(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, nullptr, &sw);
+        } else if constexpr (kGeneral) {
+          ll_new = evaluate_gen(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, nullptr, &sw);
         } else if (mp.method >= 2) {
           ll_new = evaluate_sq(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, mp.method == 2,
                                nullptr, &sw);

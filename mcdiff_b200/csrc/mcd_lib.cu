@@ -111,7 +111,7 @@ mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
   const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
   DeviceExec ex(s.red);
-  Chain<DeviceExec, true> ch(ex, P, s);
+  Chain<DeviceExec, 1> ch(ex, P, s);
   const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
   ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * blocked_ws_doubles(P, pl.nslots));
 }
@@ -123,7 +123,7 @@ mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const dou
   const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
   DeviceExec ex(s.red);
-  Chain<DeviceExec, true> ch(ex, P, s);
+  Chain<DeviceExec, 1> ch(ex, P, s);
   ch.build_tables();
   const int n = P.n, np = P.np, dim_w = P.dim_w;
   double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, P.plan[0].nslots);
@@ -139,6 +139,50 @@ mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const dou
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
     const double ll = ch.evaluate_blk(s.v, s.w, s.lag, P.plan[0], ws, 0, Pb, &sw);
+    ex.par([&](int tid) {
+      if (tid == 0) {
+        out_ll[b] = ll;
+        if (status) status[b] = (int)s.sc->status;
+      }
+    });
+  }
+}
+
+// General engine (--pull): the generator is not symmetrisable, exp(tR) by squaring with full products.
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_mc_run_gen_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec, 2> ch(ex, P, s);
+  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_loglike_gen_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
+                       double* __restrict__ out_ll, double* __restrict__ out_P, int* __restrict__ status, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec, 2> ch(ex, P, s);
+  ch.build_tables();
+  const int n = P.n, np = P.np, dim_w = P.dim_w;
+  double* slots = gws + (size_t)blockIdx.x * P.plan[0].nslots * P.np * P.ld;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    ex.par([&](int tid) {
+      for (int i = tid; i < np; i += kThreads) {
+        s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
+        s.w[i] = (i < dim_w) ? w[(size_t)b * dim_w + i] : 0.0;
+      }
+      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = P.lagtimes[l];
+      if (tid == 0) s.sc->status = 0;
+    });
+    int sw = 0;
+    double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
+    const double ll = ch.evaluate_gen(s.v, s.w, s.lag, P.plan[0], slots, 0, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -301,6 +345,9 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   P.svecs = d->spring_k > 0.0 ? sv : nullptr;
   P.spring_k = d->spring_k;
   P.clip = d->clip;
+  P.use_pull = d->use_pull ? 1 : 0;
+  P.pull = d->use_pull ? d->pull : 0.0;
+  P.reserved = 0;
   const size_t full = smem_matrix_bytes(np, ld) + smem_vectors_bytes(np);
   // the warm-start tile GEMM keeps one 4x4 tile per thread
   const int ntiles = (np / 4) * (np / 4 + 1) / 2;
@@ -314,6 +361,12 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np);
     p->blocked = (P.blocked && p->blk_smem_bytes <= (size_t)h->max_smem_optin) ? 1 : 0;
     p->squaring_ok = (p->in_smem || p->blocked) && P.plan[0].ok && P.plan[1].ok;
+    // --pull: only the general squaring engine applies (periodic, work matrices in shared memory, a LagPlan)
+    if (P.use_pull && !(P.pbc && p->in_smem && P.plan[0].ok && P.plan[1].ok)) {
+      cudaFree(blob);
+      delete p;
+      return MCD_E_UNSUPPORTED;
+    }
   }
   p->smem_bytes = p->in_smem ? full : smem_vectors_bytes(np);
   if (!p->in_smem && ntiles > kThreads) {
@@ -363,7 +416,17 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const Problem& P = p->P;
-  if (p->blocked && method >= MCD_METHOD_SQUARING) {
+  if (P.use_pull) {
+    if (lagtimes || method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA) return MCD_E_UNSUPPORTED;
+    const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
+    if (P.plan[0].nslots > 0) {
+      int rc = ensure_gws(h, (size_t)grid * P.plan[0].nslots * P.np * P.ld * sizeof(double));
+      if (rc != MCD_OK) return rc;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_loglike_gen_kernel<<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, out_ll, out_P, status, h->gws);
+  } else if (p->blocked && method >= MCD_METHOD_SQUARING) {
     if (method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
     int rc = ensure_gws(h, (size_t)grid * blocked_ws_doubles(P, P.plan[0].nslots) * sizeof(double));
@@ -414,7 +477,17 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (mp.method < MCD_METHOD_EIGEN || mp.method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
   if (mp.method >= MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
-  if (p->blocked && mp.method >= MCD_METHOD_SQUARING) {
+  if (P.use_pull) {
+    if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // general engine: tensor-core squaring only
+    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+    if (pl.nslots > 0) {
+      int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));
+      if (rc != MCD_OK) return rc;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)p->smem_bytes));
+    mcd_mc_run_gen_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+  } else if (p->blocked && mp.method >= MCD_METHOD_SQUARING) {
     if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
     const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
     int rc = ensure_gws(h, (size_t)nchains * blocked_ws_doubles(P, pl.nslots) * sizeof(double));

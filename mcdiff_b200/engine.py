@@ -72,8 +72,12 @@ class DeviceProblem:
     """Device-resident problem description (counts, lag times, bases)."""
 
     def __init__(self, eng: Engine, counts, lagtimes, pbc, v_basis=None, w_basis=None, spring_k=-1.0,
-                 string_vecs=None, clip=1e-10):
+                 string_vecs=None, clip=1e-10, pull=None):
+        """pull: dF between neighbouring bins (= -pull_force * dz, lib/MCState.py:65-67) or None."""
         self.eng = eng
+        self.pull = None if pull is None else float(pull)
+        if self.pull is not None and not pbc:
+            raise NotImplementedError("pull without pbc (lib/utils.py:49-53)")
         counts = np.asarray(counts)
         if counts.ndim != 3 or counts.shape[1] != counts.shape[2]:
             raise ValueError("counts must be [nlag][n][n]")
@@ -104,6 +108,7 @@ class DeviceProblem:
             d.w_basis = None if self.d_wb is None else self.d_wb.data_ptr()
             d.string_vecs = None if self.d_sv is None else self.d_sv.data_ptr()
             d.spring_k, d.clip = self.spring_k, float(clip)
+            d.use_pull, d.pull = (0, 0.0) if self.pull is None else (1, self.pull)
             p = C.c_void_p()
             K.check(eng.lib.mcd_problem_create(eng.handle, C.byref(d), eng.stream_ptr(), C.byref(p)),
                     "mcd_problem_create")

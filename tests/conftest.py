@@ -26,6 +26,11 @@ def gold_replay():
 
 
 @pytest.fixture(scope="session")
+def gold_pull():
+    return np.load(os.path.join(GOLDEN, "pull_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def gold_radial():
     return np.load(os.path.join(GOLDEN, "radial_golden.npz"))
 

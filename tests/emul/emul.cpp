@@ -54,6 +54,9 @@ void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
   P.svecs = d->string_vecs;
   P.spring_k = d->spring_k;
   P.clip = d->clip;
+  P.use_pull = d->use_pull ? 1 : 0;
+  P.pull = d->use_pull ? d->pull : 0.0;
+  P.reserved = 0;
   plan_lags(d->lagtimes, d->nlag, false, &P.plan[0]);
   plan_lags(d->lagtimes, d->nlag, true, &P.plan[1]);
 }
@@ -69,10 +72,31 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
   std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
   std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
   std::vector<double> store((size_t)kThreads * kMaxRegs);
+  if (P.use_pull) {   // general engine (--pull)
+    Smem s = carve(P, mat.data(), vec.data());
+    HostExec ex(store.data());
+    Chain<HostExec, 2> ch(ex, P, s);
+    ch.build_tables();
+    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < P.np; ++i) {
+        s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
+        s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
+      }
+      for (int l = 0; l < P.nlag; ++l) s.lag[l] = P.lagtimes[l];
+      s.sc->status = 0;
+      int sw = 0;
+      double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
+      out_ll[b] = ch.evaluate_gen(s.v, s.w, s.lag, P.plan[0], slots.data(), 0, Pb, &sw);
+      if (status) status[b] = (int)s.sc->status;
+      if (sweeps) sweeps[b] = sw;
+    }
+    return 0;
+  }
   if (P.blocked && method == MCD_METHOD_SQUARING) {   // blocked squaring engine (panels + global workspace)
     Smem s = carve(P, mat.data(), vec.data(), true);
     HostExec ex(store.data());
-    Chain<HostExec, true> ch(ex, P, s);
+    Chain<HostExec, 1> ch(ex, P, s);
     ch.build_tables();
     std::vector<double> ws(blocked_ws_doubles(P, P.plan[0].nslots));
     for (int b = 0; b < B; ++b) {
@@ -126,13 +150,23 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
   std::vector<double> mat(smem_matrix_bytes(P.np, P.ld) / 8 + 2);
   std::vector<unsigned char> vec(smem_vectors_bytes(P.np) + 64);
   std::vector<double> store((size_t)kThreads * kMaxRegs);
+  if (P.use_pull) {
+    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
+    for (int c = 0; c < nchains; ++c) {
+      Smem s = carve(P, mat.data(), vec.data());
+      HostExec ex(store.data());
+      Chain<HostExec, 2> ch(ex, P, s);
+      ch.run(mp, cio, c, nsteps, slots.data());
+    }
+    return 0;
+  }
   if (P.blocked && mp.method == MCD_METHOD_SQUARING) {
     const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
     std::vector<double> ws(blocked_ws_doubles(P, pl.nslots));
     for (int c = 0; c < nchains; ++c) {
       Smem s = carve(P, mat.data(), vec.data(), true);
       HostExec ex(store.data());
-      Chain<HostExec, true> ch(ex, P, s);
+      Chain<HostExec, 1> ch(ex, P, s);
       ch.run(mp, cio, c, nsteps, ws.data());
     }
     return 0;

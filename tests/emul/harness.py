@@ -44,7 +44,7 @@ class HostProblem:
     """Keeps the numpy arrays alive and exposes a ProblemDesc with host pointers."""
 
     def __init__(self, counts, lagtimes, pbc, v_basis=None, w_basis=None, spring_k=-1.0, string_vecs=None,
-                 clip=1e-10):
+                 clip=1e-10, pull=None):
         self.counts = np.ascontiguousarray(counts, dtype=np.int32)
         self.lagtimes = np.ascontiguousarray(lagtimes, dtype=np.float64)
         self.n = self.counts.shape[-1]
@@ -61,6 +61,7 @@ class HostProblem:
         d.lagtimes, d.counts = ptr(self.lagtimes), ptr(self.counts)
         d.v_basis, d.w_basis, d.string_vecs = ptr(self.v_basis), ptr(self.w_basis), ptr(self.svecs)
         d.spring_k, d.clip = float(spring_k), float(clip)
+        d.use_pull, d.pull = (0, 0.0) if pull is None else (1, float(pull))
         self.desc = d
         self.sample_dim = 6 + (self.ncosF or self.n) + (self.ncosD or self.dim_w)
 

@@ -89,7 +89,7 @@ class TapeRNG:
 
 def run_reference_replay(files, *, pbc, ncosF, ncosD, dv, dw, temp, temp_end, nmc,
                          nmc_update, move_timezero, dtimezero, k, tape_u, tape_idx,
-                         initfile=None, D0=1.0):
+                         initfile=None, D0=1.0, pull=None):
     import mcdiff.MCState as mcs
     import mcdiff.mc as mcmod
     from mcdiff.transitions import Transitions
@@ -101,7 +101,7 @@ def run_reference_replay(files, *, pbc, ncosF, ncosD, dv, dw, temp, temp_end, nm
         MC.set_MC_params(dv, dw, 0.5, D0, dtimezero, temp, nmc, nmc_update, move_timezero, k,
                          temp_end=temp_end)
         data = Transitions(files)
-        MC.set_model("CosinusModel", data, ncosF, ncosD, 0, None)
+        MC.set_model("CosinusModel", data, ncosF, ncosD, 0, pull)
         if initfile is not None:
             MC.use_initfile(initfile)
         logger = Logger(MC)
@@ -164,6 +164,8 @@ def run_reference_replay(files, *, pbc, ncosF, ncosD, dv, dw, temp, temp_end, nm
         wunit=float(MC.model.wunit), edges=np.array(MC.model.edges),
         counts=np.array(data.list_trans).astype(np.int32), lagtimes=np.array(data.list_lt, dtype=np.float64),
     )
+    if pull is not None:
+        out["dF"] = float(MC.pull)     # dF per bin the reference derived from --pull (lib/MCState.py:65-67)
     return out
 
 

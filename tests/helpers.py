@@ -2,6 +2,7 @@
 import numpy as np
 
 REPLAY_TAGS = ["cosA", "binP4", "cosP4t0", "binCut", "springP4"]
+PULL_TAGS = ["cosPull", "binPull"]     # tests/golden/pull_golden.npz (--pull trajectories of the reference)
 
 
 def replay_case(R, tag):
@@ -27,4 +28,5 @@ def replay_case(R, tag):
         svecs=O.string_vecs(dim_w, pbc) if k > 0 else None,
         nmc=nmc, nmc_update=nupd, temp=temp, temp_end=None if np.isnan(te) else te, dtemp=dtemp,
         dv=float(g("cfg_dv")), dw=float(g("cfg_dw")), dt0=float(g("cfg_dtimezero")),
-        move_timezero=bool(g("cfg_move_timezero")))
+        move_timezero=bool(g("cfg_move_timezero")),
+        pull=float(g("dF")) if (tag + "/dF") in R.files else None)     # dF per bin (lib/MCState.py:65-67)

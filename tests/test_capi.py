@@ -40,7 +40,7 @@ def test_version_and_error_strings(lib):
 
 def test_struct_layouts():
     from mcdiff_b200 import _capi as K
-    assert C.sizeof(K.ProblemDesc) == 6 * 4 + 5 * 8 + 2 * 8
+    assert C.sizeof(K.ProblemDesc) == 6 * 4 + 5 * 8 + 3 * 8      # + double pull
     assert C.sizeof(K.McParams) == 3 * 8 + 6 * 4 + 4 * 8
     assert C.sizeof(K.ChainIO) == 15 * 8
     assert K.McParams.seed.offset == 48 and K.McParams.method.offset == 40

@@ -174,3 +174,43 @@ def test_blocked_engine_mc_replay():
     assert ref["accepted"].any() and ref["accepted_t0"].any()
     np.testing.assert_allclose(ch.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
     np.testing.assert_allclose(ch.scal[0, K.S_T0], ref["timezero"], rtol=1e-13)
+
+
+def test_pull_general_engine(gold_pull):
+    """--pull: the non-symmetric generator on the general squaring engine (full m8n8k4 products on R itself)
+    against values of the unmodified reference; also sizes with padding, a single lag, a general lag plan."""
+    from oracle import mcdiff_oracle as O
+    G = gold_pull
+    for b in range(4):
+        prob = H.HostProblem(G["counts"], G["lags"], True, pull=float(G["ll/dF"][b]))
+        ll, P, st, nsq = H.loglike_batch(prob, G["ll/v"][b], G["ll/w"][b], want_P=(b == 0), method=SQUARING)
+        assert not st.any() and nsq[0] > 0
+        np.testing.assert_allclose(ll[0], G["ll/ll"][b], rtol=1e-12)
+        if b == 0:
+            assert np.max(np.abs(P[0, 0] - G["P0"])) < 1e-13
+            np.testing.assert_allclose(P[0, 3].sum(axis=0), 1.0, atol=1e-12)
+    rng = np.random.default_rng(9)
+    for n, lags, dF in [(37, (3.0, 6.0), -0.2), (60, (5.0, 10.0, 20.0), 0.1), (8, (2.0,), 0.3)]:
+        lags = np.array(lags)
+        counts = O.synthetic_counts(n, lags, seed=4, total=2.0e5, dz=1.0)[0]
+        v, w = rng.normal(0, 0.5, n), rng.normal(-1.0, 0.3, n)
+        ll, _, st, _ = H.loglike_batch(H.HostProblem(counts, lags, True, pull=dF), v, w, method=SQUARING)
+        np.testing.assert_allclose(ll[0], O.log_like_lag(v, w, lags, counts, True, pull=dF), rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag,nsteps", [("cosPull", 60), ("binPull", 40)])
+def test_pull_replay_prefix_matches_reference(gold_pull, tag, nsteps):
+    case = replay_case(gold_pull, tag)
+    g = case["g"]
+    prob = H.HostProblem(case["counts"], case["lagtimes"], True, v_basis=case["v_basis"], w_basis=case["w_basis"],
+                         pull=case["pull"])
+    ch = H.HostChains(prob, 1, g("v0"), g("w0"), g("vc0"), g("wc0"), ll0=float(g("ll0")), dv=case["dv"], dw=case["dw"],
+                      dt0=case["dt0"], temp=case["temp"])
+    mp = K.McParams()
+    mp.num_mc_update, mp.dtemp, mp.min_lt = case["nmc_update"], case["dtemp"], float(np.min(case["lagtimes"]))
+    mp.move_timezero, mp.sample_every, mp.refresh_every, mp.use_tape, mp.method = int(case["move_timezero"]), 100, 16, 1, SQUARING
+    dec, llt, _ = ch.run(nsteps, mp, g("tape_u"), g("tape_idx"))
+    assert np.array_equal(dec[0] >> 2, g("move")[:nsteps])
+    assert np.array_equal(dec[0] & 1, g("accepted")[:nsteps])
+    assert np.array_equal((dec[0] >> 1) & 1, g("accepted_t0")[:nsteps])
+    np.testing.assert_allclose(ch.scal[0, K.S_LL], g("ll_after")[nsteps - 1], rtol=1e-11)

@@ -177,3 +177,36 @@ def test_lag_scan_concurrent_streams(engine, gold_ll, tmp_path, capsys):
     lts, Dreal, t0 = extrapolate(outs, os.path.join(tmp, "hexd."))
     np.testing.assert_array_equal(lts, [10.0, 20.0, 30.0, 40.0])
     assert Dreal.shape == (100,) and np.all(np.isfinite(Dreal))
+
+
+def test_find_parameters_with_pull(engine, gold_pull, tmp_path, capsys):
+    """run-mcdiff --pull through the host API: dF = -pull dz as lib/MCState.py:65-67, first likelihood equal to
+    the reference's, chain 0 equal to the oracle replay of the device Philox tape."""
+    from mcdiff_b200 import philox
+    from mcdiff_b200.mc import find_parameters
+    from mcdiff_b200.transitions import write_Tmat_square
+    from oracle import mcdiff_oracle as O
+    G = gold_pull
+    tmp = str(tmp_path)
+    files = []
+    for l, lag in enumerate(G["lags"]):
+        fn = os.path.join(tmp, "transitions.nbins100.%d.pbc.dat" % int(lag))
+        write_Tmat_square(G["counts"][l], fn, float(lag), "pbc", edges=G["edges"], dt=1.0, dn=int(lag))
+        files.append(fn)
+    out = os.path.join(tmp, "out.pull.dat")
+    nmc, seed, pull = 120, 5, float(G["cosPull/cfg_pull"])
+    MC, logger = find_parameters(files, True, "CosinusModel", 0.3, 0.3, 0.5, 1.0, 0.5, 1.0, 1.0, nmc, 100.0, seed, out,
+                                 6, 4, 0, True, None, -1, -1, False, pull, nchains=4)
+    text = capsys.readouterr().out
+    assert MC.pull == pytest.approx(float(G["cosPull/dF"]), rel=1e-12)
+    ll_first = float([l for l in text.splitlines() if l.startswith("initial log-likelihood:")][0].split()[-1])
+    assert ll_first == pytest.approx(float(G["cosPull/ll0"]), rel=1e-9)
+    n = 100
+    vb, wb = O.cos_basis_center(n, 6), O.cos_basis_border(n, n, 4)
+    cfg = O.ChainConfig(G["counts"], G["lags"], True, v_basis=vb, w_basis=wb, dv=0.3, dw=0.3, dtimezero=0.5, temp=1.0,
+                        temp_end=1.0, nmc=nmc, num_mc_update=100.0, move_timezero=True, pull=MC.pull)
+    tu, ti = philox.chain_tape(seed, 0, 0, nmc, n, n, 6, 4)
+    ref = O.replay(cfg, G["cosPull/v0"], G["cosPull/w0"], tu, ti, v_coeff0=G["cosPull/vc0"], w_coeff0=G["cosPull/wc0"])
+    assert (MC.naccv, MC.naccw, MC.nacctimezero) == (ref["naccv"], ref["naccw"], ref["nacct0"])
+    np.testing.assert_allclose(MC.log_like, ref["ll"], rtol=1e-9)
+    assert os.path.exists(out)

@@ -11,7 +11,7 @@ information in the reference either.
 import numpy as np
 import pytest
 
-from tests.helpers import REPLAY_TAGS, replay_case
+from tests.helpers import PULL_TAGS, REPLAY_TAGS, replay_case
 
 pytestmark = pytest.mark.gpu
 
@@ -485,3 +485,52 @@ def test_radial_mc_replay_against_reference(engine, tag):
     s0 = smp.cpu().numpy()[0]
     np.testing.assert_allclose(s0[:, 0], g("log_ll")[1:], rtol=RTOL)
     np.testing.assert_allclose(s0[:, 3:], g("log_wrad")[1:], atol=1e-13)
+
+
+def test_pull_likelihood_and_propagator(engine, gold_pull):
+    """--pull (lib/utils.py:133-183): non-symmetrisable generator on the general squaring engine, against
+    values the unmodified reference produced; eigen / DFMA are refused for such a problem."""
+    from mcdiff_b200.engine import DeviceProblem
+    from mcdiff_b200._capi import McdError
+    G = gold_pull
+    for b in range(4):
+        prob = DeviceProblem(engine, G["counts"], G["lags"], True, pull=float(G["ll/dF"][b]))
+        ll, P, st = prob.loglike(G["ll/v"][b:b + 1], G["ll/w"][b:b + 1], want_P=True)
+        assert not st.any()
+        np.testing.assert_allclose(ll[0], G["ll/ll"][b], rtol=1e-12)
+        for l in range(4):
+            np.testing.assert_allclose(P[0, l].sum(axis=0), 1.0, atol=1e-12)
+        if b == 0:
+            assert np.max(np.abs(P[0, 0] - G["P0"])) < 1e-13
+            with pytest.raises(McdError):
+                prob.loglike(G["ll/v"][:1], G["ll/w"][:1], method=METHODS["eigen"])
+    with pytest.raises(NotImplementedError):
+        DeviceProblem(engine, G["counts"], G["lags"], False, pull=0.1)
+
+
+@pytest.mark.parametrize("tag", PULL_TAGS)
+def test_pull_replay_against_reference_trajectories(engine, gold_pull, tag):
+    """Full --pull trajectories of the reference (with and without time-offset moves): bit-exact decisions."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    case = replay_case(gold_pull, tag)
+    g = case["g"]
+    prob = DeviceProblem(engine, case["counts"], case["lagtimes"], True, v_basis=case["v_basis"],
+                         w_basis=case["w_basis"], pull=case["pull"])
+    ch = ChainBatch(prob, 2)
+    ch.set_state(g("v0"), g("w0"), g("vc0") if case["ncosF"] else None, g("wc0") if case["ncosD"] else None,
+                 dv=case["dv"], dw=case["dw"], dtimezero=case["dt0"], temp=case["temp"])
+    ll0 = ch.init_log_like()
+    np.testing.assert_allclose(ll0, float(g("ll0")), rtol=1e-12)
+    nsteps = case["nmc"]
+    mp = _params(case, nsteps, use_tape=1, method=METHODS["squaring"])
+    dec, llt, _ = ch.run(nsteps, mp, tape_u=g("tape_u"), tape_idx=g("tape_idx"), record=True)
+    dec = dec.cpu().numpy()
+    for c in range(2):
+        assert np.array_equal(dec[c] >> 2, g("move"))
+        assert np.array_equal(dec[c] & 1, g("accepted"))
+        assert np.array_equal((dec[c] >> 1) & 1, g("accepted_t0"))
+    st = ch.host_state()
+    np.testing.assert_allclose(st["scal"][0][0], float(g("ll")), rtol=1e-11)
+    np.testing.assert_allclose(st["scal"][0][1], float(g("timezero")), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(st["v"][0], g("v"), atol=1e-12)
+    assert not st["counters"][:, 6].any()
