@@ -534,3 +534,29 @@ def test_pull_replay_against_reference_trajectories(engine, gold_pull, tag):
     np.testing.assert_allclose(st["scal"][0][1], float(g("timezero")), rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(st["v"][0], g("v"), atol=1e-12)
     assert not st["counters"][:, 6].any()
+
+
+@pytest.mark.parametrize("n,dim_rad,lmax", [(8, 7, 5), (30, 60, 12), (52, 20, 33)])
+def test_radial_shapes(engine, n, dim_rad, lmax):
+    """Radial likelihood at the edges of the batched route: a tiny problem (Bessel sums fall back to the vector
+    pipe), more than 48 radial bins (two accumulator groups), more Bessel terms than fit one k-step multiple."""
+    from mcdiff_b200.engine import rad_loglike
+    from oracle import mcdiff_oracle as O
+    rng = np.random.default_rng(n)
+    i = np.arange(n)
+    v = 1.0 * np.cos(2 * np.pi * (i + 0.5) / n)
+    w = np.log(0.5 + 0.2 * np.cos(2 * np.pi * (i + 1.0) / n))
+    lags = np.array([4.0, 8.0])
+    zeros, table = O.bessel_tables(lmax, dim_rad)
+    rate = O.rate_matrix(v, w, True)
+    wrad0 = np.full(n, np.log(0.4))
+    counts = np.zeros((2, dim_rad, n, n))
+    for l, lt in enumerate(lags):
+        counts[l] = rng.poisson(200.0 * np.clip(O.radial_propagator(rate, wrad0, lt, zeros, table), 0.0, None))
+    wrad = wrad0[None, :] + rng.normal(0, 0.2, (2, n))
+    ll, P, st = rad_loglike(engine, v, w, True, lags, counts, table, zeros, wrad, want_P=True)
+    assert not st.any()
+    for b in range(2):
+        np.testing.assert_allclose(ll[b], O.rad_log_like_lag(rate, wrad[b], lags, counts, zeros, table), rtol=RTOL)
+    Pref = O.radial_propagator(rate, wrad[0], lags[1], zeros, table)
+    assert np.max(np.abs(P[0, 1] - Pref)) <= 1e-12 * np.max(np.abs(Pref))
