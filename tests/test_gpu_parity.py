@@ -560,3 +560,30 @@ def test_radial_shapes(engine, n, dim_rad, lmax):
         np.testing.assert_allclose(ll[b], O.rad_log_like_lag(rate, wrad[b], lags, counts, zeros, table), rtol=RTOL)
     Pref = O.radial_propagator(rate, wrad[0], lags[1], zeros, table)
     assert np.max(np.abs(P[0, 1] - Pref)) <= 1e-12 * np.max(np.abs(Pref))
+
+
+@pytest.mark.parametrize("pbc", [True, False])
+def test_small_and_odd_sizes(engine, pbc):
+    """n = 3 ... 104 including sizes that are not multiples of 8 (padding), fewer rows than threads per row-slot
+    tables, band wider than the matrix: squaring engines to 1e-11 (componentwise accurate), eigen to 1e-8 on these
+    unphysical random counts (absolute, not componentwise, accuracy)."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    rng = np.random.default_rng(5 + int(pbc))
+    for n in (3, 4, 5, 8, 9, 12, 17, 24, 33, 49, 50, 64, 97, 104):
+        lags = np.array([2.0, 4.0, 6.0]) if n % 2 else np.array([3.0, 5.0])
+        counts = rng.integers(0, 40, size=(len(lags), n, n)).astype(np.int32)
+        dim_w = n if pbc else n - 1
+        v = rng.normal(0, 0.5, (2, n))
+        w = rng.normal(-0.5, 0.4, (2, dim_w))
+        prob = DeviceProblem(engine, counts, lags, pbc)
+        ref = np.array([O.log_like_lag(v[b], w[b], lags, counts, pbc) for b in range(2)])
+        for method, tol in (("squaring", 1e-11), ("squaring_dfma", 1e-11), ("eigen", 1e-8)):
+            ll, _, st = prob.loglike(v, w, method=METHODS[method])
+            assert not st.any(), (n, method)
+            np.testing.assert_allclose(ll, ref, rtol=tol, err_msg="n=%d %s" % (n, method))
+        if pbc and n >= 8:
+            probp = DeviceProblem(engine, counts, lags, True, pull=0.15)
+            llp, _, st = probp.loglike(v, w)
+            refp = [O.log_like_lag(v[b], w[b], lags, counts, True, pull=0.15) for b in range(2)]
+            np.testing.assert_allclose(llp, refp, rtol=1e-11, err_msg="pull n=%d" % n)
