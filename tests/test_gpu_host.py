@@ -210,3 +210,32 @@ def test_find_parameters_with_pull(engine, gold_pull, tmp_path, capsys):
     assert (MC.naccv, MC.naccw, MC.nacctimezero) == (ref["naccv"], ref["naccw"], ref["nacct0"])
     np.testing.assert_allclose(MC.log_like, ref["ll"], rtol=1e-9)
     assert os.path.exists(out)
+
+
+@pytest.mark.parametrize("model,ncosF,ncosD", [("SinusCosinusModel", 5, 3), ("StepModel", 4, 2), ("OneStepModel", 4, 2)])
+def test_other_model_families_on_device(engine, gold_ll, tmp_path, capsys, model, ncosF, ncosD):
+    """The kernel takes the basis matrices of any model (lib/model.py:169-185, 238-262, 303-310): chain 0 equals the
+    oracle replay with the same bases on the device Philox tape."""
+    from mcdiff_b200 import philox
+    from mcdiff_b200.mc import find_parameters
+    from oracle import mcdiff_oracle as O
+    G = gold_ll
+    files = _files(str(tmp_path), G)
+    out = os.path.join(str(tmp_path), "out.%s.dat" % model)
+    nmc, seed = 120, 9
+    MC, logger = find_parameters(files, True, model, 0.2, 0.2, 0.5, 1.0, 0.1, 1.0, 1.0, nmc, 100.0, seed, out,
+                                 ncosF, ncosD, 0, False, None, -1, -1, False, None, nchains=3)
+    capsys.readouterr()
+    m = MC.model
+    n = 100
+    from mcdiff_b200.model import MODELS_1D
+    from mcdiff_b200.transitions import Transitions
+    m0 = MODELS_1D[model](Transitions(files), 1.0, ncosF, ncosD, 0)        # the start state the model class defines
+    vc0, wc0 = m0.v_coeff.copy(), m0.w_coeff.copy()
+    cfg = O.ChainConfig(G["P_counts"], G["P_lags"], True, v_basis=m.v_basis, w_basis=m.w_basis, dv=0.2, dw=0.2, temp=1.0,
+                        temp_end=1.0, nmc=nmc, num_mc_update=100.0)
+    tu, ti = philox.chain_tape(seed, 0, 0, nmc, n, n, ncosF, ncosD)
+    ref = O.replay(cfg, m.v_basis @ vc0, m.w_basis @ wc0, tu, ti, v_coeff0=vc0, w_coeff0=wc0)
+    assert (MC.naccv, MC.naccw) == (ref["naccv"], ref["naccw"])
+    np.testing.assert_allclose(MC.log_like, ref["ll"], rtol=1e-9)
+    np.testing.assert_allclose(MC.model.v_coeff, ref["v_coeff"], atol=1e-13)
