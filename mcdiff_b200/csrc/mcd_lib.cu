@@ -162,7 +162,8 @@ mcd_mc_run_gen_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
 
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_gen_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
-                       double* __restrict__ out_ll, double* __restrict__ out_P, int* __restrict__ status, double* gws) {
+                       const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
+                       int* __restrict__ status, double* gws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
@@ -170,19 +171,30 @@ mcd_loglike_gen_kernel(Problem P, int B, const double* __restrict__ v, const dou
   Chain<DeviceExec, 2> ch(ex, P, s);
   ch.build_tables();
   const int n = P.n, np = P.np, dim_w = P.dim_w;
-  double* slots = gws + (size_t)blockIdx.x * P.plan[0].nslots * P.np * P.ld;
+  // per-profile lag times are accepted when they are the problem's lag times plus one offset (the time-offset
+  // trial of lib/MCState.py:207-210): the LagPlan of shifted lag times then applies
+  const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
+  const int nslots = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+  double* slots = gws + (size_t)blockIdx.x * nslots * P.np * P.ld;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     ex.par([&](int tid) {
       for (int i = tid; i < np; i += kThreads) {
         s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
         s.w[i] = (i < dim_w) ? w[(size_t)b * dim_w + i] : 0.0;
       }
-      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = P.lagtimes[l];
+      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       if (tid == 0) s.sc->status = 0;
+    });
+    ex.single([&]() {
+      if (lagtimes) {
+        const double shift = s.lag[0] - P.lagtimes[0];
+        for (int l = 1; l < P.nlag; ++l)
+          if (!(fabs((s.lag[l] - P.lagtimes[l]) - shift) <= 1e-9 * fabs(P.lagtimes[l]))) s.sc->status |= MCD_ST_BAD_LAGS;
+      }
     });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = ch.evaluate_gen(s.v, s.w, s.lag, P.plan[0], slots, 0, Pb, &sw);
+    const double ll = (s.sc->status & MCD_ST_BAD_LAGS) ? nan("") : ch.evaluate_gen(s.v, s.w, s.lag, pl, slots, 0, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -409,23 +421,25 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
                       const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
                       void* stream) {
   if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
-  if (method == MCD_METHOD_AUTO) method = (p->squaring_ok && !lagtimes) ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
+  if (method == MCD_METHOD_AUTO)
+    method = (p->squaring_ok && (!lagtimes || p->P.use_pull)) ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (method < MCD_METHOD_EIGEN || method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
-  if (method >= MCD_METHOD_SQUARING && (!p->squaring_ok || lagtimes)) return MCD_E_UNSUPPORTED;
+  if (method >= MCD_METHOD_SQUARING && (!p->squaring_ok || (lagtimes && !p->P.use_pull))) return MCD_E_UNSUPPORTED;
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const Problem& P = p->P;
   if (P.use_pull) {
-    if (lagtimes || method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA) return MCD_E_UNSUPPORTED;
+    if (method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA) return MCD_E_UNSUPPORTED;
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
-    if (P.plan[0].nslots > 0) {
-      int rc = ensure_gws(h, (size_t)grid * P.plan[0].nslots * P.np * P.ld * sizeof(double));
+    const int nslots = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+    if (nslots > 0) {
+      int rc = ensure_gws(h, (size_t)grid * nslots * P.np * P.ld * sizeof(double));
       if (rc != MCD_OK) return rc;
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_gen_kernel<<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, out_ll, out_P, status, h->gws);
+    mcd_loglike_gen_kernel<<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status, h->gws);
   } else if (p->blocked && method >= MCD_METHOD_SQUARING) {
     if (method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;

@@ -587,3 +587,23 @@ def test_small_and_odd_sizes(engine, pbc):
             llp, _, st = probp.loglike(v, w)
             refp = [O.log_like_lag(v[b], w[b], lags, counts, True, pull=0.15) for b in range(2)]
             np.testing.assert_allclose(llp, refp, rtol=1e-11, err_msg="pull n=%d" % n)
+
+
+def test_pull_time_offset_through_the_likelihood_seam(engine, gold_pull):
+    """mcd_loglike_batch on a --pull problem with per-profile lag times = lag times + offset (what
+    mcmove_timezero passes, lib/MCState.py:207-210); anything else is flagged, not silently computed."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    G = gold_pull
+    dF = float(G["ll/dF"][1])
+    prob = DeviceProblem(engine, G["counts"], G["lags"], True, pull=dF)
+    v, w = G["ll/v"][:2], G["ll/w"][:2]
+    lt = np.stack([G["lags"] + 0.37, G["lags"] - 1.25])
+    ll, _, st = prob.loglike(v, w, lagtimes=lt)
+    assert not st.any()
+    for b in range(2):
+        np.testing.assert_allclose(ll[b], O.log_like_lag(v[b], w[b], lt[b], G["counts"], True, pull=dF), rtol=1e-12)
+    bad = lt.copy()
+    bad[1, 2] += 0.5
+    ll, _, st = prob.loglike(v, w, lagtimes=bad)
+    assert st[0] == 0 and st[1] == 4 and np.isnan(ll[1]) and np.isfinite(ll[0])
