@@ -19,7 +19,7 @@
 
 #include "mcd_exec.cuh"
 
-namespace mcd {
+namespace MCD_NS {
 
 constexpr int kMaxLag = 64;   // LagPlan arrays are sized for this
 constexpr int kMaxCoef = 64;
@@ -2331,4 +2331,4 @@ struct Chain {
   }
 };
 
-}  // namespace mcd
+}  // namespace MCD_NS

@@ -24,8 +24,14 @@
 
 // Optional phase clocks (-DMCD_PHASE_CLOCK, profiles/prof_phases.py): thread 0 of CTA 0 adds the cycles
 // since its previous stamp to g_phase_clk[id].  Compiled out of the product library.
+// All device code lives in namespace MCD_NS (default `mcd`): a second translation unit compiles the same
+// chain body with another CTA size (-DMCD_THREADS=128 -DMCD_NS=mcd128, mcd_small.cu).
+#ifndef MCD_NS
+#define MCD_NS mcd
+#endif
+
 #if defined(MCD_PHASE_CLOCK) && defined(__CUDACC__)
-namespace mcd {
+namespace MCD_NS {
 __device__ long long g_phase_clk[32];
 __shared__ long long s_phase_clk[33];   // [32] = previous stamp; shared memory keeps a stamp at ~2 x 30 cycles
 }
@@ -35,21 +41,21 @@ __shared__ long long s_phase_clk[33];   // [32] = previous stamp; shared memory 
   do {                                                                          \
     if (threadIdx.x == 0 && blockIdx.x == 0) {                                  \
       const long long t_ = clock64();                                           \
-      mcd::s_phase_clk[id] += t_ - mcd::s_phase_clk[32];                        \
-      mcd::s_phase_clk[32] = clock64();                                         \
+      MCD_NS::s_phase_clk[id] += t_ - MCD_NS::s_phase_clk[32];                        \
+      MCD_NS::s_phase_clk[32] = clock64();                                         \
     }                                                                           \
   } while (0)
 #define MCD_CLK_BEGIN()                                                         \
   do {                                                                          \
     if (threadIdx.x == 0 && blockIdx.x == 0) {                                  \
-      for (int q_ = 0; q_ < 32; ++q_) mcd::s_phase_clk[q_] = 0;                 \
-      mcd::s_phase_clk[32] = clock64();                                         \
+      for (int q_ = 0; q_ < 32; ++q_) MCD_NS::s_phase_clk[q_] = 0;                 \
+      MCD_NS::s_phase_clk[32] = clock64();                                         \
     }                                                                           \
   } while (0)
 #define MCD_CLK_END()                                                           \
   do {                                                                          \
     if (threadIdx.x == 0 && blockIdx.x == 0)                                    \
-      for (int q_ = 0; q_ < 32; ++q_) mcd::g_phase_clk[q_] += mcd::s_phase_clk[q_]; \
+      for (int q_ = 0; q_ < 32; ++q_) MCD_NS::g_phase_clk[q_] += MCD_NS::s_phase_clk[q_]; \
   } while (0)
 #else
 #define MCD_CLK(id) do { } while (0)
@@ -57,7 +63,7 @@ __shared__ long long s_phase_clk[33];   // [32] = previous stamp; shared memory 
 #define MCD_CLK_END() do { } while (0)
 #endif
 
-namespace mcd {
+namespace MCD_NS {
 
 #ifndef MCD_THREADS
 #define MCD_THREADS 384
@@ -262,4 +268,4 @@ struct HostExec {
 };
 #endif
 
-}  // namespace mcd
+}  // namespace MCD_NS

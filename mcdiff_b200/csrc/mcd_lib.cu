@@ -13,6 +13,13 @@
 
 using namespace mcd;
 
+// mcd_small.cu: the same chain body compiled for 128-thread CTAs (3 per SM), used for np <= kSmallBins
+size_t mcd128_problem_bytes();
+size_t mcd128_smem_bytes(int np, int ld);
+int mcd128_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
+                         double* gws, cudaStream_t st);
+constexpr int kSmallBins = 56;   // 7 x 7 tiles: at most 4 symmetric warp tasks
+
 static_assert(sizeof(mcd_mc_params) == sizeof(McParams), "mcd_mc_params layout");
 static_assert(sizeof(mcd_chain_io) == sizeof(ChainIO), "mcd_chain_io layout");
 static_assert(MCD_NSCAL == S_NSCAL && MCD_NCOUNT == C_NCOUNT, "slot counts");
@@ -514,6 +521,13 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
     if (mp.method >= MCD_METHOD_SQUARING && pl.nslots > 0) {
       int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));
       if (rc != MCD_OK) return rc;
+    }
+    if (mp.method == MCD_METHOD_SQUARING && P.np <= kSmallBins && mcd128_problem_bytes() == sizeof(Problem)) {
+      // small profiles: 128-thread CTAs, three per SM (mcd_small.cu)
+      int rc = mcd128_launch_mc_run(&P, &mp, &cio, nchains, nsteps, mcd128_smem_bytes(P.np, P.ld), h->gws, st);
+      if (rc != MCD_OK) return rc;
+      h->launches++;
+      return MCD_OK;
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));

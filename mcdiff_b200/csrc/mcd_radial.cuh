@@ -13,7 +13,7 @@
 #pragma once
 #include "mcd_chain.cuh"
 
-namespace mcd {
+namespace MCD_NS {
 
 struct RadProblem {
   int n, np, ld, pbc, dim_w, nlag, dim_rad, lmax;
@@ -852,4 +852,4 @@ mcd_rad_mc_run_kernel(RadProblem R, RadMcParams mp, RadChainIO io, int nsteps, d
 }
 #endif
 
-}  // namespace mcd
+}  // namespace MCD_NS

@@ -1,0 +1,46 @@
+// 128-thread build of the chain body for small profiles (np <= 56).
+//
+// A symmetric product of a matrix with at most 7 x 7 tiles has at most 4 warp tasks, so the 384-thread
+// kernel of mcd_lib.cu keeps 4 of its 12 warps busy and every scalar phase costs a CTA barrier.  The same
+// source compiled for 4 warps needs ~70 KB of shared memory and <= 168 registers, i.e. THREE CTAs per SM:
+// one chain's Horner passes / epilogues / Metropolis overlap the other chains' MMAs.
+// Separate translation unit, separate namespace (mcd128): nothing here changes the code of the main kernels.
+#define MCD_THREADS 128
+#define MCD_NS mcd128
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "mcd_chain.cuh"
+
+using namespace mcd128;
+
+__global__ void __launch_bounds__(kThreads, 3)
+mcd128_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec> ch(ex, P, s);
+  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld);
+}
+
+// C++ entry points used by mcd_lib.cu (the structs have the same layout in both namespaces; they are passed
+// as bytes so that the two translation units do not share types)
+size_t mcd128_problem_bytes() { return sizeof(Problem); }
+size_t mcd128_smem_bytes(int np, int ld) { return smem_matrix_bytes(np, ld) + smem_vectors_bytes(np); }
+
+int mcd128_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
+                         double* gws, cudaStream_t st) {
+  Problem P;
+  McParams mp;
+  ChainIO cio;
+  std::memcpy(&P, problem, sizeof(P));
+  std::memcpy(&mp, params, sizeof(mp));
+  std::memcpy(&cio, io, sizeof(cio));
+  cudaError_t e = cudaFuncSetAttribute(mcd128_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  mcd128_mc_run_kernel<<<nchains, kThreads, smem, st>>>(P, mp, cio, nsteps, gws);
+  return (int)cudaGetLastError();
+}

@@ -17,11 +17,22 @@ DEPS = [SRC] + [os.path.join(ROOT, "mcdiff_b200", "csrc", f) for f in ("mcd_chai
     os.path.join(ROOT, "include", "mcdiff_b200.h")]
 
 
-def build(force=False):
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
-        return SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", SRC, "-o", SO])
-    return SO
+def build(force=False, threads=None):
+    """threads=128: the chain body as the 128-thread translation unit of the library compiles it (mcd_small.cu)."""
+    so = SO if threads is None else SO.replace(".so", "%d.so" % threads)
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in DEPS):
+        return so
+    extra = [] if threads is None else ["-DMCD_THREADS=%d" % threads]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC"] + extra + [SRC, "-o", so])
+    return so
+
+
+def use_threads(threads=None):
+    """Switch the emulator library used by loglike_batch / HostChains (None = the default 384-thread build)."""
+    global _lib
+    _lib = C.CDLL(build(threads=threads))
+    _lib.emul_loglike_batch.restype = C.c_int
+    _lib.emul_mc_run.restype = C.c_int
 
 
 _lib = None

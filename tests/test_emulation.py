@@ -214,3 +214,38 @@ def test_pull_replay_prefix_matches_reference(gold_pull, tag, nsteps):
     assert np.array_equal(dec[0] & 1, g("accepted")[:nsteps])
     assert np.array_equal((dec[0] >> 1) & 1, g("accepted_t0")[:nsteps])
     np.testing.assert_allclose(ch.scal[0, K.S_LL], g("ll_after")[nsteps - 1], rtol=1e-11)
+
+
+def test_chain_body_with_128_threads():
+    """The library compiles the same chain body for 128-thread CTAs (mcd_small.cu, profiles with np <= 56): every
+    table, reduction and thread map must be free of the 384-thread assumption.  n = 48 and n = 21, cosine model with
+    time-offset moves, against the oracle replay."""
+    from oracle import mcdiff_oracle as O
+    H.use_threads(128)
+    try:
+        for n, nsteps in ((48, 40), (21, 30)):
+            lags = np.array([5.0, 10.0, 15.0])
+            counts = O.synthetic_counts(n, lags, seed=8, total=1.0e5, dz=1.0)[0]
+            vb, wb = O.cos_basis_center(n, 5), O.cos_basis_border(n, n, 4)
+            wc0 = np.zeros(4)
+            wc0[0] = -1.0
+            w0 = wb @ wc0
+            cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=0.3, dw=0.3, dtimezero=0.3, temp=1.0,
+                                nmc=nsteps, num_mc_update=10.0, move_timezero=True)
+            tu, ti = O.make_tape(np.random.default_rng(n), nsteps, cfg)
+            ref = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(5), w_coeff0=wc0)
+            prob = H.HostProblem(counts, lags, True, v_basis=vb, w_basis=wb)
+            ll0 = O.log_like_lag(np.zeros(n), w0, lags, counts, True)
+            ll, _, st, _ = H.loglike_batch(prob, np.zeros(n), w0, method=SQUARING)
+            np.testing.assert_allclose(ll[0], ll0, rtol=1e-12)
+            ch = H.HostChains(prob, 1, np.zeros(n), w0, np.zeros(5), wc0, ll0=ll0, dv=0.3, dw=0.3, dt0=0.3)
+            mp = K.McParams()
+            mp.num_mc_update, mp.dtemp, mp.min_lt, mp.move_timezero = 10.0, 0.0, 5.0, 1
+            mp.sample_every, mp.refresh_every, mp.use_tape, mp.method = 100, 16, 1, SQUARING
+            dec, _, _ = ch.run(nsteps, mp, tu, ti)
+            assert np.array_equal(dec[0] & 1, ref["accepted"])
+            assert np.array_equal((dec[0] >> 1) & 1, ref["accepted_t0"])
+            np.testing.assert_allclose(ch.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
+            np.testing.assert_allclose(ch.scal[0, K.S_DV:K.S_DW + 1], [ref["dv"], ref["dw"]], rtol=1e-13)
+    finally:
+        H.use_threads(None)

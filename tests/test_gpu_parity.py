@@ -607,3 +607,46 @@ def test_pull_time_offset_through_the_likelihood_seam(engine, gold_pull):
     bad[1, 2] += 0.5
     ll, _, st = prob.loglike(v, w, lagtimes=bad)
     assert st[0] == 0 and st[1] == 4 and np.isnan(ll[1]) and np.isfinite(ll[0])
+
+
+@pytest.mark.parametrize("n,pbc", [(48, True), (24, True), (40, False), (56, True)])
+def test_small_profiles_run_on_the_128_thread_kernel(engine, n, pbc):
+    """np <= 56: mcd_mc_run dispatches to the 128-thread build of the chain body (three CTAs per SM); device Philox
+    trajectories must equal the oracle replay exactly like the 384-thread kernel's."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from mcdiff_b200 import philox
+    from oracle import mcdiff_oracle as O
+    lags = np.array([5.0, 10.0, 15.0])
+    rng = np.random.default_rng(n)
+    if pbc:
+        counts = O.synthetic_counts(n, lags, seed=8, total=1.0e5, dz=1.0)[0]
+    else:
+        counts = rng.integers(0, 60, size=(3, n, n)).astype(np.int32)
+        ii, jj = np.indices((n, n))
+        counts[:, np.abs(ii - jj) > 6] = 0
+    dim_w = n if pbc else n - 1
+    vb, wb = O.cos_basis_center(n, 5), O.cos_basis_border(dim_w, n, 4)
+    wc0 = np.zeros(4)
+    wc0[0] = -1.0
+    w0 = wb @ wc0
+    nch, nsteps, seed = 5, 50, 31
+    prob = DeviceProblem(engine, counts, lags, pbc, v_basis=vb, w_basis=wb)
+    ch = ChainBatch(prob, nch)
+    ch.set_state(np.zeros(n), w0, np.zeros(5), wc0, dv=0.3, dw=0.3, dtimezero=0.3)
+    ch.init_log_like()
+    case = dict(nmc_update=10.0, dtemp=0.0, lagtimes=lags, move_timezero=True)
+    mp = _params(case, nsteps, use_tape=0, seed=seed, method=METHODS["squaring"])
+    d1, _, _ = ch.run(30, mp, record=True)
+    d2, _, _ = ch.run(20, mp, record=True)
+    dec = np.concatenate([d1.cpu().numpy(), d2.cpu().numpy()], axis=1)
+    st = ch.host_state()
+    assert not st["counters"][:, 6].any()
+    cfg = O.ChainConfig(counts, lags, pbc, v_basis=vb, w_basis=wb, dv=0.3, dw=0.3, dtimezero=0.3, temp=1.0, nmc=nsteps,
+                        num_mc_update=10.0, move_timezero=True)
+    for c in range(nch):
+        tu, ti = philox.chain_tape(seed, c, 0, nsteps, n, dim_w, 5, 4)
+        out = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(5), w_coeff0=wc0)
+        assert np.array_equal(dec[c] & 1, out["accepted"]), "chain %d" % c
+        assert np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
+        np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
+        np.testing.assert_allclose(st["scal"][c][2:4], [out["dv"], out["dw"]], rtol=1e-13)
