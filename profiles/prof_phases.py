@@ -1,5 +1,5 @@
 """Per-phase cycle counts of the MC kernel (bench workload) from a -DMCD_PHASE_CLOCK build.
-Build:  nvcc <flags of __graft_entry__> -DMCD_PHASE_CLOCK mcdiff_b200/csrc/mcd_lib.cu -o mcdiff_b200/libmcdiff_b200_clk.so
+Build:  nvcc <flags of __graft_entry__> -DMCD_PHASE_CLOCK mcdiff_b200/csrc/mcd_lib.cu mcdiff_b200/csrc/mcd_small.cu -o mcdiff_b200/libmcdiff_b200_clk.so
 Run:    MCDIFF_B200_LIB=mcdiff_b200/libmcdiff_b200_clk.so python profiles/prof_phases.py
 Thread 0 of CTA 0 stamps clock64() at phase boundaries; the instrumented library is never the product."""
 import ctypes as C, os, sys
