@@ -38,11 +38,12 @@ MCD_HOSTDEV size_t rad_workspace_doubles(const RadProblem& R) {
   const size_t sq = ((size_t)R.nlag * R.lmax + (size_t)kMaxSlots * kMaxRadBatch) * R.np * R.ld;
   return eig > sq ? eig : sq;
 }
-// shared memory: nbatch pairs of work matrices, the chain vectors, a0[np], elm[lmax][np] (eigen fallback),
-// exp(wrad)[np], the batch diagonals [nbatch][np], the pair table
+// shared memory: nbatch pairs of work matrices, the chain vectors, a0[np], elm[lmax][np] (only the eigen
+// fallback needs it: lag sets without a LagPlan), exp(wrad)[np], the batch diagonals [nbatch][np], the pair table
+MCD_HOSTDEV size_t rad_elm_doubles(const RadProblem& R) { return R.plan.ok ? 0 : (size_t)R.lmax * R.np; }
 MCD_HOSTDEV size_t rad_smem_bytes(const RadProblem& R, int nbatch) {
   return (size_t)nbatch * smem_matrix_bytes(R.np, R.ld) + smem_vectors_bytes(R.np) +
-         ((size_t)2 * R.np + (size_t)R.lmax * R.np + (size_t)nbatch * R.np) * 8 +
+         ((size_t)2 * R.np + rad_elm_doubles(R) + (size_t)nbatch * R.np) * 8 +
          (((size_t)R.n * (R.n + 1) + 15) & ~(size_t)15);
 }
 // pairs i <= j, padded so that the two-pair (32-byte) loads of the Bessel-sum epilogue stay in bounds
@@ -559,7 +560,13 @@ struct RadCtx {
   }
 
   __device__ __forceinline__ double loglike(const double* wrad_vec, double* Pb, int* bad_out) {
-    if (R.plan.ok && ch.dmma_ok()) return loglike_sq(wrad_vec, Pb, bad_out);
+    if (R.plan.ok) {          // elm (eigen fallback) is not allocated then: never fall through
+      if (!ch.dmma_ok()) {
+        if (bad_out) *bad_out = 1;
+        return nan("");
+      }
+      return loglike_sq(wrad_vec, Pb, bad_out);
+    }
     return loglike_eig(wrad_vec, Pb, bad_out);
   }
 
@@ -666,7 +673,7 @@ __global__ void mcd_rad_pair_counts_kernel(const double* __restrict__ counts, do
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);                                 \
   double* a0 = reinterpret_cast<double*>(smem_raw + mat_bytes + smem_vectors_bytes(R.np));                       \
   double* elm = a0 + R.np;                                                                                      \
-  double* ewr = elm + (size_t)R.lmax * R.np;                                                                    \
+  double* ewr = elm + rad_elm_doubles(R);                                                                       \
   double* ab = ewr + R.np;                                                                                      \
   unsigned char* ptab = reinterpret_cast<unsigned char*>(ab + (size_t)R.nbatch * R.np);                         \
   DeviceExec ex(s.red);                                                                                         \
