@@ -42,3 +42,58 @@ def test_two_ranks_equal_one_rank(engine, gold_ll, tmp_path):
     for key in ("log_like", "naccv", "naccw", "v_param", "w_param", "dv", "dw"):
         np.testing.assert_array_equal(a[key], b[key])
     assert open(out1).read() == open(out2).read()          # chain 0 file identical
+
+
+@pytest.mark.parametrize("mode", ["pull", "radial", "blocked"])
+def test_two_ranks_equal_one_rank_other_paths(engine, gold_ll, tmp_path, mode):
+    """Same check for the other kernels of the path: --pull (general engine), --rad (radial loop) and a 120-bin
+    profile (blocked engine)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from mcdiff_b200.transitions import write_Tmat_cube, write_Tmat_square
+    from oracle import mcdiff_oracle as O
+    tmp = str(tmp_path)
+    files = []
+    if mode == "radial":
+        RR = np.load(os.path.join(ROOT, "tests", "golden", "radial_replay_golden.npz"))
+        counts, lags = RR["radcos/counts"], RR["radcos/lags"]
+        nr, dim_rad, lmax = counts.shape[-1], int(RR["radcos/dim_rad"]), int(RR["radcos/lmax"])
+        for il, lag in enumerate(lags):
+            fn = os.path.join(tmp, "rad.%d.dat" % il)
+            write_Tmat_cube(counts[il].astype(int), fn, float(lag), "pbc", edges=np.linspace(-4.0, 4.0, nr + 1),
+                            redges=np.arange(dim_rad) * 0.5, dt=1.0, dn=int(lag))
+            files.append(fn)
+        common = ["--model", "RadCosinusModel", "--ncosDrad", "4", "--rad", str(lmax), "-n", "100", "--nmc_update", "40",
+                  "-T", "1", "--Tend", "1", "--dwrad", "0.4", "-s", "5", "--nchains", "5"]
+        keys = ("log_like", "wrad")
+    else:
+        if mode == "blocked":
+            lags = np.array([5.0, 10.0])
+            counts, _, edges, _, _ = O.synthetic_counts(n=120, lags=lags, seed=2, total=1.0e5, dz=0.5)
+            n = 120
+        else:
+            G = gold_ll
+            counts, lags, edges, n = G["P_counts"], G["P_lags"], G["P_edges"], 100
+        for l, lag in enumerate(lags):
+            fn = os.path.join(tmp, "transitions.nbins%d.%d.pbc.dat" % (n, int(lag)))
+            write_Tmat_square(counts[l], fn, float(lag), "pbc", edges=edges, dt=1.0, dn=int(lag))
+            files.append(fn)
+        common = ["--model", "CosinusModel", "--ncosF", "6", "--ncosD", "4", "-n", "100", "--nmc_update", "50", "-T", "1",
+                  "--Tend", "1", "--dv", "0.1", "--dw", "0.1", "-s", "11", "--nchains", "5"]
+        if mode == "pull":
+            common += ["--pull", "0.3"]
+        keys = ("log_like", "naccv", "naccw", "v_param", "w_param")
+    script = os.path.join(ROOT, "scripts", "run-mcdiff")
+    out1, out2 = os.path.join(tmp, "one.dat"), os.path.join(tmp, "two.dat")
+    env = dict(os.environ)
+    r1 = subprocess.run([sys.executable, script, "-o", out1] + common + files, capture_output=True, text=True, env=env)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                         "--master-addr", "127.0.0.1", "--master-port", "29534", script, "-o", out2] + common + files,
+                        capture_output=True, text=True, env=env)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    a, b = np.load(out1 + ".chains.npz"), np.load(out2 + ".chains.npz")
+    for key in keys:
+        np.testing.assert_array_equal(a[key], b[key])
+    assert open(out1).read() == open(out2).read()
