@@ -61,9 +61,9 @@ enum {
  *             G(t_i) = G(t_{i-1}) G(t_i - t_{i-1}); every distinct operand is an earlier G(t_j) or gets its
  *             own squaring chain (at most 8), so arithmetic progressions (10,20,30,40 / a single lag) need
  *             one chain, time-offset moves (--t0) two.  n <= 104: work matrices in shared memory;
- *             104 < n <= 208: blocked (matrices in a per-chain global workspace, 2 x 2 block products
- *             through shared-memory operand panels; tensor-core products only, no SQUARING_DFMA);
- *             larger n: EIGEN only. */
+ *             104 < n <= 508: blocked (matrices in a per-chain global workspace, nblk x nblk block products,
+ *             nblk = ceil(n / 104) <= 5, through shared-memory operand panels; tensor-core products only,
+ *             no SQUARING_DFMA). */
 enum { MCD_METHOD_AUTO = 0, MCD_METHOD_EIGEN = 1, MCD_METHOD_SQUARING = 2,
        MCD_METHOD_SQUARING_DFMA = 3 /* same algorithm, products on the FP64 vector pipe (A/B reference) */ };
 

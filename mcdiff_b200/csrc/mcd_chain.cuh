@@ -45,6 +45,7 @@ struct Problem {
   int n, np, ld, dim_w, pbc, nlag;
   int ncosF, ncosD;
   int nbk, lds, blocked;   // shared-memory panel size and pitch (= np, ld unless blocked), see set_layout
+  int nblk, reserved2;     // blocks per dimension of the blocked engine (np = nblk * nbk), 1 otherwise
   const double* lagtimes;  // [nlag]
   const int* counts;       // [nlag][np][np]  (padded, counts[l][i][j] = # transitions j -> i)
   const int* nsym;         // [nlag][np][np]  N_ij + N_ji (i != j), N_ii on the diagonal
@@ -170,17 +171,22 @@ struct ChainIO {
 MCD_HOSTDEV int padded_bins(int n) { return (n + 7) & ~7; }
 MCD_HOSTDEV int leading_dim(int np) { return np + 4; }
 
-// Largest bin count whose two work matrices fit in shared memory; up to twice that the squaring
-// engine runs blocked: matrices live in a per-CTA global workspace (L2) and are multiplied as
-// 2 x 2 blocks whose nbk x nbk panels are staged through the two shared-memory buffers.
+// Largest bin count whose two work matrices fit in shared memory; beyond it the squaring engine runs
+// blocked: matrices live in a per-CTA global workspace (L2) and are multiplied as nblk x nblk blocks
+// (nblk = 2 ... 5) whose nbk x nbk panels (nbk <= 104) are staged through the two shared-memory buffers.
 constexpr int kMaxSmemBins = 104;
+constexpr int kMaxBlocks = 5;
 MCD_HOSTDEV void set_layout(Problem& P, int n) {
   P.n = n;
-  P.blocked = (n > kMaxSmemBins && n <= 2 * kMaxSmemBins) ? 1 : 0;
-  P.np = P.blocked ? ((n + 15) & ~15) : padded_bins(n);
+  P.nblk = (n + kMaxSmemBins - 1) / kMaxSmemBins;
+  P.blocked = (P.nblk >= 2 && P.nblk <= kMaxBlocks) ? 1 : 0;
+  if (!P.blocked) P.nblk = 1;
+  const int q = 8 * P.nblk;
+  P.np = ((n + q - 1) / q) * q;
   P.ld = leading_dim(P.np);
-  P.nbk = P.blocked ? P.np / 2 : P.np;
+  P.nbk = P.np / P.nblk;
   P.lds = leading_dim(P.nbk);
+  P.reserved2 = 0;
 }
 
 MCD_HOSTDEV int sample_dim(const Problem& P) {
@@ -241,10 +247,13 @@ struct Smem {
   int ntiles, nblk;
 };
 
-MCD_HOSTDEV size_t smem_vectors_bytes(int np) {
-  size_t d = (size_t)np * 11 + 256 + kMaxCoef * 3 + kMaxLag * 2 + (size_t)np /*rc,rs*/ + 32 + kThreads;
+// panels: layout of the blocked engine, without the vectors and tables only the eigen engine uses
+// (lam, el, rc, rs, rp, rq, tile and Jacobi-block lists) -- at np = 520 those alone would be 100 KB
+MCD_HOSTDEV size_t smem_vectors_bytes(int np, bool panels = false) {
+  size_t d = (size_t)np * (panels ? 9 : 11) + 256 + kMaxCoef * 3 + kMaxLag * 2 + (panels ? 0 : (size_t)np) /*rc,rs*/ + 32 + kThreads;
   size_t nb = np / 4, h = np / 2;
-  size_t bytes = d * 8 + (size_t)np * 4 /*rp,rq*/ + 64 * (kThreads / 32) /*wti*/ + nb * (nb + 1) + h * (h - 1) + 16 * (kThreads / 32) + sizeof(Scalars) + 64 +
+  size_t bytes = d * 8 + (panels ? 0 : (size_t)np * 4) /*rp,rq*/ + 64 * (kThreads / 32) /*wti*/ +
+                 (panels ? 0 : nb * (nb + 1) + h * (h - 1)) + 16 * (kThreads / 32) + sizeof(Scalars) + 64 +
                  2 * kThreads + 32 /*hrow, hrem, tord*/;
   return (bytes + 15) & ~(size_t)15;
 }
@@ -267,8 +276,8 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.hv = d; d += np;
   s.lgc = d; d += 128;
   s.lgl = d; d += 128;
-  s.lam = d; d += np;
-  s.el = d; d += np;
+  s.lam = d; d += panels ? 0 : np;
+  s.el = d; d += panels ? 0 : np;
   s.v = d; d += np;
   s.w = d; d += np;
   s.vt = d; d += np;
@@ -278,18 +287,18 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.ct = d; d += kMaxCoef;
   s.lag = d; d += kMaxLag;
   s.lag_try = d; d += kMaxLag;
-  s.rc = d; d += np / 2;
-  s.rs = d; d += np / 2;
+  s.rc = d; d += panels ? 0 : np / 2;
+  s.rs = d; d += panels ? 0 : np / 2;
   s.red = d; d += 32;
   s.part = d; d += kThreads;
   s.sc = reinterpret_cast<Scalars*>(d);
   d += (sizeof(Scalars) + 7) / 8;
   int* ip = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(d) + 15) & ~(uintptr_t)15);   // wti: 128-bit loads
   s.wti = ip; ip += 16 * (kThreads / 32);
-  s.rp = ip; ip += np / 2;
-  s.rq = ip; ip += np / 2;
+  s.rp = ip; ip += panels ? 0 : np / 2;
+  s.rq = ip; ip += panels ? 0 : np / 2;
   unsigned char* c = reinterpret_cast<unsigned char*>(ip);
-  const int nb = np / 4, h = np / 2;
+  const int nb = panels ? 0 : np / 4, h = panels ? 0 : np / 2;
   s.ntiles = nb * (nb + 1) / 2;
   s.nblk = h * (h - 1) / 2;
   s.tiles = c; c += 2 * s.ntiles;
@@ -1787,28 +1796,39 @@ struct Chain {
 
   // Dg <- Xg Yg for symmetric commuting matrices in the global workspace (Dg distinct from both).
   // cnt != nullptr: Dg is the kernel of a lag time, its likelihood terms are added to s.part.
+  // Block schedule per K: for I = 0 .. nblk-1 the panel A = X_KI stays while J sweeps I .. nblk-1.
+  // Squaring (Xg == Yg): J runs DOWN to I, J == I needs no load (B = A), and the last off-diagonal panel
+  // staged, X_K,I+1, is the next I's A (pointer swap): 1 + nblk (nblk-1)/2 panel loads per K (2 for nblk = 2).
+  // General product: J alternates direction from one I to the next, so the B panel at the turn is reused.
   MCD_HD void blk_product(const double* Xg, const double* Yg, double* Dg, const int* cnt, const int* nsy, double* Pl) {
-    const int nbk = P.nbk, ldg = P.ld;
+    const int nbk = P.nbk, ldg = P.ld, nblk = P.nblk;
     const bool same = (Xg == Yg);
-    for (int K = 0; K < 2; ++K)
-      for (int blk = 0; blk < 3; ++blk) {   // C_00, C_01 (+ C_10), C_11: one call site of blk_mma
-        const int I = (blk == 2) ? 1 : 0, J = (blk == 0) ? 0 : 1;
-        const double* A;
-        const double* B;
-        if (same) {   // XT = X_K0, B2 = X_K1 serve all three blocks
-          if (blk == 0) blk_load(s.XT, Xg, K, 0, s.B2, Xg, K, 1);
-          A = I ? s.B2 : s.XT;
-          B = J ? s.B2 : s.XT;
-        } else {      // XT = X_KI, B2 = Y_KJ
-          if (blk == 0) blk_load(s.XT, Xg, K, 0, s.B2, Yg, K, 0);
-          else if (blk == 1) blk_load(nullptr, nullptr, 0, 0, s.B2, Yg, K, 1);
-          else blk_load(s.XT, Xg, K, 1, nullptr, nullptr, 0, 0);
-          A = s.XT;
-          B = s.B2;
+    for (int K = 0; K < nblk; ++K) {
+      double* A = s.XT;
+      double* B = s.B2;
+      bool have_A = false;     // squaring: A already holds X_KI (it was the previous I's last B panel)
+      int b_has = -1;          // general product: column block of Y currently staged in B
+      for (int I = 0; I < nblk; ++I) {
+        if (!have_A) blk_load(A, Xg, K, I, nullptr, nullptr, 0, 0);
+        have_A = false;
+        const bool down = same || (I & 1);
+        for (int q = 0; q < nblk - I; ++q) {
+          const int J = down ? nblk - 1 - q : I + q;
+          const double* Bp = B;
+          if (same && J == I) Bp = A;
+          else if (same || b_has != J) {
+            blk_load(nullptr, nullptr, 0, 0, B, Yg, K, J);
+            b_has = J;
+          }
+          blk_mma(A, Bp, I == J, Dg + (size_t)I * nbk * ldg + J * nbk, Dg + (size_t)J * nbk * ldg + I * nbk, K == 0,
+                  K == nblk - 1, I * nbk, J * nbk, cnt, nsy, Pl);
         }
-        blk_mma(A, B, I == J, Dg + (size_t)I * nbk * ldg + J * nbk, Dg + (size_t)J * nbk * ldg + I * nbk, K == 0, K == 1,
-                I * nbk, J * nbk, cnt, nsy, Pl);
+        if (same && I + 1 < nblk) {   // B holds X_K,I+1
+          double* tmp = A; A = B; B = tmp;
+          have_A = true;
+        }
       }
+    }
   }
 
   // likelihood terms of a kernel sitting in the global workspace (pairs i <= j)

@@ -377,7 +377,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     CUDA_TRY(cudaStreamSynchronize(st));
     plan_lags(hl, d->nlag, false, &P.plan[0]);
     plan_lags(hl, d->nlag, true, &P.plan[1]);
-    p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np);
+    p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np, true);
     p->blocked = (P.blocked && p->blk_smem_bytes <= (size_t)h->max_smem_optin) ? 1 : 0;
     p->squaring_ok = (p->in_smem || p->blocked) && P.plan[0].ok && P.plan[1].ok;
     // --pull: only the general squaring engine applies (periodic, work matrices in shared memory, a LagPlan)

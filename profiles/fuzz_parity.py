@@ -17,7 +17,7 @@ LAGSETS = [(10.0,), (5.0, 10.0, 15.0, 20.0), (10.0, 20.0, 30.0, 40.0), (2.0, 4.0
 bad = 0
 t_start = time.time()
 for it in range(ncfg):
-    n = int(rng.choice([5, 12, 21, 30, 37, 48, 56, 57, 64, 80, 97, 100, 104, 110, 128, 150, 200]))
+    n = int(rng.choice([5, 12, 21, 30, 37, 48, 56, 57, 64, 80, 97, 100, 104, 110, 128, 150, 200, 230, 320]))
     lags = np.array(LAGSETS[rng.integers(len(LAGSETS))])
     pull = float(rng.normal(0, 0.2)) if (rng.random() < 0.25 and n <= 104 and n >= 8) else None
     pbc = True if pull is not None else bool(rng.random() < 0.7)

@@ -125,7 +125,8 @@ def _blocked_problem(n, lags, pbc, seed=3):
 
 @pytest.mark.parametrize("n,lags,pbc", [(120, (5.0, 10.0, 15.0), True), (200, (5.0, 10.0, 20.0, 40.0), True),
                                         (136, (3.0, 7.0, 10.0), False), (106, (10.0,), True),
-                                        (208, (5.0, 10.0), True)])
+                                        (208, (5.0, 10.0), True), (250, (5.0, 10.0), True),
+                                        (330, (4.0, 8.0, 12.0), False)])
 def test_blocked_squaring_engine(n, lags, pbc):
     """104 < n <= 208: matrices in a global workspace, 2 x 2 block products through the
     shared-memory panels (fast plan, general plans with parked operands, non-periodic, a single

@@ -293,7 +293,9 @@ def test_large_n_generic_path(engine):
 
 @pytest.mark.parametrize("n,lags,pbc", [(120, (5.0, 10.0, 15.0), True), (200, (5.0, 10.0, 20.0, 40.0), True),
                                         (136, (3.0, 7.0, 10.0), False), (106, (10.0,), True),
-                                        (208, (5.0, 10.0), True), (168, (4.0, 4.0, 9.0), True)])
+                                        (208, (5.0, 10.0), True), (168, (4.0, 4.0, 9.0), True),
+                                        (250, (5.0, 10.0), True), (330, (4.0, 8.0, 12.0), False),
+                                        (508, (6.0, 12.0), True)])
 def test_blocked_squaring_engine(engine, n, lags, pbc):
     """104 < n <= 208 on the tensor-core squaring engine: fast and general lag plans, non-periodic,
     single lag, duplicate lag, the largest size; more profiles than CTAs of one wave are not needed,
@@ -408,20 +410,21 @@ def test_squaring_general_lag_sets(engine, gold_ll):
 
 
 def test_squaring_rejects_unsupported(engine):
-    """n = 240 exceeds even the blocked squaring engine (n <= 208): SQUARING is refused, AUTO falls
-    back to the eigen engine on global work matrices."""
+    """A lag set without a LagPlan (nine incommensurate differences): SQUARING is refused, AUTO falls back to the
+    eigen engine (here on global work matrices, n = 240)."""
     from mcdiff_b200.engine import DeviceProblem
     from mcdiff_b200._capi import McdError
     from oracle import mcdiff_oracle as O
     rng = np.random.default_rng(0)
-    counts = rng.integers(0, 5, size=(1, 240, 240))
-    prob = DeviceProblem(engine, counts, [10.0], True)
+    lags = np.cumsum([1.0, 1.1, 1.23, 1.37, 1.51, 1.69, 1.83, 1.97, 2.11])
+    counts = rng.integers(0, 5, size=(len(lags), 240, 240))
+    prob = DeviceProblem(engine, counts, lags, True)
     assert not prob.squaring_ok and not prob.in_smem
     with pytest.raises(McdError):
         prob.loglike(np.zeros(240), np.zeros(240), method=METHODS["squaring"])
     ll, _, st = prob.loglike(np.zeros(240), np.zeros(240))
     assert not st.any()
-    np.testing.assert_allclose(ll[0], O.log_like_lag(np.zeros(240), np.zeros(240), [10.0], counts, True), rtol=RTOL)
+    np.testing.assert_allclose(ll[0], O.log_like_lag(np.zeros(240), np.zeros(240), lags, counts, True), rtol=RTOL)
 
 
 @pytest.mark.parametrize("lags", [(5.0,), (5.0, 10.0, 15.0), (4.0, 6.0, 10.0),
@@ -650,3 +653,35 @@ def test_small_profiles_run_on_the_128_thread_kernel(engine, n, pbc):
         assert np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
         np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
         np.testing.assert_allclose(st["scal"][c][2:4], [out["dv"], out["dw"]], rtol=1e-13)
+
+
+def test_blocked_engine_three_blocks_mc(engine):
+    """n = 250 (3 x 3 blocks of 88 bins): MC loop with time-offset moves on device Philox streams against the oracle."""
+    from mcdiff_b200.engine import DeviceProblem, ChainBatch
+    from mcdiff_b200 import philox
+    from oracle import mcdiff_oracle as O
+    n, lags = 250, np.array([5.0, 10.0])
+    counts = O.synthetic_counts(n, lags, seed=6, total=2.0e5, dz=1.0)[0]
+    vb, wb = O.cos_basis_center(n, 5), O.cos_basis_border(n, n, 4)
+    wc0 = np.zeros(4)
+    wc0[0] = -1.0
+    w0 = wb @ wc0
+    nch, nsteps, seed = 2, 24, 17
+    prob = DeviceProblem(engine, counts, lags, True, v_basis=vb, w_basis=wb)
+    assert prob.squaring_ok and not prob.in_smem
+    ch = ChainBatch(prob, nch)
+    ch.set_state(np.zeros(n), w0, np.zeros(5), wc0, dv=0.2, dw=0.2, dtimezero=0.3)
+    ch.init_log_like()
+    case = dict(nmc_update=10.0, dtemp=0.0, lagtimes=lags, move_timezero=True)
+    mp = _params(case, nsteps, use_tape=0, seed=seed, method=METHODS["squaring"])
+    dec, _, _ = ch.run(nsteps, mp, record=True)
+    dec = dec.cpu().numpy()
+    st = ch.host_state()
+    cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=0.2, dw=0.2, dtimezero=0.3, temp=1.0, nmc=nsteps,
+                        num_mc_update=10.0, move_timezero=True)
+    for c in range(nch):
+        tu, ti = philox.chain_tape(seed, c, 0, nsteps, n, n, 5, 4)
+        out = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(5), w_coeff0=wc0)
+        assert np.array_equal(dec[c] & 1, out["accepted"]), "chain %d" % c
+        assert np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
+        np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
