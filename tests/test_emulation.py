@@ -145,8 +145,9 @@ def test_blocked_squaring_engine(n, lags, pbc):
         for l, lt in enumerate(lags):
             Pref = O.propagator(v[b], w[b], lt, pbc)
             assert np.max(np.abs(P[b, l] - Pref)) < 1e-13
-    ll_e, _, st, _ = H.loglike_batch(prob, v[:1], w[:1], method=EIGEN)      # same problem, global-memory eigen path
-    np.testing.assert_allclose(ll_e[0], ll[0], rtol=1e-9)   # eigen route: absolute, not componentwise, accuracy
+    if n <= 208:      # (the emulated Jacobi sweeps of a 330 x 330 matrix take a minute)
+        ll_e, _, st, _ = H.loglike_batch(prob, v[:1], w[:1], method=EIGEN)      # same problem, global-memory eigen path
+        np.testing.assert_allclose(ll_e[0], ll[0], rtol=1e-9)   # eigen route: absolute, not componentwise, accuracy
 
 
 def test_blocked_engine_mc_replay():
