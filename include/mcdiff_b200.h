@@ -49,7 +49,7 @@ enum {
   MCD_ST_EIG_NOCONV = 1, /* in-kernel eigensolver did not converge (non-finite input) */
   MCD_ST_NAN_TRIAL = 2,  /* a trial log-likelihood was NaN; the move was skipped like
                             lib/MCState.py:251 does */
-  MCD_ST_BAD_LAGS = 4    /* mcd_loglike_batch on a use_pull problem: per-profile lag times that are not the
+  MCD_ST_BAD_LAGS = 4    /* mcd_loglike_batch on a squaring engine: per-profile lag times that are not the
                             problem's lag times plus one offset (only that form has a LagPlan) */
 };
 
@@ -152,8 +152,9 @@ int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, in
 
 /* log L of B profiles: out_ll[b] = sum_l sum_ij counts[l,i,j] log(max(P_l[i,j], clip)) with
  * P_l = expm(lag_l R(v_b, w_b)).  lagtimes == NULL uses the problem's lag times, otherwise
- * [B][nlag] per-profile lag times (time-offset moves; EIGEN engine, or -- for use_pull problems -- the
- * general engine when they are the problem's lag times plus one offset per profile).  out_P (optional) receives
+ * [B][nlag] per-profile lag times (time-offset moves): AUTO = EIGEN for them (any lag times); an explicit
+ * MCD_METHOD_SQUARING (and every use_pull problem) accepts the problem's lag times plus one offset per profile
+ * and flags anything else with MCD_ST_BAD_LAGS.  out_P (optional) receives
  * [B][nlag][n][n] propagators, status (optional) [B] status bits.  method: MCD_METHOD_AUTO = SQUARING when
  * it applies to the problem and no per-profile lag times are given (componentwise accurate), else EIGEN;
  * an explicit MCD_METHOD_EIGEN is the independent cross-check of the squaring engine.

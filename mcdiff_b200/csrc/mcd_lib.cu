@@ -70,6 +70,14 @@ mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
   ch.run(mp, io, (long long)blockIdx.x, nsteps, slots);
 }
 
+// Per-profile lag times handed to a squaring engine must be the problem's lag times plus one offset (the
+// time-offset trial of lib/MCState.py:207-210): only that form has a LagPlan (plan[1]).  Thread 0, inside ex.single.
+__device__ __forceinline__ void check_shifted_lags(const Problem& P, const double* lag, Scalars* sc) {
+  const double shift = lag[0] - P.lagtimes[0];
+  for (int l = 1; l < P.nlag; ++l)
+    if (!(fabs((lag[l] - P.lagtimes[l]) - shift) <= 1e-9 * fabs(P.lagtimes[l]))) sc->status |= MCD_ST_BAD_LAGS;
+}
+
 template <bool kSmemMat>
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, const double* __restrict__ w,
@@ -98,10 +106,18 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
     });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = (kSmemMat && method >= MCD_METHOD_SQUARING)
-                          ? ch.evaluate_sq(s.v, s.w, s.lag, P.plan[0], slots + (size_t)blockIdx.x * P.plan[0].nslots * P.np * P.ld,
-                                           0, method == MCD_METHOD_SQUARING, Pb, &sw)
-                                                                  : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    double ll;
+    if (kSmemMat && method >= MCD_METHOD_SQUARING) {
+      const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
+      const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+      if (lagtimes) ex.single([&]() { check_shifted_lags(P, s.lag, s.sc); });
+      ll = (s.sc->status & MCD_ST_BAD_LAGS)
+               ? nan("")
+               : ch.evaluate_sq(s.v, s.w, s.lag, pl, slots + (size_t)blockIdx.x * nsl * P.np * P.ld, 0,
+                                method == MCD_METHOD_SQUARING, Pb, &sw);
+    } else {
+      ll = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    }
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -125,7 +141,8 @@ mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
 
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
-                       double* __restrict__ out_ll, double* __restrict__ out_P, int* __restrict__ status, double* gws) {
+                       const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
+                       int* __restrict__ status, double* gws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
@@ -133,19 +150,22 @@ mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const dou
   Chain<DeviceExec, 1> ch(ex, P, s);
   ch.build_tables();
   const int n = P.n, np = P.np, dim_w = P.dim_w;
-  double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, P.plan[0].nslots);
+  const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
+  const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+  double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, nsl);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     ex.par([&](int tid) {
       for (int i = tid; i < np; i += kThreads) {
         s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
         s.w[i] = (i < dim_w) ? w[(size_t)b * dim_w + i] : 0.0;
       }
-      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = P.lagtimes[l];
+      for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       if (tid == 0) s.sc->status = 0;
     });
+    if (lagtimes) ex.single([&]() { check_shifted_lags(P, s.lag, s.sc); });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
-    const double ll = ch.evaluate_blk(s.v, s.w, s.lag, P.plan[0], ws, 0, Pb, &sw);
+    const double ll = (s.sc->status & MCD_ST_BAD_LAGS) ? nan("") : ch.evaluate_blk(s.v, s.w, s.lag, pl, ws, 0, Pb, &sw);
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
@@ -192,13 +212,7 @@ mcd_loglike_gen_kernel(Problem P, int B, const double* __restrict__ v, const dou
       for (int l = tid; l < P.nlag; l += kThreads) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       if (tid == 0) s.sc->status = 0;
     });
-    ex.single([&]() {
-      if (lagtimes) {
-        const double shift = s.lag[0] - P.lagtimes[0];
-        for (int l = 1; l < P.nlag; ++l)
-          if (!(fabs((s.lag[l] - P.lagtimes[l]) - shift) <= 1e-9 * fabs(P.lagtimes[l]))) s.sc->status |= MCD_ST_BAD_LAGS;
-      }
-    });
+    if (lagtimes) ex.single([&]() { check_shifted_lags(P, s.lag, s.sc); });
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * n * n : nullptr;
     const double ll = (s.sc->status & MCD_ST_BAD_LAGS) ? nan("") : ch.evaluate_gen(s.v, s.w, s.lag, pl, slots, 0, Pb, &sw);
@@ -431,7 +445,7 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   if (method == MCD_METHOD_AUTO)
     method = (p->squaring_ok && (!lagtimes || p->P.use_pull)) ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (method < MCD_METHOD_EIGEN || method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
-  if (method >= MCD_METHOD_SQUARING && (!p->squaring_ok || (lagtimes && !p->P.use_pull))) return MCD_E_UNSUPPORTED;
+  if (method >= MCD_METHOD_SQUARING && !p->squaring_ok) return MCD_E_UNSUPPORTED;
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -450,15 +464,18 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   } else if (p->blocked && method >= MCD_METHOD_SQUARING) {
     if (method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
-    int rc = ensure_gws(h, (size_t)grid * blocked_ws_doubles(P, P.plan[0].nslots) * sizeof(double));
+    const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+    int rc = ensure_gws(h, (size_t)grid * blocked_ws_doubles(P, nsl) * sizeof(double));
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->blk_smem_bytes));
-    mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, out_ll, out_P, status, h->gws);
+    mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
+                                                                      h->gws);
   } else if (p->in_smem) {
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
-    if (method >= MCD_METHOD_SQUARING && P.plan[0].nslots > 0) {
-      int rc = ensure_gws(h, (size_t)grid * P.plan[0].nslots * P.np * P.ld * sizeof(double));
+    const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+    if (method >= MCD_METHOD_SQUARING && nsl > 0) {
+      int rc = ensure_gws(h, (size_t)grid * nsl * P.np * P.ld * sizeof(double));
       if (rc != MCD_OK) return rc;
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

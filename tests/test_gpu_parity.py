@@ -685,3 +685,29 @@ def test_blocked_engine_three_blocks_mc(engine):
         assert np.array_equal(dec[c] & 1, out["accepted"]), "chain %d" % c
         assert np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
         np.testing.assert_allclose(st["scal"][c][0], out["ll"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("n", [100, 200])
+def test_time_offset_through_the_likelihood_seam_on_squaring_engines(engine, n):
+    """mcd_loglike_batch with explicit SQUARING and per-profile lag times = lag times + offset (the time-offset
+    trial of lib/MCState.py:207-210) on the shared-memory and the blocked engine; other lag times are flagged."""
+    from mcdiff_b200.engine import DeviceProblem
+    from oracle import mcdiff_oracle as O
+    lags = np.array([5.0, 10.0, 15.0])
+    counts, _, _, F, w_true = O.synthetic_counts(n=n, lags=lags, seed=3, total=2.0e5)
+    prob = DeviceProblem(engine, counts, lags, True)
+    rng = np.random.default_rng(n)
+    v = F[None, :] + rng.normal(0, 0.2, (2, n))
+    w = w_true[None, :] + rng.normal(0, 0.2, (2, n))
+    lt = np.stack([lags + 0.41, lags - 0.9])
+    ll, _, st = prob.loglike(v, w, lagtimes=lt, method=METHODS["squaring"])
+    assert not st.any()
+    for b in range(2):
+        np.testing.assert_allclose(ll[b], O.log_like_lag(v[b], w[b], lt[b], counts, True), rtol=1e-12)
+    bad = lt.copy()
+    bad[0, 1] *= 1.01
+    ll, _, st = prob.loglike(v, w, lagtimes=bad, method=METHODS["squaring"])
+    assert st[0] == 4 and st[1] == 0 and np.isnan(ll[0]) and np.isfinite(ll[1])
+    ll_e, _, st = prob.loglike(v, w, lagtimes=bad)          # AUTO: eigen engine, any lag times
+    assert not st.any()
+    np.testing.assert_allclose(ll_e[0], O.log_like_lag(v[0], w[0], bad[0], counts, True), rtol=RTOL)
