@@ -711,3 +711,17 @@ def test_time_offset_through_the_likelihood_seam_on_squaring_engines(engine, n):
     ll_e, _, st = prob.loglike(v, w, lagtimes=bad)          # AUTO: eigen engine, any lag times
     assert not st.any()
     np.testing.assert_allclose(ll_e[0], O.log_like_lag(v[0], w[0], bad[0], counts, True), rtol=RTOL)
+
+
+def test_randomised_configurations(engine, capsys):
+    """profiles/fuzz_parity.py: random size / lag set / boundary / model / spring / time offset / pull, batched
+    likelihood + propagator against the oracle and a short device-Philox run against the oracle replay."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "profiles", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    failures = mod.run(16, 20241021, eng=engine)
+    out = capsys.readouterr().out
+    assert failures == 0, out
