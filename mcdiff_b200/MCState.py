@@ -171,14 +171,13 @@ class MCState:
             wrad = np.tile(m.wrad, (self.nchains, 1))
             wc = np.tile(m.wrad_coeff, (self.nchains, 1)) if ncos > 0 else None
             if self.jitter > 0:
-                rng = np.random.default_rng(self.seed ^ 0x5DEECE66D)
-                skip = 1 if self.rank == 0 else 0
                 if ncos > 0:
-                    wc[skip:] += self.jitter * rng.standard_normal(wc[skip:].shape)
+                    wc += self._jitter_rows(2, ncos)
                     wrad = wc @ m.wrad_basis.T
                 else:
-                    wrad[skip:] += self.jitter * rng.standard_normal(wrad[skip:].shape)
+                    wrad += self._jitter_rows(2, wrad.shape[1])
             self.chains.set_state(wrad, wc, dwrad=self.dwrad, temp=self.temp)
+            self._apply_resume()
             return
         svecs = _string_vecs(m.dim_w, self.pbc) if self.k > 0 else None
         self.string_vecs = svecs
@@ -194,28 +193,92 @@ class MCState:
         w = np.tile(m.w, (self.nchains, 1))
         vc = np.tile(m.v_coeff, (self.nchains, 1)) if m.ncosF > 0 else None
         wc = np.tile(m.w_coeff, (self.nchains, 1)) if m.ncosD > 0 else None
-        if self.jitter > 0:     # optional over-dispersed starts; chain 0 of rank 0 keeps the exact start
-            rng = np.random.default_rng(self.seed ^ 0x5DEECE66D)
-            skip = 1 if self.rank == 0 else 0
+        if self.jitter > 0:     # optional over-dispersed starts; global chain 0 keeps the exact start
             if m.ncosF > 0:
-                vc[skip:, 1:] += self.jitter * rng.standard_normal(vc[skip:, 1:].shape)
+                vc[:, 1:] += self._jitter_rows(0, m.ncosF)[:, 1:]
                 v = vc @ m.v_basis.T
             else:
-                v[skip:] += self.jitter * rng.standard_normal(v[skip:].shape)
+                v += self._jitter_rows(0, v.shape[1])
             if m.ncosD > 0:
-                wc[skip:] += self.jitter * rng.standard_normal(wc[skip:].shape)
+                wc += self._jitter_rows(1, m.ncosD)
                 w = wc @ m.w_basis.T
             else:
-                w[skip:] += self.jitter * rng.standard_normal(w[skip:].shape)
+                w += self._jitter_rows(1, w.shape[1])
         self.chains.set_state(v, w, vc, wc, dv=self.dv, dw=self.dw, dtimezero=self.dtimezero, temp=self.temp,
                               timezero=m.timezero)
+        self._apply_resume()
+
+    def _jitter_rows(self, stream, width):
+        """Gaussian start offsets of the local chains, [nchains][width].  Row c depends only on (seed, stream,
+        GLOBAL chain index): every rank draws different rows and a run does not depend on the number of GPUs.
+        Global chain 0 gets zeros (it keeps the exact start of the reference's single chain)."""
+        out = np.zeros((self.nchains, width))
+        for c in range(self.nchains):
+            g = self.chain_lo + c
+            if g == 0:
+                continue
+            rng = np.random.default_rng([self.seed & 0xFFFFFFFFFFFFFFFF, 0x5DEECE66D, int(stream), int(g)])
+            out[c] = self.jitter * rng.standard_normal(width)
+        return out
+
+    # ---- exact resume: <outfile>.chains.npz of an earlier run (SURVEY.md 5) ----------------------
+    def use_chainfile(self, filename):
+        """Continue every chain from the state an earlier run left in `<outfile>.chains.npz`: profiles,
+        coefficients, step widths, temperature, log-likelihood, acceptance counters and the step counter
+        (= Philox counter; the streams are keyed by (seed, global chain index, step), so with the same --seed the
+        continued run draws exactly the numbers the uninterrupted run would have drawn)."""
+        z = np.load(filename)
+        if int(z["scal"].shape[0]) != self.nchains_total:
+            raise ValueError("%s holds %d chains, this run has %d" % (filename, z["scal"].shape[0], self.nchains_total))
+        if bool(int(z["radial"])) != bool(self.do_radial):
+            raise ValueError("%s is a %s run" % (filename, "radial" if int(z["radial"]) else "1-D"))
+        self._resume = {k: z[k] for k in z.files}
+        self.seed = int(z["seed"])
+        self.steps_done = int(z["steps_done"])
+
+    def _apply_resume(self):
+        z = getattr(self, "_resume", None)
+        if z is None:
+            return
+        import torch
+        lo, hi = self.chain_lo, self.chain_hi
+        ch, eng = self.chains, self.engine
+        f64, i64 = torch.float64, torch.int64
+
+        def put(dst, a, dtype):
+            a = np.ascontiguousarray(a[lo:hi])
+            if a.shape != tuple(dst.shape):
+                raise ValueError("chain file does not match this model: %s vs %s" % (a.shape, tuple(dst.shape)))
+            dst.copy_(eng.to_device(a, dtype))
+
+        with torch.cuda.device(eng.device):
+            put(ch.scal, z["scal"], f64)
+            put(ch.counters, z["counters"], i64)
+            if self.do_radial:
+                put(ch.wrad, z["wrad"], f64)
+                if ch.ncos > 0:
+                    put(ch.wcoef, z["wrad_coeff"], f64)
+                    put(ch.nacc_coeff, z["naccwrad_coeff"], i64)
+            else:
+                put(ch.v, z["v"], f64)
+                put(ch.w, z["w"], f64)
+                if self.model.ncosF > 0:
+                    put(ch.vcoef, z["v_coeff"], f64)
+                    put(ch.naccv_coeff, z["naccv_coeff"], i64)
+                if self.model.ncosD > 0:
+                    put(ch.wcoef, z["w_coeff"], f64)
+                    put(ch.naccw_coeff, z["naccw_coeff"], i64)
 
     # ---- lib/MCState.py:101-137 ----------------------------------------------------------------
     def init_log_like(self):
         self._ensure_device()
+        keep = self.chains.scal[:, 0].clone() if getattr(self, "_resume", None) is not None else None
         ll = self.chains.init_log_like()          # raises ValueError("Initial likelihood diverges") on NaN
+        if keep is not None:                      # resumed run: the running value of the chain, not a recomputation
+            self.chains.scal[:, 0] = keep
+            ll = keep.cpu().numpy()
         self.chain_log_like = ll
-        self.log_like = float(ll[0])
+        self.log_like = float(ll[0]) if len(ll) else float("nan")   # a rank may own no chain (world > nchains)
         print("initial log-likelihood:", self.log_like)
         m = self.model
         if m.ncosF > 0:
@@ -263,13 +326,17 @@ class MCState:
 
     def sync_from_device(self):
         st = self.chains.host_state()
+        self.chain_scal, self.chain_counters = st["scal"], st["counters"]
         if self.do_radial:
             m = self.model
             sc, ct = st["scal"], st["counters"]
+            self.chain_naccwrad_coeff = st["nacc_coeff"]
             self.chain_wrad, self.chain_wrad_coeff = st["wrad"], st["wcoef"]
             self.chain_log_like = sc[:, 0].copy()
             self.chain_dwrad, self.chain_temp = sc[:, 1].copy(), sc[:, 2].copy()
             self.chain_naccwrad, self.chain_status = ct[:, 0].copy(), ct[:, 3].copy()
+            if self.nchains == 0:
+                return
             m.wrad = st["wrad"][0].copy()
             if getattr(m, "ncosDrad", 0) > 0:
                 m.wrad_coeff = st["wcoef"][0].copy()
@@ -289,6 +356,8 @@ class MCState:
         self.chain_nacctimezero = ct[:, K.C_NACCT0].copy()
         self.chain_status = ct[:, K.C_STATUS].copy()
         self.chain_naccv_coeff, self.chain_naccw_coeff = st["naccv_coeff"], st["naccw_coeff"]
+        if self.nchains == 0:
+            return
         # chain 0 -> the reference's scalar attributes
         m = self.model
         m.v, m.w = st["v"][0].copy(), st["w"][0].copy()
@@ -349,13 +418,21 @@ class MCState:
             for i, val in enumerate(self.naccwrad_coeff):
                 print("%8d %8d %5.1f %s %5.1f %s" % (i, val, float(val) / tot * 100, "%",
                                                     float(val) / self.nmc * 100, "%"), file=f)
-        if self.nchains > 1:
-            acc = ((self.chain_naccwrad if self.do_radial else self.chain_naccv + self.chain_naccw)
-                   / float(max(1, self.nmc)))
-            print("===== Statistics over %d chains =====" % self.nchains, file=f)
+        if self.nchains_total > 1:
+            g = getattr(self, "global_summary", None)
+            if g is not None:        # after the gather: every chain of every rank
+                acc, ll = g["acc"], g["log_like"]
+            else:
+                acc = ((self.chain_naccwrad if self.do_radial else self.chain_naccv + self.chain_naccw)
+                       / float(max(1, self.nmc)))
+                ll = self.chain_log_like
+            print("===== Statistics over %d chains =====" % len(ll), file=f)
             print("acceptance mean/min/max %6.3f %6.3f %6.3f" % (acc.mean(), acc.min(), acc.max()), file=f)
-            print("log-like   mean/min/max", self.chain_log_like.mean(), self.chain_log_like.min(),
-                  self.chain_log_like.max(), file=f)
+            print("log-like   mean/min/max", ll.mean(), ll.min(), ll.max(), file=f)
+
+    def set_global_summary(self, log_like, acc):
+        """Per-chain log-likelihood and acceptance ratio of ALL chains (after the final all_gather)."""
+        self.global_summary = dict(log_like=np.asarray(log_like), acc=np.asarray(acc))
 
     def print_coeffs_laststate(self, f, final=False):
         from .log import print_coeffs

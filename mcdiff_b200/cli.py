@@ -55,6 +55,9 @@ def build_parser():
     p.add_option("--method", dest="method", default="auto", help="propagator engine: auto | eigen | squaring")
     p.add_option("--jitter", dest="jitter", default=0.0, type="float",
                  help="Gaussian spread of the starting parameters of chains 1.. (0: all start alike)")
+    p.add_option("--resume", dest="resume", default=None, metavar="FILE",
+                 help="continue every chain exactly from FILE = <outfile>.chains.npz of an earlier run "
+                      "(same files, model, --nchains; the seed and step counters are taken from FILE)")
     return p
 
 
@@ -82,4 +85,4 @@ def main(argv=None):
                     options.seed, options.outfile, options.ncosF, options.ncosD, options.ncosDrad,
                     options.move_timezero, options.initfile, options.k, options.lmax, options.reduction,
                     options.pull, nchains=options.nchains, device=options.device, method=options.method,
-                    jitter=options.jitter)
+                    jitter=options.jitter, resume=options.resume)

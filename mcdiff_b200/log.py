@@ -104,6 +104,37 @@ class Logger:
     def chain_rows(self, chain):
         return slice(chain * self.nf_chain, (chain + 1) * self.nf_chain)
 
+    # ---- pooling over ranks: every stored quantity of the local chains as one [nchains][nf_chain * K] block ----
+    _SCALARS = ("log_like", "timezero", "dv", "dw", "dwrad", "dtimezero", "temp")
+    _VECTORS = ("v", "v_coeff", "w", "w_coeff", "wrad", "wrad_coeff")
+
+    def pack_rows(self):
+        """All rows of the local chains, chain-major: [nchains][nf_chain * K].  Column order: the scalars of
+        `_SCALARS`, then every sampled vector this Logger holds (order of `_VECTORS`)."""
+        cols = [getattr(self, k).reshape(self.nchains, self.nf_chain, 1) for k in self._SCALARS]
+        for k in self._VECTORS:
+            if hasattr(self, k):
+                a = getattr(self, k)
+                cols.append(a.reshape(self.nchains, self.nf_chain, a.shape[1]))
+        width = sum(c.shape[2] for c in cols)
+        return np.ascontiguousarray(np.concatenate(cols, axis=2).reshape(self.nchains, self.nf_chain * width))
+
+    def unpack_rows(self, rows):
+        """Inverse of pack_rows for a Logger sized for rows.shape[0] chains (global chain order)."""
+        rows = np.asarray(rows, dtype=np.float64)
+        rows = rows.reshape(self.nchains, self.nf_chain, rows.shape[1] // self.nf_chain)
+        c = 0
+        for k in self._SCALARS:
+            getattr(self, k)[:] = rows[:, :, c].reshape(-1)
+            c += 1
+        for k in self._VECTORS:
+            if hasattr(self, k):
+                a = getattr(self, k)
+                a[:] = rows[:, :, c:c + a.shape[1]].reshape(a.shape)
+                c += a.shape[1]
+        if c != rows.shape[2]:
+            raise ValueError("row width %d does not match this Logger (%d)" % (rows.shape[2], c))
+
     # ---- pickling (lib/log.py:68-71, 279-284) ---------------------------------------------
     def dump(self, filename):
         with open(filename, "wb") as f:

@@ -8,9 +8,14 @@
 Output files (formats of lib/log.py:288-376, consumed by outreading / plotresults /
 mcdiff-infty / --initf):
     <outfile>               final state of chain 0 (the reference's single-chain file)
-    <outfile>.pic           pickled Logger with the samples of ALL chains pooled
+    <outfile>.pic           pickled Logger with the samples of ALL chains of ALL ranks pooled (global chain order)
     <outfile>.pic.ave.dat   pooled posterior mean and standard deviation
-    <outfile>.chains.npz    final state, log-likelihood and acceptance counters of every chain
+    <outfile>.chains.npz    final state, log-likelihood, acceptance and step counters of every chain
+                            (`--resume` continues every chain exactly from it)
+
+Under torchrun the chains shard over the ranks (parallel.shard_range); nothing is exchanged while sampling.
+Afterwards two collectives run: an all_gather of the per-chain state/acceptance rows and a gather of the Logger
+rows on rank 0, which writes the files -- so 1 GPU and N GPUs with the same --nchains give identical files.
 """
 from __future__ import annotations
 
@@ -20,7 +25,7 @@ import numpy as np
 
 from .MCState import MCState
 from .log import Logger, write_average_from_pic
-from .parallel import all_gather_rows, dist_info
+from .parallel import all_gather_rows, dist_info, gather_rows_to_root
 from .transitions import RadTransitions, Transitions
 
 
@@ -61,13 +66,22 @@ def do_mc_cycles(MC, logger, chunk=1000):
     logger.dwrad[:] = MC.dwrad
 
 
-def _finish_radial(MC, logger, outfile, nmc, rank):
-    local = np.concatenate([MC.chain_log_like[:, None], MC.chain_dwrad[:, None],
-                            MC.chain_naccwrad[:, None].astype(float), MC.chain_status[:, None].astype(float),
-                            MC.chain_wrad], axis=1)
-    allrows = all_gather_rows(local, MC.nchains_total)
+def _pool_logger(MC, logger, rank):
+    """Rows of every chain of every rank -> one Logger on rank 0 (global chain order), so that `.pic` and
+    `.pic.ave.dat` are the pooled posterior of ALL chains whatever the number of GPUs
+    (lib/log.py:90-106, lib/outreading.py:281-301 take their statistics over the rows of this object)."""
+    rows = gather_rows_to_root(logger.pack_rows(), MC.nchains_total)
     if rank != 0:
-        return MC, logger
+        return None
+    if MC.nchains_total == logger.nchains:
+        return logger
+    pooled = Logger(MC, nchains=MC.nchains_total)
+    pooled.unpack_rows(rows)
+    return pooled
+
+
+def _write_outputs(MC, pooled, outfile):
+    """Rank 0: the reference's result file for chain 0, the pickled pooled Logger and its average."""
     if outfile is None:
         MC.print_statistics(f=sys.stdout)
         MC.print_laststate(sys.stdout, final=True)
@@ -77,13 +91,31 @@ def _finish_radial(MC, logger, outfile, nmc, rank):
             MC.print_statistics(f=sys.stdout)
             MC.print_laststate(f, final=True)
         picfile = outfile + ".pic"
-    logger.model = MC.model
-    logger.dump(picfile)
+    pooled.model = MC.model
+    pooled.dump(picfile)
     write_average_from_pic(picfile, picfile + ".ave.dat")
+
+
+def _finish_radial(MC, logger, outfile, nmc, rank):
+    ncos = getattr(MC.model, "ncosDrad", 0)
+    local = np.concatenate([MC.chain_scal, MC.chain_counters.astype(np.float64), MC.chain_wrad,
+                            MC.chain_wrad_coeff if ncos > 0 else np.zeros((MC.nchains, 0)),
+                            MC.chain_naccwrad_coeff.astype(np.float64) if ncos > 0 else np.zeros((MC.nchains, 0))],
+                           axis=1)
+    allrows = all_gather_rows(local, MC.nchains_total)
+    pooled = _pool_logger(MC, logger, rank)
+    MC.set_global_summary(log_like=allrows[:, 0], acc=allrows[:, 8] / float(max(1, nmc)))
+    if rank != 0:
+        return MC, logger
+    _write_outputs(MC, pooled, outfile)
+    n = MC.model.dim_wrad
     np.savez_compressed((outfile or "mc") + ".chains.npz", log_like=allrows[:, 0], dwrad=allrows[:, 1],
-                        naccwrad=allrows[:, 2], status=allrows[:, 3], wrad=allrows[:, 4:],
-                        edges=np.asarray(MC.model.edges), nmc=nmc, seed=MC.seed)
-    return MC, logger
+                        naccwrad=allrows[:, 8], status=allrows[:, 11], scal=allrows[:, :8],
+                        counters=allrows[:, 8:16].astype(np.int64), wrad=allrows[:, 16:16 + n],
+                        wrad_coeff=allrows[:, 16 + n:16 + n + ncos],
+                        naccwrad_coeff=allrows[:, 16 + n + ncos:].astype(np.int64),
+                        edges=np.asarray(MC.model.edges), nmc=nmc, seed=MC.seed, steps_done=MC.steps_done, radial=1)
+    return MC, pooled
 
 
 def _do_mc_cycles_radial(MC, logger, chunk):
@@ -111,7 +143,7 @@ def _do_mc_cycles_radial(MC, logger, chunk):
 
 def find_parameters(filenames, pbc, model, dv, dw, dwrad, D0, dtimezero, temp, temp_end, nmc, nmc_update, seed,
                     outfile, ncosF, ncosD, ncosDrad, move_timezero, initfile, k, lmax, reduction, pull,
-                    nchains=1, device=None, method="auto", jitter=0.0, chunk=1000):
+                    nchains=1, device=None, method="auto", jitter=0.0, chunk=1000, resume=None):
     print("mcdiff_b200: free energy and diffusion profiles from transition counts, many chains on B200")
     rank, world, _ = dist_info()
     MC = MCState(pbc, lmax, nchains=nchains, device=device, seed=seed, rank=rank, world=world, method=method,
@@ -123,43 +155,45 @@ def find_parameters(filenames, pbc, model, dv, dw, dwrad, D0, dtimezero, temp, t
         MC.use_initfile(initfile)
         MC.print_MC_params(sys.stdout)
         MC.print_coeffs_laststate(sys.stdout)
+    if resume is not None:
+        MC.use_chainfile(resume)
     logger = Logger(MC, nchains=MC.nchains)
     do_mc_cycles(MC, logger, chunk=chunk)
 
-    # ---- one collective: per-chain summaries of every rank (lib/mc.py has a single chain) ----
+    # ---- the collectives of the design, after sampling: per-chain state + acceptance counters
+    #      on every rank, the Logger rows of all chains on rank 0 (lib/mc.py has a single chain) ----
     m = MC.model
     if MC.do_radial:
         return _finish_radial(MC, logger, outfile, nmc, rank)
-    pv = MC.chain_v_coeff if m.ncosF > 0 else MC.chain_v
-    pw = MC.chain_w_coeff if m.ncosD > 0 else MC.chain_w
-    local = np.concatenate([MC.chain_log_like[:, None], MC.chain_dv[:, None], MC.chain_dw[:, None],
-                            MC.chain_naccv[:, None].astype(float), MC.chain_naccw[:, None].astype(float),
-                            MC.chain_nacctimezero[:, None].astype(float), MC.chain_status[:, None].astype(float),
-                            MC.chain_v, MC.chain_w, pv, pw], axis=1)
+    nF, nD = max(m.ncosF, 0), max(m.ncosD, 0)
+    zc = np.zeros((MC.nchains, 0))
+    local = np.concatenate([MC.chain_scal, MC.chain_counters.astype(np.float64), MC.chain_v, MC.chain_w,
+                            MC.chain_v_coeff if nF > 0 else zc, MC.chain_w_coeff if nD > 0 else zc,
+                            MC.chain_naccv_coeff.astype(np.float64) if nF > 0 else zc,
+                            MC.chain_naccw_coeff.astype(np.float64) if nD > 0 else zc], axis=1)
     allrows = all_gather_rows(local, MC.nchains_total)
+    pooled = _pool_logger(MC, logger, rank)
+    from . import _capi as K
+    MC.set_global_summary(log_like=allrows[:, K.S_LL],
+                          acc=(allrows[:, 8 + K.C_NACCV] + allrows[:, 8 + K.C_NACCW]) / float(max(1, nmc)))
     if rank != 0:
         return MC, logger
-
-    def write_final(f):
-        MC.print_statistics(f=sys.stdout)
-        MC.print_laststate(f, final=True)
-
-    if outfile is None:
-        write_final(sys.stdout)
-        picfile = "mc.pic"
-    else:
-        with open(outfile, "w") as f:
-            write_final(f)
-        picfile = outfile + ".pic"
-    logger.model = MC.model
-    logger.dump(picfile)
-    write_average_from_pic(picfile, picfile + ".ave.dat")
+    _write_outputs(MC, pooled, outfile)
     nv, nw = m.dim_v, m.dim_w
+    o = 16
+    v, w = allrows[:, o:o + nv], allrows[:, o + nv:o + nv + nw]
+    o += nv + nw
+    vc, wc = allrows[:, o:o + nF], allrows[:, o + nF:o + nF + nD]
+    o += nF + nD
     np.savez_compressed((outfile or "mc") + ".chains.npz",
-                        log_like=allrows[:, 0], dv=allrows[:, 1], dw=allrows[:, 2], naccv=allrows[:, 3],
-                        naccw=allrows[:, 4], nacctimezero=allrows[:, 5], status=allrows[:, 6],
-                        v=allrows[:, 7:7 + nv], w=allrows[:, 7 + nv:7 + nv + nw],
-                        v_param=allrows[:, 7 + nv + nw:7 + nv + nw + pv.shape[1]],
-                        w_param=allrows[:, 7 + nv + nw + pv.shape[1]:], edges=np.asarray(m.edges), nmc=nmc,
-                        seed=MC.seed)
-    return MC, logger
+                        log_like=allrows[:, K.S_LL], dv=allrows[:, K.S_DV], dw=allrows[:, K.S_DW],
+                        naccv=allrows[:, 8 + K.C_NACCV], naccw=allrows[:, 8 + K.C_NACCW],
+                        nacctimezero=allrows[:, 8 + K.C_NACCT0], status=allrows[:, 8 + K.C_STATUS],
+                        v=v, w=w, v_param=vc if nF > 0 else v, w_param=wc if nD > 0 else w,
+                        # exact resume: the whole per-chain state; the Philox counter of a chain is
+                        # (step, global chain index), so `counters[:, C_STEP]` + `seed` continue every stream
+                        scal=allrows[:, :8], counters=allrows[:, 8:16].astype(np.int64), v_coeff=vc, w_coeff=wc,
+                        naccv_coeff=allrows[:, o:o + nF].astype(np.int64),
+                        naccw_coeff=allrows[:, o + nF:o + nF + nD].astype(np.int64),
+                        edges=np.asarray(m.edges), nmc=nmc, seed=MC.seed, steps_done=MC.steps_done, radial=0)
+    return MC, pooled

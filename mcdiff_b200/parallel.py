@@ -53,6 +53,36 @@ def all_gather_rows(local_rows: np.ndarray, nchains_total: int, device=None) -> 
     return np.concatenate([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], axis=0)
 
 
+def gather_rows_to_root(local_rows: np.ndarray, nchains_total: int, device=None, chunk_bytes: int = 256 << 20):
+    """Gather per-chain rows [n_local][k] of every rank on rank 0 only ([nchains_total][k], global chain
+    order; other ranks get None).  Used for the Logger rows (every stored sample of every chain), which can be
+    large: the columns travel in chunks of at most `chunk_bytes` per rank so that the staging buffers stay small."""
+    import torch
+    import torch.distributed as dist
+    rank, world, on = dist_info()
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
+    if not on or world == 1:
+        return local_rows
+    k = local_rows.shape[1]
+    sizes = [shard_range(nchains_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    out = np.empty((nchains_total, k)) if rank == 0 else None
+    step = max(1, int(chunk_bytes // (8 * max(1, width))))
+    for c0 in range(0, k, step):
+        c1 = min(k, c0 + step)
+        buf = torch.zeros((width, c1 - c0), dtype=torch.float64, device=device)
+        if local_rows.shape[0] > 0:
+            buf[: local_rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_rows[:, c0:c1])).to(device)
+        parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, parts, dst=0)
+        if rank == 0:
+            for r, (lo, hi) in enumerate(sizes):
+                out[lo:hi, c0:c1] = parts[r][: hi - lo].cpu().numpy()
+    return out
+
+
 def reduce_max(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist

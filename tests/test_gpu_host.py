@@ -80,6 +80,28 @@ def test_find_parameters_outputs_and_restart(engine, gold_ll, tmp_path, capsys):
     assert ll_init == pytest.approx(ref["ll"], rel=2e-7)      # coefficients are stored with 9 digits
 
 
+def test_exact_resume_from_chainfile(engine, gold_ll, tmp_path, capsys):
+    """<outfile>.chains.npz holds the whole per-chain state and the Philox counters, so
+    200 steps == 100 steps + `--resume` + 100 steps, bit for bit, for every chain."""
+    from mcdiff_b200.mc import find_parameters
+    G = gold_ll
+    tmp = str(tmp_path)
+    files = _files(tmp, G)
+    args = (files, True, "CosinusModel", 0.05, 0.05, 0.5, 1.0, 0.1, 1.0, 1.0)
+    tail = (50.0, 9)
+    kw = dict(nchains=5)
+    full, a, b = (os.path.join(tmp, x) for x in ("full.dat", "a.dat", "b.dat"))
+    find_parameters(*args, 200, *tail, full, 10, 6, 0, False, None, -1, -1, False, None, **kw)
+    find_parameters(*args, 100, *tail, a, 10, 6, 0, False, None, -1, -1, False, None, **kw)
+    find_parameters(*args, 100, 50.0, 1234, b, 10, 6, 0, False, None, -1, -1, False, None, resume=a + ".chains.npz", **kw)
+    capsys.readouterr()
+    zf, zb = np.load(full + ".chains.npz"), np.load(b + ".chains.npz")
+    for key in ("scal", "counters", "v", "w", "v_coeff", "w_coeff", "naccv_coeff", "naccw_coeff"):
+        np.testing.assert_array_equal(zf[key], zb[key], err_msg=key)
+    assert int(zb["steps_done"]) == 200 and int(zb["seed"]) == 9
+    assert open(full).read() == open(b).read()
+
+
 def test_per_bin_model_and_nopbc(engine, gold_ll, tmp_path, capsys):
     from mcdiff_b200 import outreading as outr
     from mcdiff_b200.mc import find_parameters

@@ -42,6 +42,12 @@ def test_two_ranks_equal_one_rank(engine, gold_ll, tmp_path):
     for key in ("log_like", "naccv", "naccw", "v_param", "w_param", "dv", "dw"):
         np.testing.assert_array_equal(a[key], b[key])
     assert open(out1).read() == open(out2).read()          # chain 0 file identical
+    # pooled posterior: rank 0 holds the Logger rows of ALL chains of both ranks (global chain order)
+    assert open(out1 + ".pic.ave.dat").read() == open(out2 + ".pic.ave.dat").read()
+    from mcdiff_b200.log import load_logger
+    l1, l2 = load_logger(out1 + ".pic"), load_logger(out2 + ".pic")
+    assert l1.nchains == l2.nchains == 7 and l2.nf == 7 * 3
+    np.testing.assert_array_equal(l1.pack_rows(), l2.pack_rows())
 
 
 @pytest.mark.parametrize("mode", ["pull", "radial", "blocked"])
@@ -97,3 +103,4 @@ def test_two_ranks_equal_one_rank_other_paths(engine, gold_ll, tmp_path, mode):
     for key in keys:
         np.testing.assert_array_equal(a[key], b[key])
     assert open(out1).read() == open(out2).read()
+    assert open(out1 + ".pic.ave.dat").read() == open(out2 + ".pic.ave.dat").read()
