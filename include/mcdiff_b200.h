@@ -19,8 +19,11 @@
  *   - every array argument is a DEVICE pointer owned by the caller (row-major, contiguous)
  *     unless the name ends in _host.  The library keeps private copies of the problem
  *     description (mcd_problem) and never frees caller memory.
- *   - all calls are asynchronous on the cudaStream_t passed as `stream` (0 = default
- *     stream); the caller synchronises.  One handle per device per host thread.
+ *   - all compute calls are asynchronous on the cudaStream_t passed as `stream` (0 = default
+ *     stream) and never synchronise; the caller synchronises.  Per-call scratch memory is a stream-ordered
+ *     allocation (cudaMallocAsync / cudaFreeAsync on `stream`), so calls on different streams that share a
+ *     handle or a problem do not interfere.  The *_create calls synchronise `stream` once.
+ *     One handle per device; a handle is not thread-safe (it counts launches), problems are read-only.
  *   - counts[l][i][j] = number of observed transitions j -> i at lag l   (lib/tools/extract.py:86-87)
  *     w[i] lives between bin i and i+1 (pbc: w[n-1] couples bin n-1 and bin 0)  (lib/utils.py:96-97)
  */
@@ -34,19 +37,21 @@
 extern "C" {
 #endif
 
-#define MCD_VERSION 100
+#define MCD_VERSION 200
 
 enum {
   MCD_OK = 0,
   MCD_E_ARG = -1,        /* bad argument (null pointer, size out of range) */
-  MCD_E_UNSUPPORTED = -2,/* e.g. --pull (non-symmetrisable generator), n too large */
+  MCD_E_UNSUPPORTED = -2,/* e.g. n > 508, --pull without pbc or with n > 104, an engine that does not apply */
   MCD_E_NOMEM = -3,
   MCD_E_NODEVICE = -4
 };
 
 /* per-profile / per-chain status bits */
 enum {
-  MCD_ST_EIG_NOCONV = 1, /* in-kernel eigensolver did not converge (non-finite input) */
+  MCD_ST_NONFINITE = 1,  /* the propagator engine rejected the profile: non-finite v / w (eigensolver did not
+                            converge; squaring engines: lag * ||S|| non-finite or > 1e9); log L is NaN */
+  MCD_ST_EIG_NOCONV = 1, /* (older name of the same bit) */
   MCD_ST_NAN_TRIAL = 2,  /* a trial log-likelihood was NaN; the move was skipped like
                             lib/MCState.py:251 does */
   MCD_ST_BAD_LAGS = 4    /* mcd_loglike_batch on a squaring engine: per-profile lag times that are not the
@@ -141,7 +146,8 @@ int mcd_create(int device, mcd_handle** out);
 int mcd_destroy(mcd_handle* h);
 
 /* Copies the description into library-owned device memory (counts are re-packed to a padded
- * int32 layout).  `--pull` is not representable (non-symmetrisable): use the host reference. */
+ * int32 layout, N + N^T and the row/column sums are formed once).  Synchronises `stream` once (the lag
+ * times are read back to build the LagPlans).  desc->use_pull selects the general (non-symmetric) engine. */
 int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* desc, void* stream, mcd_problem** out);
 int mcd_problem_destroy(mcd_problem* p);
 /* np: padded bin count, basis_elems: doubles per chain in mcd_chain_io.basis,
@@ -168,16 +174,44 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
 int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params, const mcd_chain_io* io,
                int32_t nchains, int32_t nsteps, void* stream);
 
-/* Radial (2-D) likelihood, lib/twod.py:13-32,89-130: for each of B radial profiles
+/* Static description of a radial (2-D) problem: what RadTransitions + RadModel + the Bessel table of
+ * MCState.set_model hold (lib/transitions.py, lib/model.py:316-365, lib/twod.py:34-63).  v and w are frozen in
+ * radial mode (lib/mc.py:29-30). */
+typedef struct {
+  int32_t n;          /* bins along z */
+  int32_t pbc;
+  int32_t nlag;       /* <= 64 */
+  int32_t dim_rad;    /* radial bins */
+  int32_t lmax;       /* Bessel terms, <= 64 */
+  int32_t ncosDrad;   /* 0: per-bin moves of wrad, >0: wrad = wrad_basis . wrad_coeff */
+  const double* v;         /* [n]                          device */
+  const double* w;         /* [dim_w]                      device */
+  const double* lagtimes;  /* [nlag]                       device */
+  const double* counts;    /* [nlag][dim_rad][n][n] double device (lib/reading.py:129) */
+  const double* bessels;   /* [lmax][dim_rad]              device (lib/twod.py:45-59) */
+  const double* b0zeros;   /* [lmax]                       device */
+  const double* wrad_basis;/* [n][ncosDrad] or NULL        device (lib/model.py:349-352) */
+  double clip;             /* 1e-32 (lib/twod.py:16-23) */
+} mcd_rad_problem_desc;
+
+typedef struct mcd_rad_problem mcd_rad_problem;
+
+/* Private device copies, the LagPlan and the pair-major copy of the counts are made once here
+ * (synchronises `stream` once).  MCD_E_UNSUPPORTED when one Bessel term does not fit in shared memory. */
+int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* desc, void* stream, mcd_rad_problem** out);
+int mcd_rad_problem_destroy(mcd_rad_problem* p);
+/* np: padded bins, sample_dim: doubles per sample row, nbatch: Bessel terms advanced in lockstep,
+ * squaring_ok: 1 when the lag set has a LagPlan (else the eigen fallback runs) */
+int mcd_rad_problem_info(const mcd_rad_problem* p, int32_t* np, int32_t* sample_dim, int32_t* nbatch,
+                         int32_t* squaring_ok);
+
+/* Radial likelihood, lib/twod.py:13-32,89-130: for each of B radial profiles wrad [B][n]
  * out_ll[b] = sum_l sum_{k,i,j} counts[l,k,i,j] log(max(P_l[k,i,j], clip)),
  * P_l[k] = sum_m bessels[m,k] expm(lag_l (R(v,w) - diag(exp(wrad_b) b0zeros[m]^2 / dim_rad^2))).
- * v [n], w [dim_w] are shared by all profiles (frozen in radial mode, lib/mc.py:29-30),
- * wrad [B][n], counts [nlag][dim_rad][n][n] (double, as lib/reading.py:129),
- * bessels [lmax][dim_rad], b0zeros [lmax]. out_P optional [B][nlag][dim_rad][n][n]. */
-int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
-                          const double* v, const double* w, const double* lagtimes, const double* counts,
-                          const double* bessels, const double* b0zeros, double clip, int32_t B,
-                          const double* wrad, double* out_ll, double* out_P, int32_t* status, void* stream);
+ * out_P optional [B][nlag][dim_rad][n][n], status optional [B].  One kernel launch, asynchronous.
+ * Replaces rad_log_like_lag, lib/twod.py:13. */
+int mcd_rad_loglike_batch(mcd_handle* h, const mcd_rad_problem* p, int32_t B, const double* wrad, double* out_ll,
+                          double* out_P, int32_t* status, void* stream);
 
 /* Radial Monte-Carlo loop (only wrad is sampled; v and w are frozen), one CTA per chain.
  * Replaces the lmax > 0 branch of do_mc_cycles (lib/mc.py:29-30) = MCState.mcmove_diffusion_radial
@@ -201,7 +235,7 @@ typedef struct {
   double* scal;            /* [C][8]  {log_like, dwrad, temp, ...} */
   int64_t* counters;       /* [C][8]  {naccwrad, naccwrad_update, step, status, ...} */
   int64_t* nacc_coeff;     /* [C][max(ncosDrad,1)] */
-  const double* wrad_basis;/* [n][ncosDrad] (lib/model.py:349-352) */
+  const double* wrad_basis;/* ignored: the problem's private copy is used */
   const double* tape_u;    /* [nsteps][5]: column 1 = delta uniform, column 2 = accept uniform */
   const int32_t* tape_idx; /* [nsteps] */
   uint8_t* decisions;      /* [C][nsteps] or NULL */
@@ -209,9 +243,7 @@ typedef struct {
   double* samples;         /* [C][nsamples_cap][3 + (ncosDrad ? ncosDrad : n)] = {log_like, dwrad, temp, wrad|coeff...} */
 } mcd_rad_chain_io;
 
-int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
-                   const double* v, const double* w, const double* lagtimes, const double* counts,
-                   const double* bessels, const double* b0zeros, double clip, const mcd_rad_mc_params* params,
+int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_params* params,
                    const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream);
 
 /* FP64 FMA micro-benchmark: fills *tflops with the measured dense DFMA rate of the device

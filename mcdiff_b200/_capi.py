@@ -15,7 +15,8 @@ MCD_NSCAL = 8
 MCD_NCOUNT = 8
 S_LL, S_T0, S_DV, S_DW, S_DT0, S_TEMP = range(6)
 C_NACCV, C_NACCW, C_NACCT0, C_NACCV_UPD, C_NACCW_UPD, C_STEP, C_STATUS, C_SWEEPS = range(8)
-ST_EIG_NOCONV, ST_NAN_TRIAL = 1, 2
+ST_NONFINITE, ST_NAN_TRIAL, ST_BAD_LAGS = 1, 2, 4
+ST_EIG_NOCONV = ST_NONFINITE
 METHOD_AUTO, METHOD_EIGEN, METHOD_SQUARING, METHOD_SQUARING_DFMA = 0, 1, 2, 3
 
 c_dp = C.c_void_p  # device (or, for the test emulator, host) pointers are passed as integers
@@ -49,6 +50,15 @@ class ChainIO(C.Structure):
     ]
 
 
+class RadProblemDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("pbc", C.c_int32), ("nlag", C.c_int32), ("dim_rad", C.c_int32), ("lmax", C.c_int32),
+        ("ncosDrad", C.c_int32),
+        ("v", c_dp), ("w", c_dp), ("lagtimes", c_dp), ("counts", c_dp), ("bessels", c_dp), ("b0zeros", c_dp),
+        ("wrad_basis", c_dp), ("clip", C.c_double),
+    ]
+
+
 class RadMcParams(C.Structure):
     _fields_ = [
         ("num_mc_update", C.c_double), ("dtemp", C.c_double), ("sample_every", C.c_int32),
@@ -68,6 +78,7 @@ class RadChainIO(C.Structure):
 EXPORTS = (
     "mcd_version", "mcd_error_string", "mcd_create", "mcd_destroy", "mcd_problem_create",
     "mcd_problem_destroy", "mcd_problem_info", "mcd_loglike_batch", "mcd_mc_run",
+    "mcd_rad_problem_create", "mcd_rad_problem_destroy", "mcd_rad_problem_info",
     "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_fp64_peak", "mcd_launch_count",
 )
 
@@ -101,17 +112,18 @@ def load():
                                       C.c_void_p]
     lib.mcd_mc_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(McParams), C.POINTER(ChainIO), C.c_int32,
                                C.c_int32, C.c_void_p]
-    lib.mcd_rad_loglike_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int32,
-                                          c_dp, c_dp, c_dp, c_dp, C.c_void_p]
-    lib.mcd_rad_mc_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.POINTER(RadMcParams),
-                                   C.POINTER(RadChainIO), C.c_int32, C.c_int32, C.c_void_p]
+    lib.mcd_rad_problem_create.argtypes = [C.c_void_p, C.POINTER(RadProblemDesc), C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mcd_rad_problem_destroy.argtypes = [C.c_void_p]
+    lib.mcd_rad_problem_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    lib.mcd_rad_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_void_p]
+    lib.mcd_rad_mc_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RadMcParams), C.POINTER(RadChainIO), C.c_int32,
+                                   C.c_int32, C.c_void_p]
     lib.mcd_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.mcd_launch_count.restype = C.c_int64
     lib.mcd_launch_count.argtypes = [C.c_void_p]
     for f in ("mcd_create", "mcd_destroy", "mcd_problem_create", "mcd_problem_destroy", "mcd_problem_info",
-              "mcd_loglike_batch", "mcd_mc_run", "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_fp64_peak"):
+              "mcd_loglike_batch", "mcd_mc_run", "mcd_rad_problem_create", "mcd_rad_problem_destroy",
+              "mcd_rad_problem_info", "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_fp64_peak"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib

@@ -121,6 +121,21 @@ MCD_HOSTDEV void plan_lags(const double* lag, int L, bool shifted, LagPlan* pl) 
   pl->ok = 1;
 }
 
+// Slots a launch must provide per chain: either plan may be walked (a chain whose time offset is non-zero uses the
+// shifted plan even when no time-offset moves are made, see Chain::run).
+MCD_HOSTDEV int plan_slots(const Problem& P) {
+  return P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+}
+
+// Lag times handed to a squaring engine must be the problem's lag times plus ONE offset (the time-offset trial of
+// lib/MCState.py:207-210): only that form has a LagPlan (plan[1]).
+MCD_HOSTDEV bool shifted_lags_ok(const Problem& P, const double* lag) {
+  const double shift = lag[0] - P.lagtimes[0];
+  for (int l = 1; l < P.nlag; ++l)
+    if (!(fabs((lag[l] - P.lagtimes[l]) - shift) <= 1e-9 * fabs(P.lagtimes[l]))) return false;
+  return true;
+}
+
 struct McParams {
   double num_mc_update;  // lib/MCState.py:382 (parsed as float by the CLI)
   double dtemp;          // lib/MCState.py:46-51
@@ -142,7 +157,9 @@ enum { S_LL = 0, S_T0, S_DV, S_DW, S_DT0, S_TEMP, S_NSCAL = 8 };
 // counters[] slots
 enum { C_NACCV = 0, C_NACCW, C_NACCT0, C_NACCV_UPD, C_NACCW_UPD, C_STEP, C_STATUS, C_SWEEPS, C_NCOUNT = 8 };
 // status bits
-enum { ST_JACOBI_NOCONV = 1, ST_NAN_TRIAL = 2 };
+// ST_NONFINITE: the propagator engine rejected the profile (eigensolver did not converge, or the squaring engines met
+// a non-finite / absurd norm lag * ||S||); ST_BAD_LAGS: see shifted_lags_ok
+enum { ST_NONFINITE = 1, ST_NAN_TRIAL = 2, ST_BAD_LAGS = 4 };
 
 struct ChainIO {
   double* v;        // [C][n]
@@ -1256,7 +1273,7 @@ struct Chain {
     }
     if (squarings_out) *squarings_out = bad ? -1 : nsq;
     if (bad) {
-      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      ex.single([&]() { s.sc->status |= ST_NONFINITE; });
       return nan("");
     }
     const double ll_total = s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
@@ -1602,7 +1619,7 @@ struct Chain {
     }
     if (squarings_out) *squarings_out = bad ? -1 : nsq;
     if (bad) {
-      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      ex.single([&]() { s.sc->status |= ST_NONFINITE; });
       return nan("");
     }
     return ex.sum([&](int tid) { return s.part[tid]; });
@@ -2008,7 +2025,7 @@ struct Chain {
     }
     if (squarings_out) *squarings_out = bad ? -1 : nsq_total;
     if (bad) {
-      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      ex.single([&]() { s.sc->status |= ST_NONFINITE; });
       return nan("");
     }
     return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
@@ -2033,7 +2050,7 @@ struct Chain {
     }
     if (sweeps_out) *sweeps_out = sw;
     if (sw < 0) {
-      ex.single([&]() { s.sc->status |= ST_JACOBI_NOCONV; });
+      ex.single([&]() { s.sc->status |= ST_NONFINITE; });
       return nan("");
     }
     return loglike(lagt, Pout);
@@ -2097,6 +2114,7 @@ struct Chain {
       have_basis = 1;
     }
     long long since_refresh = 0;
+    const bool shifted_plan = mp.move_timezero || sc->timezero != 0.0;
     MCD_CLK_BEGIN();
 
     for (int it = 0; it < nsteps; ++it) {
@@ -2220,13 +2238,15 @@ struct Chain {
         MCD_CLK(1);
         int sw = 0;
         double ll_new;
+        // plan[0] assumes t_i - t_{i-1} equals an earlier lag time, which only holds for the lag times as given:
+        // a chain that carries a time offset (from --t0 moves now, or from an earlier run / set_state) walks plan[1]
+        const LagPlan& plan = P.plan[shifted_plan ? 1 : 0];
         if constexpr (kBlocked) {
-          ll_new = evaluate_blk(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, nullptr, &sw);
+          ll_new = evaluate_blk(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
         } else if constexpr (kGeneral) {
-          ll_new = evaluate_gen(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, nullptr, &sw);
+          ll_new = evaluate_gen(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
         } else if (mp.method >= 2) {
-          ll_new = evaluate_sq(vtry, wtry, lagp, P.plan[mp.move_timezero ? 1 : 0], sq_slots, mp.taylor_m, mp.method == 2,
-                               nullptr, &sw);
+          ll_new = evaluate_sq(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, mp.method == 2, nullptr, &sw);
         } else {
           ll_new = evaluate(vtry, wtry, lagp, mode, nullptr, &sw);
           have_basis = (sw >= 0);

@@ -23,16 +23,35 @@ constexpr int kSmallBins = 56;   // 7 x 7 tiles: at most 4 symmetric warp tasks
 static_assert(sizeof(mcd_mc_params) == sizeof(McParams), "mcd_mc_params layout");
 static_assert(sizeof(mcd_chain_io) == sizeof(ChainIO), "mcd_chain_io layout");
 static_assert(MCD_NSCAL == S_NSCAL && MCD_NCOUNT == C_NCOUNT, "slot counts");
-static_assert(MCD_ST_EIG_NOCONV == ST_JACOBI_NOCONV && MCD_ST_NAN_TRIAL == ST_NAN_TRIAL, "status bits");
+static_assert((int)MCD_ST_NONFINITE == (int)ST_NONFINITE && (int)MCD_ST_NAN_TRIAL == (int)ST_NAN_TRIAL &&
+              (int)MCD_ST_BAD_LAGS == (int)ST_BAD_LAGS,
+              "status bits");
 
 struct mcd_handle {
   int device;
   int sm_count;
   int max_smem_optin;
   long long launches;
-  double* gws;       // global work matrices for problems that do not fit in shared memory
-  size_t gws_bytes;
 };
+
+// Per-call scratch (LagPlan slots, blocked-engine work matrices, eigen work matrices, radial kernels) is a
+// STREAM-ORDERED allocation: cudaMallocAsync on the caller's stream before the launch, cudaFreeAsync behind it.
+// Two calls on different streams therefore never share scratch, nothing synchronises, and the pool (release
+// threshold = unlimited, set in mcd_create) hands the same blocks back to the next call on that stream.
+struct Scratch {
+  double* p = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    st = stream;
+    if (bytes == 0) return MCD_OK;
+    cudaError_t e = cudaMallocAsync((void**)&p, bytes, stream);
+    if (e != cudaSuccess) { p = nullptr; return e == cudaErrorMemoryAllocation ? MCD_E_NOMEM : (int)e; }
+    return MCD_OK;
+  }
+  ~Scratch() { if (p) cudaFreeAsync(p, st); }
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct mcd_problem {
   mcd_handle* h;
@@ -65,17 +84,13 @@ mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
   Smem s = carve(P, mat, vec);
   DeviceExec ex(s.red);
   Chain<DeviceExec> ch(ex, P, s);
-  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-  double* slots = kSmemMat ? gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld : nullptr;
+  double* slots = kSmemMat ? gws + (size_t)blockIdx.x * plan_slots(P) * P.np * P.ld : nullptr;
   ch.run(mp, io, (long long)blockIdx.x, nsteps, slots);
 }
 
-// Per-profile lag times handed to a squaring engine must be the problem's lag times plus one offset (the
-// time-offset trial of lib/MCState.py:207-210): only that form has a LagPlan (plan[1]).  Thread 0, inside ex.single.
+// Thread 0, inside ex.single (see shifted_lags_ok).
 __device__ __forceinline__ void check_shifted_lags(const Problem& P, const double* lag, Scalars* sc) {
-  const double shift = lag[0] - P.lagtimes[0];
-  for (int l = 1; l < P.nlag; ++l)
-    if (!(fabs((lag[l] - P.lagtimes[l]) - shift) <= 1e-9 * fabs(P.lagtimes[l]))) sc->status |= MCD_ST_BAD_LAGS;
+  if (!shifted_lags_ok(P, lag)) sc->status |= MCD_ST_BAD_LAGS;
 }
 
 template <bool kSmemMat>
@@ -109,7 +124,7 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
     double ll;
     if (kSmemMat && method >= MCD_METHOD_SQUARING) {
       const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
-      const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+      const int nsl = plan_slots(P);
       if (lagtimes) ex.single([&]() { check_shifted_lags(P, s.lag, s.sc); });
       ll = (s.sc->status & MCD_ST_BAD_LAGS)
                ? nan("")
@@ -135,8 +150,7 @@ mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
   DeviceExec ex(s.red);
   Chain<DeviceExec, 1> ch(ex, P, s);
-  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * blocked_ws_doubles(P, pl.nslots));
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * blocked_ws_doubles(P, plan_slots(P)));
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -151,7 +165,7 @@ mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const dou
   ch.build_tables();
   const int n = P.n, np = P.np, dim_w = P.dim_w;
   const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
-  const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+  const int nsl = plan_slots(P);
   double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, nsl);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     ex.par([&](int tid) {
@@ -183,8 +197,7 @@ mcd_mc_run_gen_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
   DeviceExec ex(s.red);
   Chain<DeviceExec, 2> ch(ex, P, s);
-  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld);
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * plan_slots(P) * P.np * P.ld);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -201,7 +214,7 @@ mcd_loglike_gen_kernel(Problem P, int B, const double* __restrict__ v, const dou
   // per-profile lag times are accepted when they are the problem's lag times plus one offset (the time-offset
   // trial of lib/MCState.py:207-210): the LagPlan of shifted lag times then applies
   const LagPlan& pl = lagtimes ? P.plan[1] : P.plan[0];
-  const int nslots = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
+  const int nslots = plan_slots(P);
   double* slots = gws + (size_t)blockIdx.x * nslots * P.np * P.ld;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     ex.par([&](int tid) {
@@ -302,8 +315,13 @@ int mcd_create(int device, mcd_handle** out) {
   if (!h) return MCD_E_NOMEM;
   h->device = device;
   h->launches = 0;
-  h->gws = nullptr;
-  h->gws_bytes = 0;
+  {   // keep freed scratch blocks in the device's default pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   *out = h;
@@ -313,15 +331,11 @@ int mcd_create(int device, mcd_handle** out) {
 int mcd_destroy(mcd_handle* h) {
   if (!h) return MCD_OK;
   cudaSetDevice(h->device);
-  if (h->gws) cudaFree(h->gws);
   delete h;
   return MCD_OK;
 }
 
 int64_t mcd_launch_count(const mcd_handle* h) { return h ? h->launches : 0; }
-
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 
 int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, mcd_problem** out) {
   if (!h || !d || !out) return MCD_E_ARG;
@@ -387,8 +401,9 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   p->in_smem = (full <= (size_t)h->max_smem_optin && ntiles <= kThreads) ? 1 : 0;
   {
     double hl[kMaxLag];
-    CUDA_TRY(cudaMemcpyAsync(hl, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    e = cudaMemcpyAsync(hl, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
     plan_lags(hl, d->nlag, false, &P.plan[0]);
     plan_lags(hl, d->nlag, true, &P.plan[1]);
     p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np, true);
@@ -429,15 +444,6 @@ int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, in
   return MCD_OK;
 }
 
-static int ensure_gws(mcd_handle* h, size_t bytes) {
-  if (h->gws_bytes >= bytes) return MCD_OK;
-  if (h->gws) { cudaDeviceSynchronize(); cudaFree(h->gws); h->gws = nullptr; h->gws_bytes = 0; }
-  cudaError_t e = cudaMalloc(&h->gws, bytes);
-  if (e != cudaSuccess) return (int)e;
-  h->gws_bytes = bytes;
-  return MCD_OK;
-}
-
 int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
                       const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
                       void* stream) {
@@ -450,46 +456,42 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const Problem& P = p->P;
+  Scratch ws;
   if (P.use_pull) {
     if (method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA) return MCD_E_UNSUPPORTED;
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
-    const int nslots = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
-    if (nslots > 0) {
-      int rc = ensure_gws(h, (size_t)grid * nslots * P.np * P.ld * sizeof(double));
-      if (rc != MCD_OK) return rc;
-    }
+    int rc = ws.alloc((size_t)grid * plan_slots(P) * P.np * P.ld * sizeof(double), st);
+    if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_gen_kernel<<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status, h->gws);
+    mcd_loglike_gen_kernel<<<grid, kThreads, p->smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status, ws.p);
   } else if (p->blocked && method >= MCD_METHOD_SQUARING) {
     if (method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
-    const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
-    int rc = ensure_gws(h, (size_t)grid * blocked_ws_doubles(P, nsl) * sizeof(double));
+    int rc = ws.alloc((size_t)grid * blocked_ws_doubles(P, plan_slots(P)) * sizeof(double), st);
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->blk_smem_bytes));
     mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
-                                                                      h->gws);
+                                                                      ws.p);
   } else if (p->in_smem) {
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
-    const int nsl = P.plan[0].nslots > P.plan[1].nslots ? P.plan[0].nslots : P.plan[1].nslots;
-    if (method >= MCD_METHOD_SQUARING && nsl > 0) {
-      int rc = ensure_gws(h, (size_t)grid * nsl * P.np * P.ld * sizeof(double));
+    if (method >= MCD_METHOD_SQUARING) {
+      int rc = ws.alloc((size_t)grid * plan_slots(P) * P.np * P.ld * sizeof(double), st);
       if (rc != MCD_OK) return rc;
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
     mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
-                                                                     status, h->gws);
+                                                                     status, ws.p);
   } else {
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
-    int rc = ensure_gws(h, (size_t)grid * smem_matrix_bytes(P.np, P.ld));
+    int rc = ws.alloc((size_t)grid * smem_matrix_bytes(P.np, P.ld), st);
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
     mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
-                                                                      status, h->gws);
+                                                                      status, ws.p);
   }
   h->launches++;
   return (int)cudaGetLastError();
@@ -515,94 +517,148 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
   if (mp.method == MCD_METHOD_AUTO) mp.method = sq_ok ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
   if (mp.method < MCD_METHOD_EIGEN || mp.method > MCD_METHOD_SQUARING_DFMA) return MCD_E_ARG;
   if (mp.method >= MCD_METHOD_SQUARING && !sq_ok) return MCD_E_UNSUPPORTED;
+  Scratch ws;
   if (P.use_pull) {
     if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // general engine: tensor-core squaring only
-    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-    if (pl.nslots > 0) {
-      int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));
-      if (rc != MCD_OK) return rc;
-    }
+    int rc = ws.alloc((size_t)nchains * plan_slots(P) * P.np * P.ld * sizeof(double), st);
+    if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_mc_run_gen_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+    mcd_mc_run_gen_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   } else if (p->blocked && mp.method >= MCD_METHOD_SQUARING) {
     if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
-    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-    int rc = ensure_gws(h, (size_t)nchains * blocked_ws_doubles(P, pl.nslots) * sizeof(double));
+    int rc = ws.alloc((size_t)nchains * blocked_ws_doubles(P, plan_slots(P)) * sizeof(double), st);
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->blk_smem_bytes));
-    mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+    mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   } else if (p->in_smem) {
-    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-    if (mp.method >= MCD_METHOD_SQUARING && pl.nslots > 0) {
-      int rc = ensure_gws(h, (size_t)nchains * pl.nslots * P.np * P.ld * sizeof(double));
+    if (mp.method >= MCD_METHOD_SQUARING) {
+      int rc = ws.alloc((size_t)nchains * plan_slots(P) * P.np * P.ld * sizeof(double), st);
       if (rc != MCD_OK) return rc;
     }
     if (mp.method == MCD_METHOD_SQUARING && P.np <= kSmallBins && mcd128_problem_bytes() == sizeof(Problem)) {
       // small profiles: 128-thread CTAs, three per SM (mcd_small.cu)
-      int rc = mcd128_launch_mc_run(&P, &mp, &cio, nchains, nsteps, mcd128_smem_bytes(P.np, P.ld), h->gws, st);
+      int rc = mcd128_launch_mc_run(&P, &mp, &cio, nchains, nsteps, mcd128_smem_bytes(P.np, P.ld), ws.p, st);
       if (rc != MCD_OK) return rc;
       h->launches++;
       return MCD_OK;
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   } else {
     const int ntiles = (P.np / 4) * (P.np / 4 + 1) / 2;
     if (ntiles > kThreads) mp.refresh_every = 1;  // always cold: warm product needs one tile per thread
-    int rc = ensure_gws(h, (size_t)nchains * smem_matrix_bytes(P.np, P.ld));
+    int rc = ws.alloc((size_t)nchains * smem_matrix_bytes(P.np, P.ld), st);
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_mc_run_kernel<false><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, h->gws);
+    mcd_mc_run_kernel<false><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   }
   h->launches++;
   return (int)cudaGetLastError();
 }
 
-// LagPlan of the radial squaring route (lag times are a device array: one small synchronous copy).
-static int rad_plan(RadProblem& R, cudaStream_t st) {
+// ---- radial problem object: private copies of everything that does not change between calls, the LagPlan and the
+//      pair-major counts are made ONCE here; the two entry points below launch one kernel and never synchronise ----
+struct mcd_rad_problem {
+  mcd_handle* h;
+  RadProblem R;      // device pointers below are owned by this object
+  void* blob;
+  double* wrad_basis;   // [n][ncosDrad] or nullptr
+  int ncosDrad;
+  size_t smem_bytes;
+};
+
+int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* stream, mcd_rad_problem** out) {
+  if (!h || !d || !out) return MCD_E_ARG;
+  if (!d->v || !d->w || !d->lagtimes || !d->counts || !d->bessels || !d->b0zeros) return MCD_E_ARG;
+  if (d->n < 3 || d->n > 256 || d->nlag < 1 || d->nlag > kMaxLag || d->dim_rad < 1 || d->lmax < 1 ||
+      d->lmax > kMaxBessel || d->ncosDrad < 0 || d->ncosDrad > kMaxCoef || (d->ncosDrad > 0 && !d->wrad_basis))
+    return MCD_E_ARG;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  mcd_rad_problem* p = new (std::nothrow) mcd_rad_problem();
+  if (!p) return MCD_E_NOMEM;
+  p->h = h;
+  RadProblem& R = p->R;
+  const int n = d->n;
+  R.n = n; R.np = padded_bins(n); R.ld = leading_dim(R.np); R.pbc = d->pbc ? 1 : 0; R.dim_w = d->pbc ? n : n - 1;
+  R.nlag = d->nlag; R.dim_rad = d->dim_rad; R.lmax = d->lmax; R.clip = d->clip; R.reserved = 0;
+  const size_t b_v = align256((size_t)n * 8), b_w = align256((size_t)R.dim_w * 8), b_lag = align256((size_t)R.nlag * 8);
+  const size_t b_cnt = align256((size_t)R.nlag * R.dim_rad * n * n * 8);
+  const size_t b_pc = align256(rad_pcounts_doubles(R) * 8);
+  const size_t b_be = align256((size_t)R.lmax * R.dim_rad * 8), b_z = align256((size_t)R.lmax * 8);
+  const size_t b_wb = align256((size_t)n * d->ncosDrad * 8);
+  unsigned char* blob = nullptr;
+  cudaError_t e = cudaMalloc(&blob, b_v + b_w + b_lag + b_cnt + b_pc + b_be + b_z + b_wb + 256);
+  if (e != cudaSuccess) { delete p; return e == cudaErrorMemoryAllocation ? MCD_E_NOMEM : (int)e; }
+  p->blob = blob;
+  unsigned char* q = blob;
+  double* dv = (double*)q; q += b_v;
+  double* dw = (double*)q; q += b_w;
+  double* dl = (double*)q; q += b_lag;
+  double* dc = (double*)q; q += b_cnt;
+  double* dp = (double*)q; q += b_pc;
+  double* db = (double*)q; q += b_be;
+  double* dz = (double*)q; q += b_z;
+  double* dwb = (double*)q;
+  cudaMemcpyAsync(dv, d->v, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(dw, d->w, (size_t)R.dim_w * 8, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(dl, d->lagtimes, (size_t)R.nlag * 8, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(dc, d->counts, (size_t)R.nlag * R.dim_rad * n * n * 8, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(db, d->bessels, (size_t)R.lmax * R.dim_rad * 8, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(dz, d->b0zeros, (size_t)R.lmax * 8, cudaMemcpyDeviceToDevice, st);
+  if (d->ncosDrad > 0) cudaMemcpyAsync(dwb, d->wrad_basis, (size_t)n * d->ncosDrad * 8, cudaMemcpyDeviceToDevice, st);
+  mcd_rad_pair_counts_kernel<<<2 * h->sm_count, 256, 0, st>>>(dc, dp, R.nlag, R.dim_rad, n);
+  h->launches++;
   double hl[kMaxLag];
-  CUDA_TRY(cudaMemcpyAsync(hl, R.lagtimes, (size_t)R.nlag * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  e = cudaMemcpyAsync(hl, dl, (size_t)R.nlag * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
+  R.v = dv; R.w = dw; R.lagtimes = dl; R.counts = dc; R.pcounts = dp; R.bessels = db; R.b0zeros = dz;
+  p->wrad_basis = d->ncosDrad > 0 ? dwb : nullptr;
+  p->ncosDrad = d->ncosDrad;
   plan_lags(hl, R.nlag, false, &R.plan);
+  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) { cudaFree(blob); delete p; return MCD_E_UNSUPPORTED; }
+  R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
+  p->smem_bytes = rad_smem_bytes(R, R.nbatch);
+  *out = p;
   return MCD_OK;
 }
 
-int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
-                          const double* v, const double* w, const double* lagtimes, const double* counts,
-                          const double* bessels, const double* b0zeros, double clip, int32_t B,
-                          const double* wrad, double* out_ll, double* out_P, int32_t* status, void* stream) {
-  if (!h || !v || !w || !lagtimes || !counts || !bessels || !b0zeros || !wrad || !out_ll) return MCD_E_ARG;
-  if (n < 3 || n > 256 || nlag < 1 || nlag > kMaxLag || dim_rad < 1 || lmax < 1 || lmax > kMaxBessel || B < 0)
-    return MCD_E_ARG;
+int mcd_rad_problem_destroy(mcd_rad_problem* p) {
+  if (!p) return MCD_OK;
+  cudaSetDevice(p->h->device);
+  cudaFree(p->blob);
+  delete p;
+  return MCD_OK;
+}
+
+int mcd_rad_problem_info(const mcd_rad_problem* p, int32_t* np, int32_t* sample_dim, int32_t* nbatch, int32_t* squaring_ok) {
+  if (!p) return MCD_E_ARG;
+  if (np) *np = p->R.np;
+  if (sample_dim) *sample_dim = 3 + (p->ncosDrad > 0 ? p->ncosDrad : p->R.n);
+  if (nbatch) *nbatch = p->R.nbatch;
+  if (squaring_ok) *squaring_ok = p->R.plan.ok;
+  return MCD_OK;
+}
+
+int mcd_rad_loglike_batch(mcd_handle* h, const mcd_rad_problem* p, int32_t B, const double* wrad, double* out_ll,
+                          double* out_P, int32_t* status, void* stream) {
+  if (!h || !p || !wrad || !out_ll || B < 0) return MCD_E_ARG;
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  RadProblem R;
-  R.n = n; R.np = padded_bins(n); R.ld = leading_dim(R.np); R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
-  R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
-  R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
-  R.clip = clip;
-  int prc = rad_plan(R, st);
-  if (prc != MCD_OK) return prc;
+  const RadProblem& R = p->R;
   const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
-  const size_t per_cta = rad_workspace_doubles(R) * sizeof(double);
-  int rc = ensure_gws(h, (size_t)grid * per_cta + rad_pcounts_doubles(R) * sizeof(double));
+  Scratch ws;
+  int rc = ws.alloc((size_t)grid * rad_workspace_doubles(R) * sizeof(double), st);
   if (rc != MCD_OK) return rc;
-  {   // pair-major copy of the counts behind the per-CTA workspaces (stream ordered before the main kernel)
-    double* pc = h->gws + (size_t)grid * rad_workspace_doubles(R);
-    mcd_rad_pair_counts_kernel<<<2 * h->sm_count, 256, 0, st>>>(counts, pc, nlag, dim_rad, n);
-    h->launches++;
-    R.pcounts = pc;
-  }
-  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
-  R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
-  const size_t smem = rad_smem_bytes(R, R.nbatch);
-  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcd_rad_loglike_kernel<<<grid, kThreads, smem, st>>>(R, B, wrad, out_ll, out_P, status, h->gws);
+  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+  mcd_rad_loglike_kernel<<<grid, kThreads, p->smem_bytes, st>>>(R, B, wrad, out_ll, out_P, status, ws.p);
   h->launches++;
   return (int)cudaGetLastError();
 }
@@ -610,43 +666,27 @@ int mcd_rad_loglike_batch(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, i
 static_assert(sizeof(mcd_rad_mc_params) == sizeof(RadMcParams), "mcd_rad_mc_params layout");
 static_assert(sizeof(mcd_rad_chain_io) == sizeof(RadChainIO), "mcd_rad_chain_io layout");
 
-int mcd_rad_mc_run(mcd_handle* h, int32_t n, int32_t pbc, int32_t nlag, int32_t dim_rad, int32_t lmax,
-                   const double* v, const double* w, const double* lagtimes, const double* counts,
-                   const double* bessels, const double* b0zeros, double clip, const mcd_rad_mc_params* params,
+int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_params* params,
                    const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream) {
-  if (!h || !v || !w || !lagtimes || !counts || !bessels || !b0zeros || !params || !io) return MCD_E_ARG;
+  if (!h || !p || !params || !io) return MCD_E_ARG;
   if (!io->wrad || !io->scal || !io->counters) return MCD_E_ARG;
-  if (n < 3 || n > 256 || nlag < 1 || nlag > kMaxLag || dim_rad < 1 || lmax < 1 || lmax > kMaxBessel) return MCD_E_ARG;
-  if (params->ncosDrad < 0 || params->ncosDrad > kMaxCoef) return MCD_E_ARG;
-  if (params->ncosDrad > 0 && (!io->wcoef || !io->wrad_basis || !io->nacc_coeff)) return MCD_E_ARG;
+  if (params->ncosDrad != p->ncosDrad) return MCD_E_ARG;
+  if (params->ncosDrad > 0 && (!io->wcoef || !io->nacc_coeff)) return MCD_E_ARG;
   if (params->use_tape && (!io->tape_u || !io->tape_idx)) return MCD_E_ARG;
   if (nchains <= 0 || nsteps <= 0) return nchains < 0 || nsteps < 0 ? MCD_E_ARG : MCD_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  RadProblem R;
-  R.n = n; R.np = padded_bins(n); R.ld = leading_dim(R.np); R.pbc = pbc ? 1 : 0; R.dim_w = pbc ? n : n - 1;
-  R.nlag = nlag; R.dim_rad = dim_rad; R.lmax = lmax;
-  R.v = v; R.w = w; R.lagtimes = lagtimes; R.counts = counts; R.bessels = bessels; R.b0zeros = b0zeros;
-  R.clip = clip;
-  int prc = rad_plan(R, st);
-  if (prc != MCD_OK) return prc;
-  int rc = ensure_gws(h, ((size_t)nchains * rad_workspace_doubles(R) + rad_pcounts_doubles(R)) * sizeof(double));
+  const RadProblem& R = p->R;
+  Scratch ws;
+  int rc = ws.alloc((size_t)nchains * rad_workspace_doubles(R) * sizeof(double), st);
   if (rc != MCD_OK) return rc;
-  {
-    double* pc = h->gws + (size_t)nchains * rad_workspace_doubles(R);
-    mcd_rad_pair_counts_kernel<<<2 * h->sm_count, 256, 0, st>>>(counts, pc, nlag, dim_rad, n);
-    h->launches++;
-    R.pcounts = pc;
-  }
-  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) return MCD_E_UNSUPPORTED;
-  R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
-  const size_t smem = rad_smem_bytes(R, R.nbatch);
   RadMcParams mp;
   RadChainIO cio;
   std::memcpy(&mp, params, sizeof(mp));
   std::memcpy(&cio, io, sizeof(cio));
-  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mcd_rad_mc_run_kernel<<<nchains, kThreads, smem, st>>>(R, mp, cio, nsteps, h->gws);
+  cio.wrad_basis = p->wrad_basis;   // the library's private copy
+  CUDA_TRY(cudaFuncSetAttribute(mcd_rad_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+  mcd_rad_mc_run_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(R, mp, cio, nsteps, ws.p);
   h->launches++;
   return (int)cudaGetLastError();
 }

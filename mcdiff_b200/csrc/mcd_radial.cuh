@@ -713,7 +713,7 @@ mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, dou
     ex.par([&](int tid) {
       if (tid == 0) {
         out_ll[b] = ll;
-        if (status) status[b] = bad ? ST_JACOBI_NOCONV : 0;
+        if (status) status[b] = bad ? ST_NONFINITE : 0;
       }
     });
   }

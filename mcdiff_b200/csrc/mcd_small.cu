@@ -22,8 +22,7 @@ mcd128_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
   DeviceExec ex(s.red);
   Chain<DeviceExec> ch(ex, P, s);
-  const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * pl.nslots * P.np * P.ld);
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * plan_slots(P) * P.np * P.ld);
 }
 
 // C++ entry points used by mcd_lib.cu (the structs have the same layout in both namespaces; they are passed

@@ -234,7 +234,10 @@ class ChainBatch:
             t0 = self.scal[:, K.S_T0]
             if bool((t0 != 0).any()):
                 lag = (prob.d_lag[None, :] + t0[:, None]).contiguous()
-            ll, _, status = prob.loglike_device(self.v, self.w, lag)
+            # the engine the MC loop will use (ll_cur and the trial values must come from the same arithmetic):
+            # lag times shifted by the chain's time offset have a LagPlan (plan[1]) on every squaring engine
+            method = K.METHOD_SQUARING if (lag is not None and prob.squaring_ok) else K.METHOD_AUTO
+            ll, _, status = prob.loglike_device(self.v, self.w, lag, method=method)
             if prob.spring_k > 0:  # lib/MCState.py:121-124
                 d = self.w[:, 1:] - self.w[:, :-1]
                 e = 0.5 * prob.spring_k * (d * d).sum(dim=1)
@@ -291,29 +294,69 @@ class ChainBatch:
         return out
 
 
+class RadialProblem:
+    """Device-resident radial problem (mcd_rad_problem): frozen v / w, lag times, radial count cubes, Bessel table,
+    optional wrad basis.  The LagPlan and the pair-major counts are made once at creation."""
+
+    def __init__(self, eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad_basis=None, clip=1e-32):
+        self.eng = eng
+        f64 = torch.float64
+        counts = np.asarray(counts, dtype=np.float64)
+        if counts.ndim != 4 or counts.shape[2] != counts.shape[3]:
+            raise ValueError("counts must be [nlag][dim_rad][n][n]")
+        self.nlag, self.dim_rad, self.n, _ = counts.shape
+        self.lmax = int(np.asarray(bessels).shape[0])
+        self.pbc = bool(pbc)
+        self.ncos = 0 if wrad_basis is None else int(np.asarray(wrad_basis).shape[1])
+        with torch.cuda.device(eng.device):
+            keep = [eng.to_device(np.asarray(a, dtype=np.float64), f64)
+                    for a in (v, w, lagtimes, counts, bessels, b0zeros)]
+            d_basis = None if wrad_basis is None else eng.to_device(np.asarray(wrad_basis, dtype=np.float64), f64)
+            d = K.RadProblemDesc()
+            d.n, d.pbc, d.nlag, d.dim_rad, d.lmax, d.ncosDrad = self.n, int(self.pbc), self.nlag, self.dim_rad, self.lmax, self.ncos
+            d.v, d.w, d.lagtimes, d.counts, d.bessels, d.b0zeros = (t.data_ptr() for t in keep)
+            d.wrad_basis = None if d_basis is None else d_basis.data_ptr()
+            d.clip = float(clip)
+            p = C.c_void_p()
+            K.check(eng.lib.mcd_rad_problem_create(eng.handle, C.byref(d), eng.stream_ptr(), C.byref(p)),
+                    "mcd_rad_problem_create")      # synchronises: the staging tensors may go
+            self.ptr = p
+            np_, sd, nb, sq = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            K.check(eng.lib.mcd_rad_problem_info(p, C.byref(np_), C.byref(sd), C.byref(nb), C.byref(sq)))
+            self.np, self.sample_dim, self.nbatch, self.squaring_ok = np_.value, sd.value, nb.value, bool(sq.value)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.eng.lib.mcd_rad_problem_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def loglike_device(self, d_wrad, want_P=False):
+        eng = self.eng
+        B = d_wrad.shape[0]
+        out = torch.empty(B, dtype=torch.float64, device=eng.device)
+        status = torch.empty(B, dtype=torch.int32, device=eng.device)
+        P = (torch.empty((B, self.nlag, self.dim_rad, self.n, self.n), dtype=torch.float64, device=eng.device)
+             if want_P else None)
+        K.check(eng.lib.mcd_rad_loglike_batch(eng.handle, self.ptr, B, _dev(d_wrad), _dev(out), _dev(P), _dev(status),
+                                              eng.stream_ptr()), "mcd_rad_loglike_batch")
+        return out, P, status
+
+
 def rad_loglike(eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad, clip=1e-32, want_P=False):
     """Radial likelihood seam: mcdiff.twod.rad_log_like_lag (lib/twod.py:13-32)."""
-    v = np.asarray(v, dtype=np.float64)
-    w = np.asarray(w, dtype=np.float64)
-    counts = np.asarray(counts, dtype=np.float64)
     wrad = np.atleast_2d(np.asarray(wrad, dtype=np.float64))
-    nlag, dim_rad, n, _ = counts.shape
-    lmax = int(np.asarray(bessels).shape[0])
-    B = wrad.shape[0]
+    prob = RadialProblem(eng, v, w, pbc, lagtimes, counts, bessels, b0zeros, clip=clip)
     with torch.cuda.device(eng.device):
-        f64 = torch.float64
-        d_v, d_w = eng.to_device(v, f64), eng.to_device(w, f64)
-        d_l, d_c = eng.to_device(np.asarray(lagtimes, dtype=np.float64), f64), eng.to_device(counts, f64)
-        d_b, d_z = eng.to_device(np.asarray(bessels, dtype=np.float64), f64), eng.to_device(np.asarray(b0zeros, dtype=np.float64), f64)
-        d_r = eng.to_device(wrad, f64)
-        out = torch.empty(B, dtype=f64, device=eng.device)
-        status = torch.empty(B, dtype=torch.int32, device=eng.device)
-        P = torch.empty((B, nlag, dim_rad, n, n), dtype=f64, device=eng.device) if want_P else None
-        K.check(eng.lib.mcd_rad_loglike_batch(eng.handle, n, int(bool(pbc)), nlag, dim_rad, lmax, _dev(d_v), _dev(d_w),
-                                              _dev(d_l), _dev(d_c), _dev(d_b), _dev(d_z), float(clip), B, _dev(d_r),
-                                              _dev(out), _dev(P), _dev(status), eng.stream_ptr()),
-                "mcd_rad_loglike_batch")
-        return out.cpu().numpy(), (None if P is None else P.cpu().numpy()), status.cpu().numpy()
+        out, P, status = prob.loglike_device(eng.to_device(wrad, torch.float64), want_P)
+        res = out.cpu().numpy(), (None if P is None else P.cpu().numpy()), status.cpu().numpy()
+    prob.close()
+    return res
 
 
 class RadialChains:
@@ -324,21 +367,14 @@ class RadialChains:
                  clip=1e-32):
         self.eng = eng
         f64 = torch.float64
-        counts = np.asarray(counts, dtype=np.float64)
-        self.nlag, self.dim_rad, self.n, _ = counts.shape
-        self.lmax = int(np.asarray(bessels).shape[0])
+        self.prob = RadialProblem(eng, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad_basis=wrad_basis, clip=clip)
+        self.nlag, self.dim_rad, self.n, self.lmax = self.prob.nlag, self.prob.dim_rad, self.prob.n, self.prob.lmax
         self.pbc = bool(pbc)
         self.C = int(nchains)
         self.clip = float(clip)
-        self.ncos = 0 if wrad_basis is None else int(np.asarray(wrad_basis).shape[1])
+        self.ncos = self.prob.ncos
         dev = eng.device
         with torch.cuda.device(dev):
-            self.d_v, self.d_w = eng.to_device(np.asarray(v, dtype=np.float64), f64), eng.to_device(np.asarray(w, dtype=np.float64), f64)
-            self.d_lag = eng.to_device(np.asarray(lagtimes, dtype=np.float64), f64)
-            self.d_counts = eng.to_device(counts, f64)
-            self.d_bess = eng.to_device(np.asarray(bessels, dtype=np.float64), f64)
-            self.d_zeros = eng.to_device(np.asarray(b0zeros, dtype=np.float64), f64)
-            self.d_basis = None if wrad_basis is None else eng.to_device(np.asarray(wrad_basis, dtype=np.float64), f64)
             self.wrad = torch.zeros((self.C, self.n), dtype=f64, device=dev)
             self.wcoef = torch.zeros((self.C, max(self.ncos, 1)), dtype=f64, device=dev)
             self.scal = torch.zeros((self.C, 8), dtype=f64, device=dev)
@@ -366,13 +402,7 @@ class RadialChains:
     def init_log_like(self):
         eng = self.eng
         with torch.cuda.device(eng.device):
-            out = torch.empty(self.C, dtype=torch.float64, device=eng.device)
-            status = torch.empty(self.C, dtype=torch.int32, device=eng.device)
-            K.check(eng.lib.mcd_rad_loglike_batch(eng.handle, self.n, int(self.pbc), self.nlag, self.dim_rad, self.lmax,
-                                                  _dev(self.d_v), _dev(self.d_w), _dev(self.d_lag), _dev(self.d_counts),
-                                                  _dev(self.d_bess), _dev(self.d_zeros), self.clip, self.C,
-                                                  _dev(self.wrad), _dev(out), None, _dev(status), eng.stream_ptr()),
-                    "mcd_rad_loglike_batch")
+            out, _, status = self.prob.loglike_device(self.wrad)
             self.scal[:, 0] = out
             host = out.cpu().numpy()
         if np.any(np.isnan(host)):
@@ -391,7 +421,7 @@ class RadialChains:
             io = K.RadChainIO()
             io.wrad, io.wcoef, io.scal = self.wrad.data_ptr(), self.wcoef.data_ptr(), self.scal.data_ptr()
             io.counters, io.nacc_coeff = self.counters.data_ptr(), self.nacc_coeff.data_ptr()
-            io.wrad_basis = None if self.d_basis is None else self.d_basis.data_ptr()
+            io.wrad_basis = None
             keep = []
             if tape_u is not None:
                 tu = eng.to_device(np.asarray(tape_u, dtype=np.float64), torch.float64)
@@ -406,10 +436,8 @@ class RadialChains:
             if nsamples_cap > 0:
                 smp = torch.zeros((self.C, nsamples_cap, self.sample_dim), dtype=torch.float64, device=dev)
                 io.samples = smp.data_ptr()
-            K.check(eng.lib.mcd_rad_mc_run(eng.handle, self.n, int(self.pbc), self.nlag, self.dim_rad, self.lmax,
-                                           _dev(self.d_v), _dev(self.d_w), _dev(self.d_lag), _dev(self.d_counts),
-                                           _dev(self.d_bess), _dev(self.d_zeros), self.clip, C.byref(mp), C.byref(io),
-                                           self.C, int(nsteps), eng.stream_ptr()), "mcd_rad_mc_run")
+            K.check(eng.lib.mcd_rad_mc_run(eng.handle, self.prob.ptr, C.byref(mp), C.byref(io), self.C, int(nsteps),
+                                           eng.stream_ptr()), "mcd_rad_mc_run")
             self._keep = keep
         return dec, llt, smp
 

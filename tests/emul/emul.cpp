@@ -83,11 +83,13 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
         s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
         s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
       }
-      for (int l = 0; l < P.nlag; ++l) s.lag[l] = P.lagtimes[l];
+      for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       s.sc->status = 0;
+      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;   // as mcd_loglike_gen_kernel
       int sw = 0;
       double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
-      out_ll[b] = ch.evaluate_gen(s.v, s.w, s.lag, P.plan[0], slots.data(), 0, Pb, &sw);
+      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
+                                               : ch.evaluate_gen(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], slots.data(), 0, Pb, &sw);
       if (status) status[b] = (int)s.sc->status;
       if (sweeps) sweeps[b] = sw;
     }
@@ -98,17 +100,19 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     HostExec ex(store.data());
     Chain<HostExec, 1> ch(ex, P, s);
     ch.build_tables();
-    std::vector<double> ws(blocked_ws_doubles(P, P.plan[0].nslots));
+    std::vector<double> ws(blocked_ws_doubles(P, plan_slots(P)));
     for (int b = 0; b < B; ++b) {
       for (int i = 0; i < P.np; ++i) {
         s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
         s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
       }
-      for (int l = 0; l < P.nlag; ++l) s.lag[l] = P.lagtimes[l];
+      for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       s.sc->status = 0;
+      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;   // as mcd_loglike_blk_kernel
       int sw = 0;
       double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
-      out_ll[b] = ch.evaluate_blk(s.v, s.w, s.lag, P.plan[0], ws.data(), 0, Pb, &sw);
+      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
+                                               : ch.evaluate_blk(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], ws.data(), 0, Pb, &sw);
       if (status) status[b] = (int)s.sc->status;
       if (sweeps) sweeps[b] = sw;
     }
@@ -128,8 +132,14 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     int sw = 0;
     double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
     std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
-    out_ll[b] = (method >= MCD_METHOD_SQUARING) ? ch.evaluate_sq(s.v, s.w, s.lag, P.plan[0], slots.data(), 0, method == MCD_METHOD_SQUARING, Pb, &sw)
-                                                : ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    if (method >= MCD_METHOD_SQUARING) {   // as mcd_loglike_kernel: shifted lag times walk plan[1], anything else is flagged
+      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;
+      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
+                                               : ch.evaluate_sq(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], slots.data(), 0,
+                                                                method == MCD_METHOD_SQUARING, Pb, &sw);
+    } else {
+      out_ll[b] = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    }
     if (status) status[b] = (int)s.sc->status;
     if (sweeps) sweeps[b] = sw;
   }
@@ -161,8 +171,7 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
     return 0;
   }
   if (P.blocked && mp.method == MCD_METHOD_SQUARING) {
-    const LagPlan& pl = P.plan[mp.move_timezero ? 1 : 0];
-    std::vector<double> ws(blocked_ws_doubles(P, pl.nslots));
+    std::vector<double> ws(blocked_ws_doubles(P, plan_slots(P)));
     for (int c = 0; c < nchains; ++c) {
       Smem s = carve(P, mat.data(), vec.data(), true);
       HostExec ex(store.data());

@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_version_and_error_strings(lib):
-    assert lib.mcd_version() == 100
+    assert lib.mcd_version() == 200          # MCD_VERSION of include/mcdiff_b200.h
     assert lib.mcd_error_string(0) == b"ok"
     assert lib.mcd_error_string(-1) == b"invalid argument"
     assert lib.mcd_error_string(-2) == b"unsupported configuration"
@@ -44,6 +44,8 @@ def test_struct_layouts():
     assert C.sizeof(K.McParams) == 3 * 8 + 6 * 4 + 4 * 8
     assert C.sizeof(K.ChainIO) == 15 * 8
     assert K.McParams.seed.offset == 48 and K.McParams.method.offset == 40
+    assert C.sizeof(K.RadProblemDesc) == 6 * 4 + 7 * 8 + 8
+    assert C.sizeof(K.RadMcParams) == 2 * 8 + 4 * 4 + 4 * 8 and C.sizeof(K.RadChainIO) == 11 * 8
 
 
 def test_argument_errors_without_gpu(lib):
@@ -51,6 +53,8 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mcd_create(0, None) == -1
     assert lib.mcd_destroy(None) == 0
     assert lib.mcd_problem_destroy(None) == 0
+    assert lib.mcd_rad_problem_destroy(None) == 0
+    assert lib.mcd_rad_problem_create(None, None, None, None) == -1
     assert lib.mcd_launch_count(None) == 0
     import torch
     if not torch.cuda.is_available():

@@ -251,3 +251,56 @@ def test_chain_body_with_128_threads():
             np.testing.assert_allclose(ch.scal[0, K.S_DV:K.S_DW + 1], [ref["dv"], ref["dw"]], rtol=1e-13)
     finally:
         H.use_threads(None)
+
+
+# ---- time offsets on the squaring engines (plan selection, emulator mirrors the kernels) -------------
+@pytest.mark.parametrize("lags", [[10.0, 20.0, 30.0, 40.0], [5.0, 10.0, 25.0]])
+def test_shifted_lag_likelihood_on_squaring_engine(lags):
+    """Per-profile lag times = the problem's lag times + one offset walk plan[1] on the squaring engine and agree
+    with the oracle (scipy expm at the shifted lag times); anything else is flagged MCD_ST_BAD_LAGS."""
+    from oracle import mcdiff_oracle as O
+    n = 24
+    lags = np.array(lags)
+    counts = O.synthetic_counts(n, lags, seed=5, total=5.0e4, dz=1.0)[0]
+    prob = H.HostProblem(counts, lags, True)
+    rng = np.random.default_rng(1)
+    v = rng.normal(0.0, 0.5, (3, n))
+    w = -1.0 + rng.normal(0.0, 0.3, (3, n))
+    shift = np.array([3.0, -1.5, 0.0])
+    lt = lags[None, :] + shift[:, None]
+    ll, _, st, _ = H.loglike_batch(prob, v, w, lagtimes=lt, method=SQUARING)
+    assert not st.any()
+    ref = np.array([O.log_like_lag(v[b], w[b], lt[b], counts, True) for b in range(3)])
+    np.testing.assert_allclose(ll, ref, rtol=1e-11)
+    ll_e, _, st_e, _ = H.loglike_batch(prob, v, w, lagtimes=lt, method=EIGEN)
+    np.testing.assert_allclose(ll_e, ref, rtol=1e-9)
+    bad = lt.copy()
+    bad[1, 1] += 0.5                                   # not an offset of the problem's lag times
+    ll_b, _, st_b, _ = H.loglike_batch(prob, v, w, lagtimes=bad, method=SQUARING)
+    assert st_b[1] == K.ST_BAD_LAGS and np.isnan(ll_b[1]) and st_b[0] == 0 and st_b[2] == 0
+    np.testing.assert_allclose(ll_b[[0, 2]], ref[[0, 2]], rtol=1e-11)
+
+
+@pytest.mark.parametrize("method", [EIGEN, SQUARING])
+def test_time_offset_without_time_offset_moves(method):
+    """A chain that CARRIES a time offset (continued --t0 run, set_state(timezero=...)) but makes no time-offset
+    moves must evaluate its trials at lag + t0: on the squaring engines that is the shifted LagPlan."""
+    from oracle import mcdiff_oracle as O
+    n, nsteps, tau = 24, 30, 3.0
+    lags = np.array([10.0, 20.0, 30.0, 40.0])
+    counts = O.synthetic_counts(n, lags, seed=7, total=5.0e4, dz=1.0)[0]
+    prob = H.HostProblem(counts, lags, True)
+    v0, w0 = np.zeros(n), np.full(n, -1.0)
+    ll0 = O.log_like_lag(v0, w0, lags + tau, counts, True)
+    ch = H.HostChains(prob, 1, v0, w0, ll0=ll0, dv=0.3, dw=0.3, timezero=tau)
+    cfg = O.ChainConfig(counts, lags, True, dv=0.3, dw=0.3, temp=1.0, nmc=nsteps, num_mc_update=10.0)
+    tu, ti = O.make_tape(np.random.default_rng(3), nsteps, cfg)
+    mp = K.McParams()
+    mp.num_mc_update, mp.min_lt, mp.move_timezero, mp.sample_every = 10.0, 10.0, 0, 100
+    mp.refresh_every, mp.use_tape, mp.method = 16, 1, method
+    dec, llt, _ = ch.run(nsteps, mp, tu, ti)
+    ref = O.replay(cfg, v0, w0, tu, ti, timezero0=tau)
+    assert np.array_equal(dec[0] & 1, ref["accepted"])
+    np.testing.assert_allclose(llt[0], ref["ll_try"], rtol=1e-10)
+    np.testing.assert_allclose(ch.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
+    assert ch.scal[0, K.S_T0] == tau and not ch.counters[0, K.C_STATUS]
