@@ -1,22 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- MC steps/s of the mcdiff Monte-Carlo likelihood loop on B200.
 
-Metric (BASELINE.json): MC steps/sec summed over all chains at 100 bins x 4 lag times,
-plus the fraction of the FP64 roofline.  One bench "step" = ONE launch of the fused chain
-kernel that advances every chain of this rank by MC_PER_LAUNCH Monte-Carlo steps (one MC
-step = proposal + rate matrix + 4 propagators expm(lag R) + log L + Metropolis,
-i.e. one iteration of lib/mc.py:27 of the reference).
+Metric (BASELINE.json): MC steps/sec summed over all chains at 100 bins x 4 lag times, plus the fraction of the FP64
+roofline.  One bench "step" = ONE launch of the fused chain kernel that advances every chain of this rank by
+MC_PER_LAUNCH Monte-Carlo steps (one MC step = proposal + rate matrix + 4 propagators expm(lag R) + log L +
+Metropolis, i.e. one iteration of lib/mc.py:27 of the reference).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Under torchrun (N > 1) every rank owns CHAINS_PER_GPU chains (weak scaling, no data-path
-collective; one NCCL all_gather of the posterior summaries at the end).
+Legs of the b200 arm (one JSON line, rank 0):
+  value      headline: BASELINE shape, 1024 chains per GPU resident in HBM, K timed launches (weak scaling)
+  e2e        the same metric through the USER API: find_parameters(files..., nchains=) = run-mcdiff: transition
+             files in, <out>.dat / .pic / .pic.ave.dat / .chains.npz out, uploads, the final NCCL gathers and the
+             device->host reads inside the timed region
+  strong     e2e with a FIXED total of 4096 chains over the N GPUs (strong-scaling point)
+  secondary  config 3 (200 bins x 8 lags, Fourier 12/8, blocked engine) and config 5 (radial model), 512 chains per
+             GPU each: MC steps/s, algorithmic flops, fraction of the FP64 peak, kernel name
+  cpu_baseline  (N = 1) the UNMODIFIED reference's do_mc_cycles (baseline/_ref, scripts/install_reference.sh) on one
+             host core; the oracle port only when the reference is not installed
+`--impl reference` times the reference's own loop on all host cores (one chain per core) + the two single-process
+variants of BASELINE.md 4.3.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -24,6 +37,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 N_BINS = 100
 LAGS = (10.0, 20.0, 30.0, 40.0)
@@ -32,9 +46,11 @@ MC_PER_LAUNCH = 200
 NCOS_F, NCOS_D = 10, 6           # the reference's own example model (examples/example-HexdWat-run1.sh)
 DV = DW = 0.05
 NMC_UPDATE = 1000.0
-NCU_DRAM_BYTES_PER_LAUNCH = 3954944 + 56320
+STRONG_CHAINS = 4096
 METRIC = "MC steps/sec (all chains, 100 bins x 4 lags)"
 UNIT = "MC steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 chains x 200 steps), ncu --set full, see profiles/
+NCU_DRAM_BYTES_PER_LAUNCH = {"mcd_mc_run_kernel<true>": 3954944 + 56320}
 
 
 def flops_per_mc_step(n, L):
@@ -42,16 +58,65 @@ def flops_per_mc_step(n, L):
     return 9.0 * n ** 3 + L * (2.0 * n ** 3 + 3.0 * n ** 2)
 
 
-def workload():
-    from oracle import mcdiff_oracle as O   # synthetic-input generator only
-    counts, lags, edges, F, w_true = O.synthetic_counts(N_BINS, LAGS)
-    vb = O.cos_basis_center(N_BINS, NCOS_F)
-    wb = O.cos_basis_border(N_BINS, N_BINS, NCOS_D)
-    dz = edges[1] - edges[0]
-    wc0 = np.zeros(NCOS_D)
-    wc0[0] = np.log(1.0) - np.log(dz * dz)       # D0 = 1 A^2/ps
-    return dict(counts=counts.astype(np.int32), lags=lags, vb=vb, wb=wb, vc0=np.zeros(NCOS_F), wc0=wc0,
-                v0=np.zeros(N_BINS), w0=wb @ wc0)
+def flops_per_radial_step(n, L, lmax, dim_rad):
+    """SURVEY.md 8(d), radial: lmax 9 n^3 + L lmax 2 n^3 + L (2 dim_rad lmax n^2 + 3 dim_rad n^2)."""
+    return lmax * 9.0 * n ** 3 + L * lmax * 2.0 * n ** 3 + L * (2.0 * dim_rad * lmax * n ** 2 + 3.0 * dim_rad * n ** 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic inputs (SURVEY.md 8d).  Input GENERATION only: a truth profile, its propagator and multinomial counts.
+# Neither the product nor the oracle is involved, so both arms read byte-identical files.
+# ---------------------------------------------------------------------------------------------------------------
+def truth_rate_matrix(F, w):
+    """Periodic rate matrix of lib/utils.py:77-103 for the truth profile (generator side only)."""
+    n = len(F)
+    R = np.zeros((n, n))
+    for i in range(n):
+        j = (i + 1) % n
+        R[j, i] = np.exp(w[i] - 0.5 * (F[j] - F[i]))
+        R[i, j] = np.exp(w[i] + 0.5 * (F[j] - F[i]))
+    R[np.arange(n), np.arange(n)] = -R.sum(axis=0)
+    return R
+
+
+def synthetic_counts(n, lags, seed=20240607, total=1.0e6, dz=0.5):
+    import scipy.linalg
+    i = np.arange(n)
+    F = 2.0 * np.cos(2 * np.pi * (i + 0.5) / n) + 0.5 * np.cos(4 * np.pi * (i + 0.5) / n)
+    D = 0.5 + 0.3 * np.cos(2 * np.pi * (i + 1.0) / n)
+    w = np.log(D) - np.log(dz * dz / 1.0)
+    rng = np.random.default_rng(seed)
+    pi = np.exp(-F)
+    pi /= pi.sum()
+    M = np.round(total * pi).astype(np.int64)
+    R = truth_rate_matrix(F, w)
+    out = np.zeros((len(lags), n, n), dtype=np.int64)
+    for il, lag in enumerate(lags):
+        P = np.clip(scipy.linalg.expm(lag * R), 0.0, None)
+        P /= P.sum(axis=0, keepdims=True)
+        for j in range(n):
+            out[il, :, j] = rng.multinomial(M[j], P[:, j])
+    return out, np.linspace(-n * dz / 2, n * dz / 2, n + 1)
+
+
+def write_square_files(outdir, counts, lags, edges, tag="pbc"):
+    """Reference text format (lib/tools/extract.py:19-36); plain writer so that the reference arm needs no product code."""
+    files = []
+    n = counts.shape[-1]
+    for l, lag in enumerate(lags):
+        fn = os.path.join(outdir, "transitions.nbins%d.%d.%s.dat" % (n, int(lag), tag))
+        with open(fn, "w") as f:
+            f.write("#lt    {}\n#count {}\n#dt    {}\n#dn    {}\n".format(float(lag), tag, 1.0, int(lag)))
+            f.write("#edges  " + " ".join(str(b) for b in edges) + "\n")
+            for row in counts[l]:
+                f.write(" ".join(str(x) for x in row) + "\n")
+        files.append(fn)
+    return files
+
+
+def headline_files(outdir):
+    counts, edges = synthetic_counts(N_BINS, LAGS)
+    return write_square_files(outdir, counts, LAGS, edges)
 
 
 class ClockSampler(threading.Thread):
@@ -89,67 +154,192 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(power) if power else None, "samples": len(self.rows), "reasons": reasons}
 
 
-def cpu_port_steps_per_s(wl, nsteps, seed=1):
-    """Oracle port of the reference loop (scipy expm), one chain, one core."""
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the unmodified reference (baseline/_ref) or, when it is not installed, the oracle port
+# ---------------------------------------------------------------------------------------------------------------
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "mcdiff"))
+
+
+def cpu_model_string():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _reference_chain(files, nmc, seed):
+    """`nmc` steps of ONE chain of the unmodified reference: mcdiff.mc.do_mc_cycles (lib/mc.py:20-51) on the MCState
+    that lib/mc.py:62-86 builds.  Returns (seconds inside do_mc_cycles, final log-likelihood)."""
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import mcdiff.mc as rmc
+    from mcdiff.MCState import MCState
+    from mcdiff.log import Logger
+    from mcdiff.transitions import Transitions
+    import warnings
+    warnings.filterwarnings("ignore", category=RuntimeWarning)    # the reference overflows exp() in its accept test
+    np.random.seed(seed)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        MC = MCState(True, -1)
+        MC.set_MC_params(DV, DW, 0.5, 1.0, 0.1, 1.0, nmc, NMC_UPDATE, False, -1, temp_end=1.0)
+        MC.set_model("CosinusModel", Transitions(files), NCOS_F, NCOS_D, 0, None)
+        logger = Logger(MC)
+        t0 = time.perf_counter()
+        rmc.do_mc_cycles(MC, logger)
+        el = time.perf_counter() - t0
+    return el, float(MC.log_like)
+
+
+def _port_chain(files, nmc, seed):
+    """Fallback when baseline/_ref is absent: the oracle's restatement of the same loop."""
     from oracle import mcdiff_oracle as O
-    cfg = O.ChainConfig(wl["counts"], wl["lags"], True, v_basis=wl["vb"], w_basis=wl["wb"], dv=DV, dw=DW,
-                        temp=1.0, nmc=nsteps, num_mc_update=NMC_UPDATE)
-    tu, ti = O.make_tape(np.random.default_rng(seed), nsteps, cfg)
+    counts = np.array([O.read_counts(fn)[1] for fn in files])
+    vb, wb = O.cos_basis_center(N_BINS, NCOS_F), O.cos_basis_border(N_BINS, N_BINS, NCOS_D)
+    wc0 = np.zeros(NCOS_D)
+    wc0[0] = -np.log(0.25)
+    cfg = O.ChainConfig(counts, np.array(LAGS), True, v_basis=vb, w_basis=wb, dv=DV, dw=DW, temp=1.0, nmc=nmc,
+                        num_mc_update=NMC_UPDATE)
+    tu, ti = O.make_tape(np.random.default_rng(seed), nmc, cfg)
     t0 = time.perf_counter()
-    O.replay(cfg, wl["v0"], wl["w0"], tu, ti, v_coeff0=wl["vc0"], w_coeff0=wl["wc0"])
-    return nsteps / (time.perf_counter() - t0)
+    out = O.replay(cfg, np.zeros(N_BINS), wb @ wc0, tu, ti, v_coeff0=np.zeros(NCOS_F), w_coeff0=wc0)
+    return time.perf_counter() - t0, float(out["ll"])
 
 
-_WL_CACHE = None
+def cpu_chain(files, nmc, seed):
+    return (_reference_chain if reference_available() else _port_chain)(files, nmc, seed)
 
 
 def _ref_worker(args):
-    global _WL_CACHE
-    nsteps, seed = args
-    if _WL_CACHE is None:              # once per worker process, outside the timed steps (warm-up)
-        _WL_CACHE = workload()
-    wl = _WL_CACHE
-    from oracle import mcdiff_oracle as O
-    cfg = O.ChainConfig(wl["counts"], wl["lags"], True, v_basis=wl["vb"], w_basis=wl["wb"], dv=DV, dw=DW,
-                        temp=1.0, nmc=nsteps, num_mc_update=NMC_UPDATE)
-    tu, ti = O.make_tape(np.random.default_rng(seed), nsteps, cfg)
-    O.replay(cfg, wl["v0"], wl["w0"], tu, ti, v_coeff0=wl["vc0"], w_coeff0=wl["wc0"])
-    return nsteps
+    files, nmc, seed = args
+    el, _ = cpu_chain(files, nmc, seed)
+    return nmc, el
+
+
+def _single_process_rate(files, nmc, threads):
+    """One chain in a fresh process with `threads` BLAS threads (BASELINE.md 4.3 variants i and ii)."""
+    env = dict(os.environ)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        env[var] = str(threads)
+    code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+            "el, ll = bench.cpu_chain(%r, %d, 1); print(json.dumps([el, ll]))" % (ROOT, list(files), nmc))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    if out.returncode != 0:
+        return None
+    el, _ = json.loads(out.stdout.strip().splitlines()[-1])
+    return nmc / el
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port: scipy.linalg.expm per lag
-    per step, lib/utils.py:307-368) on all host cores, one independent chain per core."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, one independent chain
+    per core (BLAS threads = 1: they hurt at n = 100), plus the single-process variants."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[var] = "1"      # BLAS threads hurt at n = 100 (SURVEY.md 6); one chain per core instead
+        os.environ[var] = "1"
     cores = os.cpu_count() or 1
-    per_step = 150           # MC steps per worker per bench step (bounded sample, ~0.3 s per step)
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        for w in range(max(1, args.warmup)):
-            pool.map(_ref_worker, [(8, 1000 + w * cores + c) for c in range(cores)], chunksize=1)
-        t0 = time.perf_counter()
-        done = 0
-        for k in range(args.steps):
-            done += sum(pool.map(_ref_worker, [(per_step, k * cores + c) for c in range(cores)], chunksize=1))
-        el = time.perf_counter() - t0
-    val = done / el
+    per_step = 150           # MC steps per worker per bench step (bounded sample, ~0.4 s per step)
+    tmp = tempfile.mkdtemp(prefix="mcd_bench_ref_")
+    try:
+        files = headline_files(tmp)
+        kind = "reference" if reference_available() else "port"
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(cores) as pool:
+            for w in range(max(1, args.warmup)):
+                pool.map(_ref_worker, [(files, 8, 1000 + w * cores + c) for c in range(cores)], chunksize=1)
+            t0 = time.perf_counter()
+            done = 0
+            for k in range(args.steps):
+                done += sum(r[0] for r in pool.map(_ref_worker, [(files, per_step, k * cores + c) for c in range(cores)],
+                                                   chunksize=1))
+            el = time.perf_counter() - t0
+        val = done / el
+        one = _single_process_rate(files, 600, 1)
+        allthreads = _single_process_rate(files, 600, cores)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    import scipy
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic pbc 100 bins x 4 lags {10,20,30,40}, CosinusModel ncosF=10 ncosD=6, "
-                               "one chain per host core", "mc_steps_per_step": per_step * cores},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d MC steps per core per bench step, %d cores, BLAS threads=1" % (per_step, cores)},
+        "config": {"workload": "synthetic pbc 100 bins x 4 lags {10,20,30,40} (SURVEY 8d, seed 20240607), CosinusModel "
+                               "ncosF=10 ncosD=6, F=0 D=1 start, dv=dw=0.05, T=1; one chain per host core",
+                   "mc_steps_per_step": per_step * cores},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d MC steps per core per bench step, %d cores, BLAS threads=1; %s" % (
+                             per_step, cores, "mcdiff.mc.do_mc_cycles of the unmodified reference (baseline/_ref)"
+                             if kind == "reference" else "oracle port (baseline/_ref not installed)"),
+                         "variants": {"one_process_1_thread": one, "one_process_all_threads": allthreads,
+                                      "one_process_per_core_aggregate": val},
+                         "cpu_model": cpu_model_string(), "numpy": np.__version__, "scipy": scipy.__version__},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def _mc_params(K, rank_offset, lags, method=0, seed=1):
+    mp = K.McParams()
+    mp.num_mc_update = NMC_UPDATE
+    mp.dtemp = 0.0
+    mp.min_lt = float(min(lags))
+    mp.move_timezero = 0
+    mp.sample_every = 100
+    mp.refresh_every = 512
+    mp.use_tape = 0
+    mp.seed = seed
+    mp.chain_offset = rank_offset
+    mp.tape_stride = 0
+    mp.method = method
+    return mp
+
+
+def _time_launches(torch, dist, world, flush, launch, steps, warmup):
+    """W untimed launches, then K timed ones bracketed by barrier + synchronize; returns (total ms max over ranks,
+    mean kernel ms of this rank)."""
+    for _ in range(warmup):
+        launch()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ev0.record()
+    for k in range(steps):
+        flush.zero_()                       # L2 flush between timed iterations
+        kev[k][0].record()
+        launch()
+        kev[k][1].record()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), kernel_ms
+
+
+def _bcast_path(dist, world, rank, make):
+    """rank 0 creates a scratch directory (and its files), every rank learns the path."""
+    obj = [make() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(obj, src=0)
+    return obj[0]
 
 
 def run_gpu(args):
@@ -157,7 +347,11 @@ def run_gpu(args):
     import torch.distributed as dist
     import __graft_entry__ as g
     from mcdiff_b200 import _capi as K
-    from mcdiff_b200.engine import Engine, DeviceProblem, ChainBatch
+    from mcdiff_b200 import engine as E
+    from mcdiff_b200.engine import ChainBatch, DeviceProblem, Engine, RadialChains, RadialProblem
+    from mcdiff_b200.mc import find_parameters
+    from mcdiff_b200.model import CosinusModel, RadCosinusModel
+    from mcdiff_b200.transitions import RadTransitions, Transitions, write_Tmat_cube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,139 +365,208 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     eng = Engine(local)
-    wl = workload()
+    method = {"auto": 0, "eigen": 1, "squaring": 2, "squaring_dfma": 3}[args.method]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=eng.device)   # > 126 MB L2
+    peak_tf = eng.fp64_peak_tflops()
+
+    def make_inputs():
+        d = tempfile.mkdtemp(prefix="mcd_bench_")
+        headline_files(d)
+        c3, e3 = synthetic_counts(200, C3_LAGS, seed=3)
+        os.makedirs(os.path.join(d, "c3"))
+        write_square_files(os.path.join(d, "c3"), c3, C3_LAGS, e3)
+        return d
+
+    C3_LAGS = (5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0)
+    tmp = _bcast_path(dist, world, rank, make_inputs)
+    files = [os.path.join(tmp, "transitions.nbins%d.%d.pbc.dat" % (N_BINS, int(l))) for l in LAGS]
+    sink = io.StringIO()
+
+    # ---------------- headline: device-resident arm, inputs already in HBM ----------------
+    data = Transitions(files)
+    model = CosinusModel(data, 1.0, NCOS_F, NCOS_D)           # the product's own bases and start (F = 0, D = 1)
+    prob = DeviceProblem(eng, np.asarray(data.list_trans).astype(np.int64), data.list_lt, True,
+                         v_basis=model.v_basis, w_basis=model.w_basis)
     nch = CHAINS_PER_GPU
     L = len(LAGS)
-
-    def params(seed=1):
-        mp = K.McParams()
-        mp.num_mc_update = NMC_UPDATE
-        mp.dtemp = 0.0
-        mp.min_lt = float(min(LAGS))
-        mp.move_timezero = 0
-        mp.sample_every = 100
-        mp.refresh_every = 512
-        mp.use_tape = 0
-        mp.seed = seed
-        mp.chain_offset = rank * nch
-        mp.tape_stride = 0
-        mp.method = {"auto": 0, "eigen": 1, "squaring": 2, "squaring_dfma": 3}[args.method]
-        return mp
-
-    # ---------------- device-resident arm: inputs already in HBM ----------------
-    prob = DeviceProblem(eng, wl["counts"], wl["lags"], True, v_basis=wl["vb"], w_basis=wl["wb"])
-    chains = ChainBatch(prob, nch)
-    chains.set_state(wl["v0"], wl["w0"], wl["vc0"], wl["wc0"], dv=DV, dw=DW)
-    chains.init_log_like()
-    mp = params()
     nsamp = MC_PER_LAUNCH // 100
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=eng.device)   # > 126 MB L2
+
+    def headline(nchains):
+        chains = ChainBatch(prob, nchains)
+        chains.set_state(model.v, model.w, model.v_coeff, model.w_coeff, dv=DV, dw=DW)
+        chains.init_log_like()
+        mp = _mc_params(K, rank * nchains, LAGS, method)
+        return chains, (lambda: chains.run(MC_PER_LAUNCH, mp, nsamples_cap=nsamp))
+
+    chains, launch = headline(nch)
     for _ in range(args.warmup):
-        chains.run(MC_PER_LAUNCH, mp, nsamples_cap=nsamp)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        launch()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev0.record()
-    for k in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations
-        kev[k][0].record()
-        chains.run(MC_PER_LAUNCH, mp, nsamples_cap=nsamp)
-        kev[k][1].record()
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    ms_max, kernel_ms = _time_launches(torch, dist, world, flush, launch, args.steps, 0)
     launches = eng.launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_mc = float(world) * nch * MC_PER_LAUNCH * args.steps
-    value = total_mc / (ms_max * 1e-3)
-
-    # posterior summaries: the one collective of the design (per-chain acceptance + log L)
+    value = float(world) * nch * MC_PER_LAUNCH * args.steps / (ms_max * 1e-3)
     st = chains.host_state()
-    summary = torch.tensor(np.concatenate([st["scal"][:, :6], st["counters"][:, :3].astype(np.float64)], axis=1),
-                           dtype=torch.float64, device=eng.device)
-    if world > 1:
-        gathered = torch.empty((world,) + tuple(summary.shape), dtype=torch.float64, device=eng.device)
-        dist.all_gather_into_tensor(gathered, summary)
-        summary_all = gathered.reshape(-1, summary.shape[1]).cpu().numpy()
-    else:
-        summary_all = summary.cpu().numpy()
     bad = int(st["counters"][:, 6].astype(bool).sum())
+    squarings = float(st["counters"][:, 7].sum()) / max(1.0, float(st["counters"][:, 5].sum()))
+    acc = float((st["counters"][:, 0] + st["counters"][:, 1]).sum() / max(1.0, float(st["counters"][:, 5].sum())))
+    # a chain count that fills whole waves of 148 CTAs (7 x 148): what the wave quantisation of 1024 costs
+    nch148 = 7 * 148
+    chains148, launch148 = headline(nch148)
+    ms148, _ = _time_launches(torch, dist, world, flush, launch148, max(2, min(args.steps, 4)), 3)
+    value148 = float(world) * nch148 * MC_PER_LAUNCH * max(2, min(args.steps, 4)) / (ms148 * 1e-3)
+    del chains148
 
-    # ---------------- end-to-end arm: host buffers in, host results out, every step ----------------
-    h_counts = torch.from_numpy(wl["counts"]).pin_memory()
-    st_h = dict(v=torch.from_numpy(st["v"]).pin_memory(), w=torch.from_numpy(st["w"]).pin_memory(),
-                vc=torch.from_numpy(st["vcoef"]).pin_memory(), wc=torch.from_numpy(st["wcoef"]).pin_memory(),
-                scal=torch.from_numpy(st["scal"]).pin_memory(),
-                counters=torch.from_numpy(st["counters"]).pin_memory())
-    e2e_steps = max(2, min(args.steps, 5))
-    h2d = d2h = 0
+    # ---------------- secondary: config 3 (200 x 8, blocked engine) and config 5 (radial) ----------------
+    secondary = {}
+    sec_steps = max(2, min(args.steps, 3))
+    # config 3
+    files3 = [os.path.join(tmp, "c3", "transitions.nbins200.%d.pbc.dat" % int(l)) for l in C3_LAGS]
+    data3 = Transitions(files3)
+    model3 = CosinusModel(data3, 1.0, 12, 8)
+    prob3 = DeviceProblem(eng, np.asarray(data3.list_trans).astype(np.int64), data3.list_lt, True,
+                          v_basis=model3.v_basis, w_basis=model3.w_basis)
+    ch3 = ChainBatch(prob3, 512)
+    ch3.set_state(model3.v, model3.w, model3.v_coeff, model3.w_coeff, dv=DV, dw=DW)
+    ch3.init_log_like()
+    mp3 = _mc_params(K, rank * 512, C3_LAGS, 0)
+    C3_MC = 20
+    ms3, k3 = _time_launches(torch, dist, world, flush, lambda: ch3.run(C3_MC, mp3), sec_steps, 3)
+    fl3 = flops_per_mc_step(200, len(C3_LAGS))
+    st3 = ch3.host_state()
+    secondary["config3_200bins_8lags"] = {
+        "value": float(world) * 512 * C3_MC * sec_steps / (ms3 * 1e-3), "unit": UNIT, "chains_per_gpu": 512,
+        "mc_steps_per_launch": C3_MC, "launches": sec_steps, "kernel": "mcd_mc_run_blk_kernel",
+        "kernel_ms_per_launch": k3, "algorithmic_flops_per_mc_step": fl3,
+        "achieved_tflops": 512 * C3_MC * fl3 / (k3 * 1e-3) / 1e12,
+        "frac": 512 * C3_MC * fl3 / (k3 * 1e-3) / 1e12 / peak_tf,
+        "squarings_per_mc_step": float(st3["counters"][:, 7].sum()) / max(1.0, float(st3["counters"][:, 5].sum())),
+        "chains_with_status": int(st3["counters"][:, 6].astype(bool).sum()),
+        "workload": "synthetic pbc 200 bins x 8 lags {5..40} (seed 3), CosinusModel ncosF=12 ncosD=8"}
+    del ch3
+    # config 5: radial cube drawn from the product's own radial propagator at a truth profile (generation only)
+    RN, RDIM, RLMAX, RLAGS = 30, 41, 20, (5.0, 10.0)
 
-    def e2e_step():
-        nonlocal h2d, d2h
-        p2 = DeviceProblem(eng, h_counts.numpy(), wl["lags"], True, v_basis=wl["vb"], w_basis=wl["wb"])
-        c2 = ChainBatch(p2, nch, keep_basis=True)
-        c2.v.copy_(st_h["v"], non_blocking=True)
-        c2.w.copy_(st_h["w"], non_blocking=True)
-        c2.vcoef.copy_(st_h["vc"], non_blocking=True)
-        c2.wcoef.copy_(st_h["wc"], non_blocking=True)
-        c2.scal.copy_(st_h["scal"], non_blocking=True)
-        c2.counters.copy_(st_h["counters"], non_blocking=True)
-        _, _, smp = c2.run(MC_PER_LAUNCH, mp, nsamples_cap=nsamp)
-        out = c2.host_state()
-        smp_h = smp.cpu()
-        h2d = (h_counts.numel() * 4 + wl["vb"].nbytes + wl["wb"].nbytes + wl["lags"].nbytes
-               + sum(x.numel() * x.element_size() for x in st_h.values()))
-        d2h = sum(v_.nbytes for v_ in out.values() if v_ is not None) + smp_h.numel() * 8
-        p2.close()
-        return out
+    def make_radial():
+        from scipy import special
+        # v, w are frozen in radial runs: the truth uses the flat profiles the model starts from (F = 0, D = 1)
+        v = np.zeros(RN)
+        w = np.full(RN, -np.log(0.25))
+        wrad = np.log((0.4 + 0.15 * np.cos(2 * np.pi * (np.arange(RN) + 0.5) / RN)) / 0.25)
+        zeros = special.jn_zeros(0, RLMAX)
+        r = np.arange(RDIM, dtype=np.float64) + 0.5
+        bess = np.array([2 * r * special.j0(r / RDIM * z) / special.j1(z) ** 2 / RDIM ** 2 for z in zeros])
+        p0 = RadialProblem(eng, v, w, True, RLAGS, np.zeros((len(RLAGS), RDIM, RN, RN)), bess, zeros)
+        _, P, _ = p0.loglike_device(eng.to_device(wrad[None, :], torch.float64), want_P=True)
+        P = np.clip(E.to_host(P)[0], 0.0, None)
+        p0.close()
+        cube = np.random.default_rng(0).poisson(2000.0 * P * np.exp(-v)[None, None, None, :])
+        fns = []
+        for l, lag in enumerate(RLAGS):
+            fn = os.path.join(tmp, "rad.%d.dat" % int(lag))
+            write_Tmat_cube(cube[l].astype(int), fn, float(lag), "pbc", edges=np.linspace(-7.5, 7.5, RN + 1),
+                            redges=np.arange(RDIM) * 0.5, dt=1.0, dn=int(lag))
+            fns.append(fn)
+        return fns
 
-    e2e_step()
-    torch.cuda.synchronize()
+    if rank == 0:
+        make_radial()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = float(world) * nch * MC_PER_LAUNCH * e2e_steps / float(t.item())
+    rfiles = [os.path.join(tmp, "rad.%d.dat" % int(l)) for l in RLAGS]
+    rdata = RadTransitions(rfiles)
+    rmodel = RadCosinusModel(rdata, 1.0, 0, 0, 0, 4)
+    from scipy import special
+    zeros = special.jn_zeros(0, RLMAX)
+    rr = np.arange(rmodel.dim_rad, dtype=np.float64) + 0.5
+    bess = np.array([2 * rr * special.j0(rr / rmodel.dim_rad * z) / special.j1(z) ** 2 / rmodel.dim_rad ** 2 for z in zeros])
+    rch = RadialChains(eng, rmodel.v, rmodel.w, True, rdata.list_lt, rdata.list_trans, bess, zeros, 512,
+                       wrad_basis=rmodel.wrad_basis)
+    rch.set_state(rmodel.wrad, rmodel.wrad_coeff, dwrad=0.05)
+    rch.init_log_like()
+    R_MC = 20
+    msr, kr = _time_launches(torch, dist, world, flush,
+                             lambda: rch.run(R_MC, num_mc_update=NMC_UPDATE, seed=1, chain_offset=rank * 512),
+                             sec_steps, 3)
+    flr = flops_per_radial_step(RN, len(RLAGS), RLMAX, rmodel.dim_rad)
+    rst = rch.host_state()
+    secondary["config5_radial"] = {
+        "value": float(world) * 512 * R_MC * sec_steps / (msr * 1e-3), "unit": UNIT, "chains_per_gpu": 512,
+        "mc_steps_per_launch": R_MC, "launches": sec_steps, "kernel": "mcd_rad_mc_run_kernel",
+        "kernel_ms_per_launch": kr, "algorithmic_flops_per_mc_step": flr,
+        "achieved_tflops": 512 * R_MC * flr / (kr * 1e-3) / 1e12,
+        "frac": 512 * R_MC * flr / (kr * 1e-3) / 1e12 / peak_tf,
+        "chains_with_status": int(rst["counters"][:, 3].astype(bool).sum()),
+        "mean_acceptance": float(rst["counters"][:, 0].sum() / max(1.0, float(rst["counters"][:, 2].sum()))),
+        "workload": "radial model n=30 bins, dim_rad=%d, lmax=20, lags {5,10}, RadCosinusModel ncosDrad=4 "
+                    "(SURVEY 8d recipe, Poisson(2000 P e^-v), seed 0)" % rmodel.dim_rad}
+    del rch
 
+    # ---------------- end to end through the user API: files in, result files out ----------------
+    def e2e_leg(nchains_total, nmc, reps, tag):
+        out = os.path.join(tmp, "%s.r%d.dat" % (tag, rank)) if rank != 0 else os.path.join(tmp, tag + ".dat")
+        best = []
+        h2d = d2h = 0
+        for r in range(reps + 1):               # the first call is the warm-up
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            E.TRAFFIC["h2d"] = E.TRAFFIC["d2h"] = 0
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sink):
+                find_parameters(files, True, "CosinusModel", DV, DW, 0.5, 1.0, 0.1, 1.0, 1.0, nmc, NMC_UPDATE, 1, out,
+                                NCOS_F, NCOS_D, 0, False, None, -1, -1, False, None, nchains=nchains_total, device=local,
+                                chunk=MC_PER_LAUNCH)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            el = time.perf_counter() - t0
+            sink.seek(0)
+            sink.truncate(0)
+            if r > 0:
+                best.append(el)
+                h2d, d2h = E.TRAFFIC["h2d"], E.TRAFFIC["d2h"]
+        t = torch.tensor([float(np.mean(best))], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return nchains_total * nmc / float(t.item()), float(t.item()), int(h2d), int(d2h)
+
+    e2e_reps = max(2, min(args.steps, 3))
+    E2E_NMC = 1000
+    e2e_value, e2e_s, h2d, d2h = e2e_leg(world * nch, E2E_NMC, e2e_reps, "e2e")
+    strong_value, strong_s, _, _ = e2e_leg(STRONG_CHAINS, MC_PER_LAUNCH, 2, "strong")
+
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---------------- roofline + CPU baseline (rank 0) ----------------
-    peak_tf = eng.fp64_peak_tflops()
     fl = flops_per_mc_step(N_BINS, L)
     achieved_tf = nch * MC_PER_LAUNCH * fl / (kernel_ms * 1e-3) / 1e12
+    engine_name = ("eigen" if (args.method == "eigen" or not prob.squaring_ok)
+                   else ("squaring_dfma" if args.method == "squaring_dfma" else "squaring_dmma"))
+    # executed tensor-core flops: (squarings + L - 1) symmetric products of 12 warp tasks x 8 tiles x (np / 4) m8n8k4
+    # (512 flop each); squarings per step is counted by the kernel.  ncu's DMMA instruction count agrees (profiles/).
+    executed = (squarings + L - 1) * 96 * (prob.np // 4) * 512.0 if engine_name == "squaring_dmma" else None
     cpu = None
     if world == 1:
         for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
             os.environ[var] = "1"
-        nref = 2500
-        cpu_val = cpu_port_steps_per_s(wl, nref)
-        cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d MC steps of one chain, oracle port of lib/mc.py loop (scipy expm), same 100x4 workload" % nref}
-    sweeps = float(st["counters"][:, 7].sum()) / max(1.0, float(st["counters"][:, 5].sum()))
+        nref = 4000
+        rate = _single_process_rate(files, nref, 1)
+        kind = "reference" if reference_available() else "port"
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d MC steps of one chain, %s, same 100x4 files, BLAS threads=1" % (
+                   nref, "mcdiff.mc.do_mc_cycles of the unmodified reference (baseline/_ref)" if kind == "reference"
+                   else "oracle port of lib/mc.py (baseline/_ref not installed)"),
+               "cpu_model": cpu_model_string(), "host_cores": os.cpu_count()}
+    kname = "mcd_mc_run_kernel<true>"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -314,28 +577,34 @@ def run_gpu(args):
             "chains_per_gpu": nch, "mc_steps_per_launch": MC_PER_LAUNCH, "mc_steps_per_bench_step": nch * MC_PER_LAUNCH,
             "l2": "256 MiB buffer rewritten between timed launches; working set (160 KB counts + per-chain state) "
                   "is smem/L2 resident by design, the kernel is FP64/shared-memory bound, not HBM bound",
-            "philox_seed": 1, "propagator_engine": ("eigen" if (args.method == "eigen" or not prob.squaring_ok) else ("squaring_dfma" if args.method == "squaring_dfma" else "squaring_dmma")),
-            "jacobi_sweeps_or_squarings_per_mc_step": sweeps, "chains_with_status": bad,
-            "mean_acceptance": float((summary_all[:, 6] + summary_all[:, 7]).sum() / max(1.0, float(world) * st["counters"][:, 5].sum())),
+            "philox_seed": 1, "propagator_engine": engine_name,
+            "jacobi_sweeps_or_squarings_per_mc_step": squarings, "chains_with_status": bad,
+            "mean_acceptance": acc,
+            "value_at_1036_chains_per_gpu": value148,
         },
         "roofline": {"bound": "tensor", "bound_detail": "FP64 tensor pipe (DMMA m8n8k4); same nominal peak as the FP64 vector pipe",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this configuration
-                     # (ncu --set full, profiles/r01_ncu_full_mc_run_final.csv): 4.0 MB
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (nch, MC_PER_LAUNCH) == (1024, 200) else None,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kname) if (nch, MC_PER_LAUNCH) == (1024, 200) else None,
                      "traffic_unit": "bytes of DRAM traffic per launch (ncu); the kernel is not HBM bound",
                      "peak_source": "measured here by mcd_fp64_peak (dense DFMA loop); MEASURED_PEAKS.json has no FP64 "
                                     "figure; nominal 148 SM x 64 DFMA x 2 x 1.965 GHz = 37.2",
-                     "algorithmic_flops_per_mc_step": fl, "kernel": "mcd_mc_run_kernel<true>",
-                     "kernel_ms_per_launch": kernel_ms},
+                     "algorithmic_flops_per_mc_step": fl, "executed_flops_per_mc_step": executed,
+                     "executed_frac": (nch * MC_PER_LAUNCH * executed / (kernel_ms * 1e-3) / 1e12 / peak_tf) if executed else None,
+                     "kernel": kname, "kernel_ms_per_launch": kernel_ms},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_reps, "seconds_per_step": e2e_s,
+                "api": "mcdiff_b200.mc.find_parameters (= run-mcdiff): %d transition files in, .dat/.pic/.pic.ave.dat/"
+                       ".chains.npz out, %d chains x %d MC steps, gathers included" % (L, world * nch, E2E_NMC)},
+        "strong": {"value": strong_value, "unit": UNIT, "chains_total": STRONG_CHAINS, "mc_steps": MC_PER_LAUNCH,
+                   "seconds": strong_s, "api": "find_parameters, fixed total chains over %d GPU(s)" % world},
+        "secondary": secondary,
         "gpu_launches": int(launches),
     }
     print(json.dumps(line), flush=True)
+    shutil.rmtree(tmp, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
 

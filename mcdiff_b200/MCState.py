@@ -19,6 +19,7 @@ from . import _capi as K
 from .model import MODELS_1D, Model, RadCosinusModel, RadModel
 from .outreading import read_Dcoeffs, read_Dradcoeffs, read_Drad, read_Fcoeffs, read_F_D_edges, read_dv_dw
 from .parallel import shard_range
+from .engine import to_host
 
 
 def _string_vecs(n, pbc):
@@ -276,7 +277,7 @@ class MCState:
         ll = self.chains.init_log_like()          # raises ValueError("Initial likelihood diverges") on NaN
         if keep is not None:                      # resumed run: the running value of the chain, not a recomputation
             self.chains.scal[:, 0] = keep
-            ll = keep.cpu().numpy()
+            ll = to_host(keep)
         self.chain_log_like = ll
         self.log_like = float(ll[0]) if len(ll) else float("nan")   # a rank may own no chain (world > nchains)
         print("initial log-likelihood:", self.log_like)
@@ -318,11 +319,11 @@ class MCState:
                                         nsamples_cap=nsamp)
             self.steps_done += nsteps
             self.sync_from_device()
-            return None if smp is None else smp.cpu().numpy()
+            return None if smp is None else to_host(smp)
         _, _, smp = self.chains.run(nsteps, self.mc_params(), nsamples_cap=nsamp)
         self.steps_done += nsteps
         self.sync_from_device()
-        return None if smp is None else smp.cpu().numpy()
+        return None if smp is None else to_host(smp)
 
     def sync_from_device(self):
         st = self.chains.host_state()

@@ -17,6 +17,15 @@ from . import _capi as K
 
 SAMPLE_HEAD = 6  # log_like, timezero, dv, dw, dtimezero, temp
 
+# bytes this layer moved between host and device (bench.py's e2e leg reports them per step)
+TRAFFIC = {"h2d": 0, "d2h": 0}
+
+
+def to_host(t):
+    """Device tensor -> numpy (synchronising copy), counted in TRAFFIC."""
+    TRAFFIC["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
 
 def _dev(t):
     return None if t is None else C.c_void_p(t.data_ptr())
@@ -50,6 +59,8 @@ class Engine:
     def to_device(self, a, dtype):
         """Host array -> device tensor through pinned memory (async on the current stream)."""
         if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                TRAFFIC["h2d"] += a.numel() * a.element_size()
             return a.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
         a = np.ascontiguousarray(a)
         if not a.flags.writeable:
@@ -57,6 +68,7 @@ class Engine:
         t = torch.from_numpy(a)
         if t.dtype != dtype:
             t = t.to(dtype)
+        TRAFFIC["h2d"] += t.numel() * t.element_size()
         return t.pin_memory().to(self.device, non_blocking=True)
 
     def fp64_peak_tflops(self) -> float:
@@ -160,9 +172,9 @@ class DeviceProblem:
                     raise ValueError("lagtimes must be [B][nlag]")
                 d_l = eng.to_device(lt, torch.float64)
             out, P, status = self.loglike_device(d_v, d_w, d_l, want_P, method)
-            ll = out.cpu().numpy()
-            st = status.cpu().numpy()
-            Pn = None if P is None else P.cpu().numpy()
+            ll = to_host(out)
+            st = to_host(status)
+            Pn = None if P is None else to_host(P)
         return ll, Pn, st
 
 
@@ -245,7 +257,7 @@ class ChainBatch:
                     e = e + 0.5 * prob.spring_k * (self.w[:, 0] - self.w[:, -1]) ** 2
                 ll = ll - e
             self.scal[:, K.S_LL] = ll
-            host = ll.cpu().numpy()
+            host = to_host(ll)
         if np.any(np.isnan(host)):
             raise ValueError("Initial likelihood diverges")  # lib/MCState.py:116-117
         return host
@@ -286,11 +298,11 @@ class ChainBatch:
     def host_state(self):
         """Device -> host copy of the whole chain state (one synchronisation)."""
         with torch.cuda.device(self.eng.device):
-            out = dict(v=self.v.cpu().numpy(), w=self.w.cpu().numpy(), scal=self.scal.cpu().numpy(),
-                       counters=self.counters.cpu().numpy(),
-                       vcoef=self.vcoef.cpu().numpy() if self.prob.ncosF else None,
-                       wcoef=self.wcoef.cpu().numpy() if self.prob.ncosD else None,
-                       naccv_coeff=self.naccv_coeff.cpu().numpy(), naccw_coeff=self.naccw_coeff.cpu().numpy())
+            out = dict(v=to_host(self.v), w=to_host(self.w), scal=to_host(self.scal),
+                       counters=to_host(self.counters),
+                       vcoef=to_host(self.vcoef) if self.prob.ncosF else None,
+                       wcoef=to_host(self.wcoef) if self.prob.ncosD else None,
+                       naccv_coeff=to_host(self.naccv_coeff), naccw_coeff=to_host(self.naccw_coeff))
         return out
 
 
@@ -354,7 +366,7 @@ def rad_loglike(eng: Engine, v, w, pbc, lagtimes, counts, bessels, b0zeros, wrad
     prob = RadialProblem(eng, v, w, pbc, lagtimes, counts, bessels, b0zeros, clip=clip)
     with torch.cuda.device(eng.device):
         out, P, status = prob.loglike_device(eng.to_device(wrad, torch.float64), want_P)
-        res = out.cpu().numpy(), (None if P is None else P.cpu().numpy()), status.cpu().numpy()
+        res = to_host(out), (None if P is None else to_host(P)), to_host(status)
     prob.close()
     return res
 
@@ -404,7 +416,7 @@ class RadialChains:
         with torch.cuda.device(eng.device):
             out, _, status = self.prob.loglike_device(self.wrad)
             self.scal[:, 0] = out
-            host = out.cpu().numpy()
+            host = to_host(out)
         if np.any(np.isnan(host)):
             raise ValueError("Initial likelihood diverges")
         return host
@@ -443,5 +455,5 @@ class RadialChains:
 
     def host_state(self):
         with torch.cuda.device(self.eng.device):
-            return dict(wrad=self.wrad.cpu().numpy(), wcoef=self.wcoef.cpu().numpy(), scal=self.scal.cpu().numpy(),
-                        counters=self.counters.cpu().numpy(), nacc_coeff=self.nacc_coeff.cpu().numpy())
+            return dict(wrad=to_host(self.wrad), wcoef=to_host(self.wcoef), scal=to_host(self.scal),
+                        counters=to_host(self.counters), nacc_coeff=to_host(self.nacc_coeff))
