@@ -37,13 +37,16 @@ def _string_vecs(n, pbc):
 
 class MCState:
     def __init__(self, pbc, lmax=-1, nchains=1, device=None, seed=None, rank=0, world=1, method="auto",
-                 jitter=0.0):
+                 jitter=0.0, chain_range=None):
         self.pbc = pbc
         self.lmax = lmax
         self.do_radial = lmax > 0
         self.nchains_total = int(nchains)
         self.rank, self.world = int(rank), int(world)
-        self.chain_lo, self.chain_hi = shard_range(self.nchains_total, self.rank, self.world)
+        # chain_range: an explicit [lo, hi) of the global chain index (lag scans shard (problem, chain) pairs,
+        # parallel.pair_shard), else the block partition of the chains over the ranks
+        self.chain_lo, self.chain_hi = (shard_range(self.nchains_total, self.rank, self.world)
+                                        if chain_range is None else (int(chain_range[0]), int(chain_range[1])))
         self.nchains = self.chain_hi - self.chain_lo
         self.device = device
         self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
@@ -326,7 +329,11 @@ class MCState:
         return None if smp is None else to_host(smp)
 
     def sync_from_device(self):
-        st = self.chains.host_state()
+        self.set_host_state(self.chains.host_state())
+
+    def set_host_state(self, st):
+        """Per-chain arrays + the reference's scalar attributes (from row 0) out of a host_state() dictionary --
+        this rank's chains, or the rows of ALL chains gathered on rank 0 (infty.run_lag_scan)."""
         self.chain_scal, self.chain_counters = st["scal"], st["counters"]
         if self.do_radial:
             m = self.model
@@ -336,7 +343,7 @@ class MCState:
             self.chain_log_like = sc[:, 0].copy()
             self.chain_dwrad, self.chain_temp = sc[:, 1].copy(), sc[:, 2].copy()
             self.chain_naccwrad, self.chain_status = ct[:, 0].copy(), ct[:, 3].copy()
-            if self.nchains == 0:
+            if len(sc) == 0:
                 return
             m.wrad = st["wrad"][0].copy()
             if getattr(m, "ncosDrad", 0) > 0:
@@ -357,7 +364,7 @@ class MCState:
         self.chain_nacctimezero = ct[:, K.C_NACCT0].copy()
         self.chain_status = ct[:, K.C_STATUS].copy()
         self.chain_naccv_coeff, self.chain_naccw_coeff = st["naccv_coeff"], st["naccw_coeff"]
-        if self.nchains == 0:
+        if len(sc) == 0:
             return
         # chain 0 -> the reference's scalar attributes
         m = self.model

@@ -20,6 +20,46 @@ def shard_range(nchains: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def pair_shard(nproblems: int, nchains: int, rank: int, world: int):
+    """Lag scans (BASELINE config 4): the nproblems x nchains (problem, chain) pairs, numbered
+    problem-major, are block-partitioned over the ranks.  Returns [(lo, hi)] per problem: the chains of that
+    problem this rank owns (lo == hi: none)."""
+    glo, ghi = shard_range(int(nproblems) * int(nchains), rank, world)
+    out = []
+    for k in range(int(nproblems)):
+        lo, hi = max(glo, k * nchains), min(ghi, (k + 1) * nchains)
+        out.append((lo - k * nchains, hi - k * nchains) if hi > lo else (0, 0))
+    return out
+
+
+def gather_ranges_to_root(local_rows: np.ndarray, ranges, device=None):
+    """Rows [hi_r - lo_r][k] of every rank r (ranges = [(lo_r, hi_r)] for ALL ranks, disjoint, covering
+    [0, total)) -> [total][k] on rank 0 in global order; None elsewhere.  One gather of equal padded blocks."""
+    import torch
+    import torch.distributed as dist
+    rank, world, on = dist_info()
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
+    if not on or world == 1:
+        return local_rows
+    k = local_rows.shape[1]
+    width = max(1, max(hi - lo for lo, hi in ranges))
+    total = sum(hi - lo for lo, hi in ranges)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    buf = torch.zeros((width, k), dtype=torch.float64, device=device)
+    if local_rows.shape[0] > 0:
+        buf[: local_rows.shape[0]] = torch.from_numpy(local_rows).to(device)
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, parts, dst=0)
+    if rank != 0:
+        return None
+    out = np.empty((total, k))
+    for r, (lo, hi) in enumerate(ranges):
+        if hi > lo:
+            out[lo:hi] = parts[r][: hi - lo].cpu().numpy()
+    return out
+
+
 def dist_info():
     """(rank, world, initialised) from torch.distributed, (0, 1, False) when not initialised."""
     try:

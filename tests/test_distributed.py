@@ -144,3 +144,58 @@ def test_jitter_depends_on_global_chain_only():
     assert not full[0].any() and full[1:].all()
     assert not np.array_equal(full[1], full[2])
     assert not np.array_equal(one._jitter_rows(0, 5)[1], full[1])
+
+
+# ---- lag scan (BASELINE config 4): (problem, chain) pairs block-partitioned over the ranks -------------------
+def test_pair_shard_covers_every_pair_once():
+    from mcdiff_b200.parallel import pair_shard
+    for nprob, nch, world in ((16, 256, 8), (4, 5, 3), (3, 7, 2), (2, 3, 8), (16, 1, 5)):
+        seen = np.zeros((nprob, nch), dtype=int)
+        sizes = []
+        for r in range(world):
+            sh = pair_shard(nprob, nch, r, world)
+            assert len(sh) == nprob
+            sizes.append(sum(hi - lo for lo, hi in sh))
+            for k, (lo, hi) in enumerate(sh):
+                seen[k, lo:hi] += 1
+        assert np.all(seen == 1)
+        assert max(sizes) - min(sizes) <= 1                      # balanced to within one pair
+
+
+def _scan_worker(rank, world, port, nprob, nch, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mcdiff_b200.parallel import gather_ranges_to_root, pair_shard
+    shards = [pair_shard(nprob, nch, r, world) for r in range(world)]
+    got = []
+    for k in range(nprob):
+        lo, hi = shards[rank][k]
+        local = np.stack([np.full(hi - lo, float(k)), np.arange(lo, hi, dtype=np.float64),
+                          np.full(hi - lo, float(rank))], axis=1).reshape(hi - lo, 3)
+        got.append(gather_ranges_to_root(local, [shards[r][k] for r in range(world)], device="cpu"))
+    q.put((rank, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nprob,nch", [(4, 5), (3, 2)])
+def test_gloo_world2_lag_scan_gather(nprob, nch):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scan_worker, args=(r, world, port, nprob, nch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(g is None for g in got[1])                         # rank 0 alone holds the gathered rows
+    half = (nprob * nch + 1) // 2
+    for k, rows in enumerate(got[0]):
+        assert rows.shape == (nch, 3)
+        np.testing.assert_array_equal(rows[:, 0], k)
+        np.testing.assert_array_equal(rows[:, 1], np.arange(nch))          # global chain order within the problem
+        np.testing.assert_array_equal(rows[:, 2], [(0.0 if k * nch + c < half else 1.0) for c in range(nch)])

@@ -99,7 +99,9 @@ def test_exact_resume_from_chainfile(engine, gold_ll, tmp_path, capsys):
     for key in ("scal", "counters", "v", "w", "v_coeff", "w_coeff", "naccv_coeff", "naccw_coeff"):
         np.testing.assert_array_equal(zf[key], zb[key], err_msg=key)
     assert int(zb["steps_done"]) == 200 and int(zb["seed"]) == 9
-    assert open(full).read() == open(b).read()
+    # the final file is the same except for the line that echoes this invocation's --nmc (100 vs 200)
+    strip = lambda fn: [l for l in open(fn).read().splitlines() if not l.startswith("n(MC)=")]  # noqa: E731
+    assert strip(full) == strip(b)
 
 
 def test_per_bin_model_and_nopbc(engine, gold_ll, tmp_path, capsys):

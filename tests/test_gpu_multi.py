@@ -104,3 +104,39 @@ def test_two_ranks_equal_one_rank_other_paths(engine, gold_ll, tmp_path, mode):
         np.testing.assert_array_equal(a[key], b[key])
     assert open(out1).read() == open(out2).read()
     assert open(out1 + ".pic.ave.dat").read() == open(out2 + ".pic.ave.dat").read()
+
+
+def test_lag_scan_two_ranks_equal_one_rank(engine, gold_ll, tmp_path):
+    """BASELINE config 4: the (problem, chain) pairs of a lag scan sharded over two ranks give the files of a
+    one-GPU scan (per-lag .dat of chain 0, every chain's final state, the mcdiff-infty extrapolation)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from mcdiff_b200.transitions import write_Tmat_square
+    G = gold_ll
+    tmp = str(tmp_path)
+    files = []
+    for l, lag in enumerate(G["P_lags"][:3]):
+        fn = os.path.join(tmp, "transitions.nbins100.%d.pbc.dat" % int(lag))
+        write_Tmat_square(G["P_counts"][l], fn, float(lag), "pbc", edges=G["P_edges"], dt=1.0, dn=int(lag))
+        files.append(fn)
+    common = ["--ncosF", "6", "--ncosD", "4", "-n", "200", "--nmc_update", "100", "-T", "1", "--Tend", "1",
+              "--dv", "0.2", "--dw", "0.2", "-s", "21", "--nchains", "5", "hexd"] + files      # 15 pairs: 8 + 7
+    script = os.path.join(ROOT, "scripts", "mcdiff-lagscan")
+    d1, d2 = os.path.join(tmp, "one"), os.path.join(tmp, "two")
+    env = dict(os.environ)
+    r1 = subprocess.run([sys.executable, script, "-o", d1] + common, capture_output=True, text=True, env=env)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                         "--master-addr", "127.0.0.1", "--master-port", "29535", script, "-o", d2] + common,
+                        capture_output=True, text=True, env=env)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    names = ["out.nbins100.%d.pbc.dat" % l for l in (10, 20, 30)] + ["hexd.Dreal.dat", "hexd.t0.dat"]
+    for nm in names:
+        assert open(os.path.join(d1, nm)).read() == open(os.path.join(d2, nm)).read(), nm
+    for nm in names[:3]:
+        a, b = np.load(os.path.join(d1, nm + ".chains.npz")), np.load(os.path.join(d2, nm + ".chains.npz"))
+        assert a["log_like"].shape == (5,)
+        for key in ("log_like", "v", "w", "naccv", "naccw", "status"):
+            np.testing.assert_array_equal(a[key], b[key])
+        assert len(np.unique(a["log_like"])) == 5
