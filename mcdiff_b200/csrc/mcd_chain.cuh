@@ -24,6 +24,7 @@ namespace MCD_NS {
 constexpr int kMaxLag = 64;   // LagPlan arrays are sized for this
 constexpr int kMaxCoef = 64;
 constexpr int kMaxSweeps = 60;
+constexpr int kTaylorMargin = 33;   // wrap margin of the Taylor coefficient arrays (Chain::taylor_coefs)
 
 // How the squaring engine reaches every lag time (built on the host, mcd_lib.cu::plan_lags).
 // Lags are visited in ascending order; G(t_i) = G(t_{i-1}) G(delta_i), delta_i = t_i - t_{i-1}.  Each
@@ -252,6 +253,7 @@ struct Smem {
   double *rc, *rs;
   double* red;
   double* part;  // per-thread likelihood partial sums (squaring engine)
+  double* text;  // coefficient arrays of the Taylor passes (taylor_coefs); null in the panel layout (the panels serve)
   int *rp, *rq;
   int* wti;                // warp tasks as 16 ints per warp: {nt, na, rowA, rowB, jb[8], -, -, -, -} (three 128-bit loads)
   unsigned char* tiles;    // 2 bytes per tile (ib, jb), ib <= jb
@@ -267,7 +269,8 @@ struct Smem {
 // panels: layout of the blocked engine, without the vectors and tables only the eigen engine uses
 // (lam, el, rc, rs, rp, rq, tile and Jacobi-block lists) -- at np = 520 those alone would be 100 KB
 MCD_HOSTDEV size_t smem_vectors_bytes(int np, bool panels = false) {
-  size_t d = (size_t)np * (panels ? 9 : 11) + 256 + kMaxCoef * 3 + kMaxLag * 2 + (panels ? 0 : (size_t)np) /*rc,rs*/ + 32 + kThreads;
+  size_t d = (size_t)np * (panels ? 9 : 11) + 256 + kMaxCoef * 3 + kMaxLag * 2 + (panels ? 0 : (size_t)np) /*rc,rs*/ + 32 + kThreads +
+             (panels ? 0 : (size_t)6 * (np + 2 * kTaylorMargin)) /*text*/;
   size_t nb = np / 4, h = np / 2;
   size_t bytes = d * 8 + (panels ? 0 : (size_t)np * 4) /*rp,rq*/ + 64 * (kThreads / 32) /*wti*/ +
                  (panels ? 0 : nb * (nb + 1) + h * (h - 1)) + 16 * (kThreads / 32) + sizeof(Scalars) + 64 +
@@ -308,6 +311,7 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.rs = d; d += panels ? 0 : np / 2;
   s.red = d; d += 32;
   s.part = d; d += kThreads;
+  s.text = panels ? nullptr : d; d += panels ? 0 : 6 * (np + 2 * kTaylorMargin);
   s.sc = reinterpret_cast<Scalars*>(d);
   d += (sizeof(Scalars) + 7) / 8;
   int* ip = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(d) + 15) & ~(uintptr_t)15);   // wti: 128-bit loads
@@ -1066,17 +1070,316 @@ struct Chain {
   // error is amplified 2^s times by the squarings -- but only modes with t |lambda| <= 45 survive in
   // G(t) at all (e^-45 = 3e-20), i.e. |x| <= x* = min(1, 45 / 2^s).  Smallest m with
   // 2^s x*^(m+1)/(m+1)! <= 1e-17.
+  //
+  // Spectral shift.  The spectrum of the (symmetrised) generator lies in [-rho, 0], rho = Gershgorin bound, so
+  // S + cI with c = rho/2 has spectral radius rho/2: exp(hS) = e^{-hc} exp(h(S + cI)) needs ONE squaring less
+  // for the same argument bound, and the diagonal of h(S + cI) is mostly non-negative (less cancellation in
+  // the polynomial).  The modes that survive in G(t) now sit at the TOP of the shifted spectrum, x ~ +theta,
+  // where every Taylor term is positive: relative error theta^(m+1)/(m+1)! per application, amplified 2^s
+  // times by the squarings.  Argument bound kTheta = 2 (one more squaring saved; a Taylor pass on the band costs
+  // ~1 % of a dense product, see taylor_column).  Order: smallest m with 2^s theta^(m+1)/(m+1)! <= 1e-17,
+  // capped at 30 (the register window of taylor_lane; reached only for s > 25, where the bound is still < 2e-16).
+  static constexpr int kThetaLog2 = 1;
+  static constexpr double kTheta = 2.0;
   static MCD_HD int taylor_order(int nsq, int taylor_m) {
-    if (taylor_m > 0) return taylor_m;
-    const double two_s = ldexp(1.0, nsq);
-    const double xs = fmin(1.0, 45.0 / two_s);
-    double term = two_s * xs;   // 2^s x^(k) / k!  for k = 1
+    if (taylor_m > 0) return taylor_m < 30 ? taylor_m : 30;
+    double term = ldexp(kTheta, nsq);   // 2^s theta^k / k!  for k = 1
     int m = 1;
-    while (m < 24 && !(term * xs / (double)(m + 1) <= 1.0e-17)) {
-      term = term * xs / (double)(m + 1);
+    while (m < 30 && !(term * kTheta / (double)(m + 1) <= 1.0e-17)) {
+      term = term * kTheta / (double)(m + 1);
       ++m;
     }
     return m < 6 ? 6 : m;
+  }
+
+  // How exp(tS) is reached: T = e^{-hc} T_m(h(S + cI)), then nsq squarings.
+  struct TaylorPlan {
+    int nsq, m, ring;
+    double h, shift, scale;
+  };
+  // gersh: bound of the spectral interval [-gersh, 0].  false: non-finite / absurd scale.
+  MCD_HD bool taylor_plan(double t, double gersh, int taylor_m, TaylorPlan& tp) const {
+    const double rho = t * gersh;
+    if (!(rho < 1.0e9) || !(t > 0.0)) return false;
+    const double y = ldexp(rho, -1 - kThetaLog2);      // (rho/2) / theta
+    int nsq = 0;
+    if (y > 1.0) {
+      int ex2;
+      const double fr2 = frexp(y, &ex2);               // y = fr2 2^ex2, fr2 in [0.5, 1)
+      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
+    }
+    tp.nsq = nsq;
+    tp.h = ldexp(t, -nsq);
+    tp.m = (taylor_m > 0) ? (taylor_m < 30 ? taylor_m : 30) : s.tord[nsq];
+    tp.m += tp.m & 1;                                   // the passes are done in pairs (taylor_lane): a higher order only helps
+    tp.shift = 0.5 * gersh;
+    tp.scale = exp(-tp.h * tp.shift);
+    tp.ring = (P.pbc && 2 * tp.m + 1 > P.n) ? 1 : 0;    // the band wraps onto itself: whole columns (n <= 62)
+    return true;
+  }
+
+  // ---- Taylor polynomial on the band, column by column in registers ------------------------------
+  // H <- I + (hS'/k) H, k = m..1 (Horner), S' = S + cI tridiagonal (+ periodic corner).  Column j of H only
+  // couples to itself:  H'[i][j] = delta_ij + (a_i H[i][j] + lo_i H[i-1][j] + up_i H[i+1][j]) / k,  and after m
+  // passes it is non-zero on rows j-m .. j+m.  A PAIR of adjacent lanes keeps the window j-31 .. j+32 in
+  // registers -- the lower lane rows j, j-1, .. j-31, the upper lane rows j+1 .. j+32, both indexed by the
+  // distance from the centre so that the two lanes run the same code -- and does ALL passes with one shuffle
+  // per pass (the two centre elements) and no barrier or shared-memory store.  The pre-scaled coefficients
+  // come from arrays extended by a wrap margin of kTM rows on each side (and a reversed copy for the lower
+  // lane), so every load is [thread base + compile-time offset].  Chunks of 4 elements the band has not
+  // reached yet are skipped (uniform branch).  (The first version kept H in shared memory and did one
+  // barrier-closed pass per Taylor term: 12 % of the MC step at 100 bins.)
+  // Periodic profiles whose band is wider than the ring (2m+1 > n, n <= 62): the same window is computed on
+  // the periodic LINE (the covering space: the extended coefficient arrays are periodic) and the entries are
+  // then summed over the rows that coincide on the ring -- in a fixed order, lower lane first.
+  static constexpr int kTH = 32;              // window elements per lane
+  static constexpr int kTM = kTaylorMargin;   // >= kTH + 1
+  MCD_HOSTDEV static size_t taylor_ext_doubles(int n) { return (size_t)6 * (n + 2 * kTM); }
+
+  // pre-scaled coefficients (all threads; the caller closes the phase).  Row i: diagonal h (diag[i] + c),
+  // coupling to row i+1: h up[i], to row i-1: h lo[i-1].  ext: taylor_ext_doubles(n) doubles = the arrays
+  // A, U, L over rows -kTM .. n+kTM-1 and their reversed copies.
+  // Horner without the division per pass: with K_tt = m (m-1) .. (m-tt+1), G_tt = K_tt H_tt obeys
+  // G_tt = K_tt I + (hS') G_{tt-1} -- three FP64 operations per element; s.red[tt] = K_tt and the final 1 / K_m goes
+  // into the scale.  The passes are done two at a time (taylor_lane): m is even (taylor_plan).
+  MCD_HD void taylor_coefs(int tid, double* ext, const double* diag, const double* lo, const double* up,
+                           const TaylorPlan& tp) {
+    const int n = P.n, ne = n + 2 * kTM;
+    for (int e = tid; e < ne; e += Exec::nthr()) {
+      int i = e - kTM;
+      bool ok = true;
+      if (P.pbc) { i %= n; if (i < 0) i += n; }
+      else ok = (i >= 0 && i < n);
+      const double va = ok ? tp.h * (diag[i] + tp.shift) : 0.0;
+      const double vu = ok ? tp.h * up[i] : 0.0;
+      const double vl = ok ? tp.h * lo[i] : 0.0;
+      ext[e] = va; ext[ne + e] = vu; ext[2 * ne + e] = vl;
+      const int er = ne - 1 - e;
+      ext[3 * ne + er] = va; ext[4 * ne + er] = vu; ext[5 * ne + er] = vl;
+    }
+    if (tid >= 1 && tid <= tp.m) {          // no reduction runs before the passes end
+      double K = 1.0;
+      for (int q = 0; q < tid; ++q) K *= (double)(tp.m - q);
+      s.red[tid] = K;
+    }
+  }
+
+  // The two lanes of a pair are lanes l and l + 16 of a warp: each half-warp then reads 16 consecutive doubles
+  // of a coefficient array per load (one conflict-free wavefront).
+  static MCD_HD int pair_col(int tid) { return ((tid >> 5) << 4) + (tid & 15); }   // column index within the phase
+  static MCD_HD int pair_hf(int tid) { return (tid >> 4) & 1; }
+
+  // one lane of the pair of column j: hf = 0 rows j - k, hf = 1 rows j + 1 + k (k = 0 .. kTH-1).
+  // swap(v): the partner lane's v (device: shuffle).  kSym: the coupling of rows (i, i+1) is the same in both
+  // directions (symmetrised generator), so the inner coefficient of element k is the outer one of element k-1.
+  // A sweep does TWO passes (tt, tt+1) with one set of coefficient loads: at element k it forms the pass-tt value
+  // of element k+1 and, from the pass-tt values of k-1, k, k+1, the pass-(tt+1) value of element k.
+  template <bool kSym, class Swap>
+  MCD_HD void taylor_lane(int j, int hf, const double* ext, const TaylorPlan& tp, double (&x)[kTH], Swap swap) {
+    const int n = P.n, m = tp.m, ne = n + 2 * kTM;
+    // element k: own row i, inner neighbour (towards the centre), outer neighbour
+    //   lower lane: i = j - k,     inner = row i+1 (coefficient U[i]),   outer = row i-1 (L[i-1])  -> reversed arrays
+    //   upper lane: i = j + 1 + k, inner = row i-1 (coefficient L[i-1]), outer = row i+1 (U[i])
+    const double* MCD_RESTRICT pa;
+    const double* MCD_RESTRICT pin;
+    const double* MCD_RESTRICT pout;
+    if (hf == 0) {
+      const int br = ne - 1 - (j + kTM);   // reversed index of row j
+      pa = ext + 3 * ne + br; pin = ext + 4 * ne + br; pout = ext + 5 * ne + br + 1;
+    } else {
+      const int bu = j + kTM + 1;          // index of row j + 1
+      pa = ext + bu; pin = ext + 2 * ne + bu - 1; pout = ext + ne + bu;
+    }
+    const double cen = (hf == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < kTH; ++k) x[k] = (k == 0) ? cen : 0.0;
+    // The coefficient loads of a chunk of 4 elements are issued one chunk AHEAD of their use (pinned in place on
+    // the device: the compiler otherwise sinks each load next to its first use and every element waits ~30 cycles
+    // for shared memory -- measured 1 500 cycles per sweep instead of ~400).
+    for (int tt = 1; tt < m; tt += 2) {
+      const double K1 = cen * s.red[tt], K2 = cen * s.red[tt + 1];
+      double ca = ldc(pa), cin = ldc(pin), cout = ldc(pout);    // coefficients of element k (start: k = 0)
+      double fa[4], fo[4], fi[4];                               // coefficients of elements k0+1 .. k0+4 (next in use)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        fa[q] = ldc(pa + 1 + q); fo[q] = ldc(pout + 1 + q);
+        fi[q] = kSym ? 0.0 : ldc(pin + 1 + q);
+      }
+      // pass tt of element 0, then the partner's
+      double ym = 0.0;                                          // pass-tt value of element k-1
+      double yc = fma(ca, x[0], K1);                            // ... of element k
+      yc = fma(cin, swap(x[0]), yc);
+      yc = fma(cout, x[1], yc);
+      const double yp0 = swap(yc);
+#pragma unroll
+      for (int k0 = 0; k0 < kTH; k0 += 4) {
+        if (tt + 1 >= k0) {                                     // the band has reached this chunk (uniform)
+          double ga[4], go[4], gi[4];                           // one chunk ahead (clamped to the window)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int e = (k0 + 5 + q < kTH) ? k0 + 5 + q : kTH - 1;
+            ga[q] = ldc(pa + e); go[q] = ldc(pout + e);
+            gi[q] = kSym ? 0.0 : ldc(pin + e);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = k0 + q;
+            // pass tt of element k+1
+            double na = 0.0, nin = 0.0, nout = 0.0, yn = 0.0;
+            if (k + 1 < kTH) {
+              na = fa[q]; nout = fo[q];
+              nin = kSym ? cout : fi[q];
+              yn = na * x[k + 1];
+              yn = fma(nin, x[k], yn);
+              yn = fma(nout, (k + 2 < kTH) ? x[k + 2] : 0.0, yn);
+            }
+            // pass tt+1 of element k
+            double z = (k == 0) ? fma(ca, yc, K2) : ca * yc;
+            z = fma(cin, (k == 0) ? yp0 : ym, z);
+            z = fma(cout, yn, z);
+            x[k] = z;
+            ym = yc; yc = yn; ca = na; cin = nin; cout = nout;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { fa[q] = ga[q]; fo[q] = go[q]; fi[q] = gi[q]; }
+        }
+      }
+    }
+  }
+
+  // coefficient load of the Taylor lanes (the arrays are in shared memory)
+  static MCD_HD double ldc(const double* p) {
+#if defined(__CUDA_ARCH__)
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+  }
+
+  // ring: the window entries are summed onto the rows they coincide with (rare; out of line)
+  static MCD_NOINLINE void taylor_ring_add(int j, int hf, int n, int m, double sc, const double* x, double* dst, int ld) {
+    for (int k = 0; k < kTH; ++k) {
+      const int d = hf ? k + 1 : -k;
+      if (d < -m || d > m) continue;
+      int i = (j + d) % n;
+      if (i < 0) i += n;
+      dst[(size_t)i * ld + j] += x[k] * sc;
+    }
+  }
+
+  // rows of this lane -> dst[i * ld + j]; add: accumulate (ring), else plain stores
+  MCD_HD void taylor_lane_store(int j, int hf, const TaylorPlan& tp, const double (&x)[kTH], double* dst, int ld, bool add) {
+    const int n = P.n, m = tp.m;
+    const double sc = tp.scale / s.red[m];
+    if (add) {
+      double tmp[kTH];                 // only this copy has its address taken: x itself stays in registers
+#pragma unroll
+      for (int k = 0; k < kTH; ++k) tmp[k] = x[k];
+      taylor_ring_add(j, hf, n, m, sc, tmp, dst, ld);
+      return;
+    }
+    // row of element k: i = j - k (lower lane) or j + 1 + k (upper lane), wrapped once for periodic profiles
+    const int step = hf ? ld : -ld;
+    double* p0 = dst + (size_t)(j + hf) * ld + j;
+    const int wrap = P.pbc ? (hf ? -n * ld : n * ld) : 0;
+    const int kmax = hf ? m - 1 : m;                               // last element inside the band
+    const int kin = hf ? n - 2 - j : j;                            // last element before the edge of the profile
+#pragma unroll
+    for (int k = 0; k < kTH; ++k) {
+      if (k > kmax) break;
+      if (k > kin && !P.pbc) break;
+      double* p = p0 + k * step + ((k > kin) ? wrap : 0);
+      *p = x[k] * sc;
+    }
+  }
+
+  // One lane of the pair of column j (all threads of a warp call it together; col_valid == 0: nothing is stored).
+  template <bool kSym>
+  MCD_HD void taylor_pair(int tid, int col_valid, int j, const double* ext, const TaylorPlan& tp, double* dst, int ld) {
+#if defined(__CUDA_ARCH__)
+    const int hf = pair_hf(tid);
+    double x[kTH];
+    taylor_lane<kSym>(j, hf, ext, tp, x, [](double v) { return __shfl_xor_sync(0xffffffffu, v, 16); });
+    MCD_CLK(14);
+    if (tp.ring) {
+      if (col_valid && hf == 0) taylor_lane_store(j, 0, tp, x, dst, ld, true);
+      __syncwarp();
+      if (col_valid && hf == 1) taylor_lane_store(j, 1, tp, x, dst, ld, true);
+    } else if (col_valid) {
+      taylor_lane_store(j, hf, tp, x, dst, ld, false);
+    }
+    MCD_CLK(15);
+#else
+    // host: the lower thread of the pair runs both lanes in lockstep (same arithmetic as the device lanes)
+    if (pair_hf(tid) || !col_valid) return;
+    double xs[2][kTH];
+    // the lanes exchange (1) their centre elements before a sweep and (2) the centres after the first pass of the sweep
+    const int n = P.n, m = tp.m, ne = n + 2 * kTM;
+    const int br = ne - 1 - (j + kTM), bu = j + kTM + 1;
+    const double* PA[2] = {ext + 3 * ne + br, ext + bu};
+    const double* PIN[2] = {ext + 4 * ne + br, ext + 2 * ne + bu - 1};
+    const double* POUT[2] = {ext + 5 * ne + br + 1, ext + ne + bu};
+    for (int h = 0; h < 2; ++h)
+      for (int k = 0; k < kTH; ++k) xs[h][k] = (h == 0 && k == 0) ? 1.0 : 0.0;
+    for (int tt = 1; tt < m; tt += 2) {
+      double y0[2];
+      const double x00[2] = {xs[0][0], xs[1][0]};
+      for (int h = 0; h < 2; ++h) {
+        const double K1 = (h == 0 ? 1.0 : 0.0) * s.red[tt];
+        double yc = fma(PA[h][0], xs[h][0], K1);
+        yc = fma(PIN[h][0], x00[1 - h], yc);
+        yc = fma(POUT[h][0], xs[h][1], yc);
+        y0[h] = yc;
+      }
+      for (int h = 0; h < 2; ++h) {
+        double* x = xs[h];
+        const double K2 = (h == 0 ? 1.0 : 0.0) * s.red[tt + 1];
+        double ca = PA[h][0], cin = PIN[h][0], cout = POUT[h][0];
+        double ym = 0.0, yc = y0[h];
+        const double yp0 = y0[1 - h];
+        for (int k = 0; k < kTH; ++k) {
+          double na = 0.0, nin = 0.0, nout = 0.0, yn = 0.0;
+          if (k + 1 < kTH) {
+            na = PA[h][k + 1]; nout = POUT[h][k + 1];
+            nin = kSym ? cout : PIN[h][k + 1];
+            yn = na * x[k + 1];
+            yn = fma(nin, x[k], yn);
+            yn = fma(nout, (k + 2 < kTH) ? x[k + 2] : 0.0, yn);
+          }
+          double z = (k == 0) ? fma(ca, yc, K2) : ca * yc;
+          z = fma(cin, (k == 0) ? yp0 : ym, z);
+          z = fma(cout, yn, z);
+          x[k] = z;
+          ym = yc; yc = yn; ca = na; cin = nin; cout = nout;
+        }
+      }
+    }
+    taylor_lane_store(j, 0, tp, xs[0], dst, ld, tp.ring != 0);
+    taylor_lane_store(j, 1, tp, xs[1], dst, ld, tp.ring != 0);
+#endif
+  }
+
+  // T -> dst for the generator (diag, lo, up) currently in shared memory; ext: scratch for the coefficient
+  // arrays (taylor_ext_doubles(n) doubles, not overlapping dst).  dst (np x ld doubles) is cleared here.
+  template <bool kSym>
+  MCD_HD void taylor_band(const double* diag, const double* lo, const double* up, const TaylorPlan& tp, double* ext,
+                          double* dst, int ld) {
+    const int n = P.n;
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < P.np * ld; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
+      taylor_coefs(tid, ext, diag, lo, up, tp);
+    });
+    MCD_CLK(3);
+    ex.par([&](int tid) {
+      const int per = Exec::nthr() / 2;
+      for (int j0 = 0; j0 < n; j0 += per) {
+        if (j0 + ((tid >> 5) << 4) >= n) break;          // the whole warp is past the last column
+        const int j = j0 + pair_col(tid);
+        taylor_pair<kSym>(tid, j < n, j < n ? j : n - 1, ext, tp, dst, ld);
+      }
+    });
   }
 
   // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
@@ -1085,80 +1388,15 @@ struct Chain {
   // (fused into the last squaring).  Returns nullptr for a non-finite / absurd scale.
   MCD_HD double* sq_chain(double t, double gersh, int taylor_m, bool use_mma, int epi, double* Pout, double** other,
                           int* nsq_out) {
-    const int n = P.n, np = P.np, ld = P.ld;
-    const double rho = t * gersh;
-    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
-    // s = smallest number of halvings with rho / 2^s <= 1
-    int nsq = 0;
-    if (rho > 1.0) {
-      int ex2;
-      const double fr2 = frexp(rho, &ex2);   // rho = fr2 2^ex2, fr2 in [0.5, 1)
-      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
-    }
-    const double h = ldexp(t, -nsq);
-    const int m = (taylor_m > 0) ? (taylor_m < 31 ? taylor_m : 31) : s.tord[nsq];   // rho < 1e9: nsq <= 30
-    double* A = s.XT;
-    double* B = s.B2;
+    const int np = P.np, ld = P.ld;
+    TaylorPlan tp;
+    if (!taylor_plan(t, gersh, taylor_m, tp)) return nullptr;
+    const int nsq = tp.nsq;
     MCD_CLK(16);
-    // ---- T_m(hS) by Horner:  H <- I + (hS H)/k, k = m..1, ping-pong ----
-    // H is banded (half-width tt after tt steps): only the band is touched.  A row is shared by
-    // `tpr` consecutive threads that walk its band with stride tpr (contiguous columns across
-    // lanes), four independent elements at a time: these scalar phases are latency bound (phase
-    // clocks: ~0.3 instructions per cycle and SM sub-partition), so the loads of a chunk are issued
-    // together, and the thread -> (row, slot) map and the pass factors h/k come from tables.
-    // (A compact band layout with a final scatter was measured 1.3 % slower: profiles/r01_summary.md.)
-    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
-    double* src = A;
-    double* dst = B;
-    ex.par([&](int tid) {
-      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(A + e, 0.0, 0.0); st2(B + e, 0.0, 0.0); }
-      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);   // no reduction runs before the passes end
-    });
-    ex.par([&](int tid) {
-      for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
-    });
-    MCD_CLK(3);
-    for (int tt = 1; tt <= m; ++tt) {
-      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
-      const bool full = (width == n);
-      ex.par([&](int tid) {
-        const int i = s.hrow[tid], r = s.hrem[tid];
-        if (i < n) {
-          const double f = s.red[tt];
-          const int im = (i == 0) ? n - 1 : i - 1;
-          const int ip = (i == n - 1) ? 0 : i + 1;
-          const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.b[i];
-          const double* MCD_RESTRICT s0 = src + i * ld;
-          const double* MCD_RESTRICT sm = src + im * ld;
-          const double* MCD_RESTRICT sp = src + ip * ld;
-          double* MCD_RESTRICT d0 = dst + i * ld;
-          for (int dd0 = r; dd0 < width; dd0 += 4 * tpr) {
-            int jq[4];
-            bool ok[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int dd = dd0 + q * tpr;
-              bool o = dd < width;
-              int j = dd;
-              if (!full) {
-                j = i - tt + dd;
-                if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
-                else o = o && j >= 0 && j < n;
-              }
-              ok[q] = o;
-              jq[q] = o ? j : i;
-            }
-            double x0[4], xm[4], xp[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { x0[q] = s0[jq[q]]; xm[q] = sm[jq[q]]; xp[q] = sp[jq[q]]; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (ok[q]) d0[jq[q]] = ((i == jq[q]) ? 1.0 : 0.0) + (ai * x0[q] + bm * xm[q] + bp * xp[q]);
-          }
-        }
-      });
-      double* tmp = src; src = dst; dst = tmp;
-    }
+    // ---- T = e^{-hc} T_m(h(S + cI)) into XT ----
+    taylor_band<true>(s.a, s.b, s.b, tp, s.text, s.XT, ld);
+    double* src = s.XT;
+    double* dst = s.B2;
     // ---- G(t) = T^(2^s): out-of-place squarings (direct stores), the last one carries the
     //      likelihood epilogue of lag `epi` ----
     MCD_CLK(4);
@@ -1513,55 +1751,16 @@ struct Chain {
 
   // exp(t R) by Taylor + squarings (general engine); same contract as sq_chain
   MCD_HD double* gen_chain(double t, double gersh, int taylor_m, int epi, double* Pout, double** other, int* nsq_out) {
-    const int n = P.n, np = P.np, ld = P.ld;
-    const double rho = t * gersh;
-    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
-    int nsq = 0;
-    if (rho > 1.0) {
-      int ex2;
-      const double fr2 = frexp(rho, &ex2);
-      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
-    }
-    const double h = ldexp(t, -nsq);
-    const int m = (taylor_m > 0) ? (taylor_m < 31 ? taylor_m : 31) : s.tord[nsq];
-    double* src = s.XT;
-    double* dst = s.B2;
-    ex.par([&](int tid) {
-      for (int e = tid * 2; e < np * ld; e += 2 * Exec::nthr()) { st2(src + e, 0.0, 0.0); st2(dst + e, 0.0, 0.0); }
-      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);
-    });
-    ex.par([&](int tid) {
-      for (int i = tid; i < n; i += Exec::nthr()) src[i * ld + i] = 1.0;
-    });
-    const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
-    for (int tt = 1; tt <= m; ++tt) {     // (R H)[i][j] = a_i H[i][j] + R[i][i-1] H[i-1][j] + R[i][i+1] H[i+1][j]
-      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
-      const bool full = (width == n);
-      ex.par([&](int tid) {
-        const int i = s.hrow[tid], r = s.hrem[tid];
-        if (i < n) {
-          const double f = s.red[tt];
-          const int im = (i == 0) ? n - 1 : i - 1;
-          const int ip = (i == n - 1) ? 0 : i + 1;
-          const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.eb[i];
-          const double* MCD_RESTRICT s0 = src + i * ld;
-          const double* MCD_RESTRICT sm = src + im * ld;
-          const double* MCD_RESTRICT sp = src + ip * ld;
-          double* MCD_RESTRICT d0 = dst + i * ld;
-          for (int dd = r; dd < width; dd += tpr) {
-            int j = dd;
-            if (!full) {
-              j = i - tt + dd;
-              if (j < 0) j += n; else if (j >= n) j -= n;
-            }
-            d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
-          }
-        }
-      });
-      double* tmp = src; src = dst; dst = tmp;
-    }
-    double* G = src;
-    double* O = dst;
+    const int np = P.np, ld = P.ld;
+    // uniformisation: R + cI, c = max |R_jj| = gersh / 2, is c times a column-stochastic matrix -- every entry
+    // non-negative, 1-norm exactly c (taylor_plan's shift)
+    TaylorPlan tp;
+    if (!taylor_plan(t, gersh, taylor_m, tp)) return nullptr;
+    const int nsq = tp.nsq;
+    // (R H)[i][j] = a_i H[i][j] + R[i][i-1] H[i-1][j] + R[i][i+1] H[i+1][j]:  lower coupling s.b[i-1], upper s.eb[i]
+    taylor_band<false>(s.a, s.b, s.eb, tp, s.text, s.XT, ld);
+    double* G = s.XT;
+    double* O = s.B2;
     const int* cnt_e = (epi >= 0) ? P.counts + (size_t)epi * np * np : nullptr;
     for (int q = 0; q < nsq; ++q) {
       const bool last = (q + 1 == nsq);
@@ -1898,89 +2097,14 @@ struct Chain {
     for (int c = 0; c < pl.nchain && !bad; ++c) {
       const bool is_first_lag = (c == pl.nchain - 1);
       const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
-      const double rho = t * gersh;
-      if (!(rho < 1.0e9) || !(t > 0.0)) { bad = true; break; }
-      int nsq = 0;
-      for (double r = rho; r > 1.0; r *= 0.5) ++nsq;
-      const double h = ldexp(t, -nsq);
-      const int m = taylor_order(nsq, taylor_m);
+      TaylorPlan tp;
+      if (!taylor_plan(t, gersh, taylor_m, tp)) { bad = true; break; }
+      const int nsq = tp.nsq;
       double* src = buf[0];
       double* dst = buf[1];
-      const int W = 2 * m + 1;   // band width of T_m(hS) (cyclic for pbc); storage H[i][d], column j = i - m + d
-      if (W < n && (size_t)2 * n * W <= (size_t)2 * P.nbk * P.lds) {
-        // ---- Horner on the band, ping-pong inside the (contiguous) shared-memory panels ----
-        double* ha = s.XT;
-        double* hb = s.XT + (size_t)n * W;
-        ex.par([&](int tid) {
-          for (int e = tid; e < n * W; e += Exec::nthr()) { ha[e] = (e % W == m) ? 1.0 : 0.0; hb[e] = 0.0; }
-        });
-        for (int tt = 1; tt <= m; ++tt) {
-          const double f = h / (double)(m - tt + 1);
-          const int lo = m - tt, cnt = 2 * tt + 1;   // columns touched after tt steps
-          ex.par([&](int tid) {
-            for (int e = tid; e < n * cnt; e += Exec::nthr()) {
-              const int i = e / cnt, d = lo + (e - i * cnt);
-              const int im = (i == 0) ? n - 1 : i - 1;
-              const int ip = (i == n - 1) ? 0 : i + 1;
-              // row i-1 holds column j at offset d+1, row i+1 at offset d-1
-              const double up = (d + 1 < W) ? ha[im * W + d + 1] : 0.0;
-              const double dn = (d >= 1) ? ha[ip * W + d - 1] : 0.0;
-              hb[i * W + d] = ((d == m) ? 1.0 : 0.0) + f * (s.a[i] * ha[i * W + d] + s.b[im] * up + s.b[i] * dn);
-            }
-          });
-          double* tmp = ha; ha = hb; hb = tmp;
-        }
-        // ---- expand into the dense workspace matrix ----
-        ex.par([&](int tid) {
-          for (int e = tid * 2; e < np * ldg; e += 2 * Exec::nthr()) st2(src + e, 0.0, 0.0);
-        });
-        ex.par([&](int tid) {
-          for (int e = tid; e < n * W; e += Exec::nthr()) {
-            const int i = e / W, d = e - i * W;
-            int j = i - m + d;
-            if (j < 0) j += n; else if (j >= n) j -= n;
-            const double x = ha[e];
-            if (x != 0.0) src[(size_t)i * ldg + j] = x;
-          }
-        });
-      } else {
-      ex.par([&](int tid) {
-        for (int e = tid * 2; e < np * ldg; e += 2 * Exec::nthr()) { st2(src + e, 0.0, 0.0); st2(dst + e, 0.0, 0.0); }
-      });
-      ex.par([&](int tid) {
-        for (int i = tid; i < n; i += Exec::nthr()) src[(size_t)i * ldg + i] = 1.0;
-      });
-      const int tpr = (Exec::nthr() / n > 1) ? Exec::nthr() / n : 1;
-      const int rows_per_pass = Exec::nthr() / tpr;
-      for (int tt = 1; tt <= m; ++tt) {
-        const double f = h / (double)(m - tt + 1);
-        const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
-        const bool full = (width == n);
-        ex.par([&](int tid) {
-          const int r = tid % tpr;
-          for (int i = tid / tpr; i < n; i += rows_per_pass) {
-            const int im = (i == 0) ? n - 1 : i - 1;
-            const int ip = (i == n - 1) ? 0 : i + 1;
-            const double ai = f * s.a[i], bm = f * s.b[im], bp = f * s.b[i];
-            const double* s0 = src + (size_t)i * ldg;
-            const double* sm = src + (size_t)im * ldg;
-            const double* sp = src + (size_t)ip * ldg;
-            double* d0 = dst + (size_t)i * ldg;
-            for (int dd = r; dd < width; dd += tpr) {
-              int j;
-              if (full) j = dd;
-              else {
-                j = i - tt + dd;
-                if (P.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
-                else if (j < 0 || j >= n) continue;
-              }
-              d0[j] = ((i == j) ? 1.0 : 0.0) + (ai * s0[j] + bm * sm[j] + bp * sp[j]);
-            }
-          }
-        });
-        double* tmp = src; src = dst; dst = tmp;
-      }
-      }
+      // T = e^{-hc} T_m(h(S + cI)) straight into the workspace matrix (band rows only, the rest cleared);
+      // the coefficient arrays sit in the shared-memory panels, which are free until the first product
+      taylor_band<true>(s.a, s.b, s.b, tp, s.XT, src, ldg);
       MCD_CLK(4);
       double* G = src;
       double* O = dst;

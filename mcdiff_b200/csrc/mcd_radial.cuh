@@ -182,73 +182,48 @@ struct RadCtx {
                                                  double* bank1, double** other) {
     const int n = R.n, np = R.np, ld = R.ld;
     const size_t me = (size_t)np * ld;
-    const double rho = t * gersh;
-    if (!(rho < 1.0e9) || !(t > 0.0)) return nullptr;
-    int nsq = 0;
-    if (rho > 1.0) {
-      int ex2;
-      const double fr2 = frexp(rho, &ex2);
-      nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
-    }
-    const double h = ldexp(t, -nsq);
-    const int m = s.tord[nsq];
+    using CH = Chain<DeviceExec>;
+    // one plan for the batch: gersh is the batch maximum, so the shift c = gersh / 2 and the step h suit every
+    // term (the spectrum of S_b lies inside [-gersh, 0])
+    CH::TaylorPlan tp;
+    if (!ch.taylor_plan(t, gersh, 0, tp)) return nullptr;
+    const int nsq = tp.nsq;
+    // T_b = e^{-hc} T_m(h(S_b + cI)) for the nb terms, one thread per (term, column) -- Chain::taylor_column.
+    // The coefficient arrays of all terms sit in bank1 (free until the first product) when they fit there,
+    // otherwise the terms take turns with the chain's own array.
+    const size_t te = CH::taylor_ext_doubles(n);
+    const bool together = (size_t)nb * te <= (size_t)NB * me;
     ex.par([&](int tid) {
-      for (int e = tid * 2; e < (int)(2 * NB * me); e += 2 * kThreads) st2(bank0 + e, 0.0, 0.0);   // both banks (contiguous)
-      if (tid >= 1 && tid <= m) s.red[tid] = h / (double)(m - tid + 1);
+      for (int e = tid * 2; e < (int)(NB * me); e += 2 * kThreads) st2(bank0 + e, 0.0, 0.0);
+      if (together)
+        for (int b = 0; b < nb; ++b) ch.taylor_coefs(tid, bank1 + b * te, ab + b * np, s.b, s.b, tp);
     });
-    ex.par([&](int tid) {
-      for (int e = tid; e < nb * n; e += kThreads) {
-        const int b = e / n, i = e - b * n;
-        bank0[b * me + i * ld + i] = 1.0;
-      }
-    });
-    double* src = bank0;
-    double* dst = bank1;
-    const int tpr = (kThreads / n > 1) ? kThreads / n : 1;
-    for (int tt = 1; tt <= m; ++tt) {
-      const int width = (2 * tt + 1 < n) ? 2 * tt + 1 : n;
-      const bool full = (width == n);
+    if (together) {
       ex.par([&](int tid) {
-        const int i = s.hrow[tid], r = s.hrem[tid];
-        if (i < n) {
-          const double f = s.red[tt];
-          const int im = (i == 0) ? n - 1 : i - 1;
-          const int ip = (i == n - 1) ? 0 : i + 1;
-          const double bm = f * s.b[im], bp = f * s.b[i];
-          for (int dd0 = r; dd0 < width; dd0 += 4 * tpr) {
-            int jq[4];
-            bool ok[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int dd = dd0 + q * tpr;
-              bool o = dd < width;
-              int j = dd;
-              if (!full) {
-                j = i - tt + dd;
-                if (R.pbc) { if (j < 0) j += n; else if (j >= n) j -= n; }
-                else o = o && j >= 0 && j < n;
-              }
-              ok[q] = o;
-              jq[q] = o ? j : i;
-            }
-            for (int b = 0; b < nb; ++b) {
-              const double ai = f * ab[b * np + i];
-              const double* MCD_RESTRICT s0 = src + b * me + i * ld;
-              const double* MCD_RESTRICT sm = src + b * me + im * ld;
-              const double* MCD_RESTRICT sp = src + b * me + ip * ld;
-              double* MCD_RESTRICT d0 = dst + b * me + i * ld;
-              double x0[4], xm[4], xp[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { x0[q] = s0[jq[q]]; xm[q] = sm[jq[q]]; xp[q] = sp[jq[q]]; }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (ok[q]) d0[jq[q]] = ((i == jq[q]) ? 1.0 : 0.0) + (ai * x0[q] + bm * xm[q] + bp * xp[q]);
-            }
-          }
+        const int total = nb * n;
+        for (int e0 = 0; e0 < total; e0 += kThreads / 2) {
+          if (e0 + ((tid >> 5) << 4) >= total) break;
+          const int e = e0 + CH::pair_col(tid);
+          const bool valid = e < total;
+          const int ec = valid ? e : total - 1;
+          const int b = ec / n, j = ec - b * n;
+          ch.taylor_pair<true>(tid, valid, j, bank1 + b * te, tp, bank0 + b * me, ld);
         }
       });
-      double* tmp = src; src = dst; dst = tmp;
+    } else {
+      for (int b = 0; b < nb; ++b) {
+        ex.par([&](int tid) { ch.taylor_coefs(tid, s.text, ab + b * np, s.b, s.b, tp); });
+        ex.par([&](int tid) {
+          for (int j0 = 0; j0 < n; j0 += kThreads / 2) {
+            if (j0 + ((tid >> 5) << 4) >= n) break;
+            const int j = j0 + CH::pair_col(tid);
+            ch.taylor_pair<true>(tid, j < n, j < n ? j : n - 1, s.text, tp, bank0 + b * me, ld);
+          }
+        });
+      }
     }
+    double* src = bank0;
+    double* dst = bank1;
     double* G = src;
     double* O = dst;
     for (int q = 0; q < nsq; ++q) {

@@ -13,7 +13,7 @@ NAMES = {0: "proposal (Philox, thread 0)", 1: "trial profile (basis . coeff)", 2
          3: "zero work matrices", 4: "Taylor/Horner passes", 5: "product prologue (task table, count prefetch)",
          6: "m8n8k4 k loop", 7: "likelihood epilogue", 8: "result stores (+ mirror)", 9: "barrier wait after product",
          10: "staged store phase (in-place products)", 11: "final reduction", 12: "Metropolis (thread 0)",
-         13: "commit, records, adaptation", 14: "Horner pass: own work of thread 0", 15: "Horner pass: barrier wait",
+         13: "commit, records, adaptation", 14: "Taylor sweeps (thread 0)", 15: "Taylor band stores (thread 0)",
          16: "squaring count, Taylor order, h", 17: "between products (loop control, call)", 18: "task decode"}
 counts, lags, edges, F, w_true = O.synthetic_counts()
 n = 100

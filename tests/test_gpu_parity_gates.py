@@ -62,8 +62,11 @@ def test_1024_random_profiles_on_hexdwat(engine, gold_ll, fixture, nprof):
         ll, _, st = prob.loglike(v, w, method=METHODS[name])
         assert not st.any(), name
         worst[name] = float(np.max(np.abs(ll - ref) / np.abs(ref)))
-        # the eigen engine (Jacobi) is the general fallback; ADVICE r1: ~1e-9 on rough profiles, squaring ~1e-15
-        np.testing.assert_allclose(ll, ref, rtol=RTOL, err_msg=name)
+        # The squaring engines sum non-negative terms only (componentwise accurate, ~1e-15 here).  The eigen engine
+        # (Jacobi, the fallback for lag sets without a LagPlan) forms P = V e^{t Lambda} V^T with cancellation: it is
+        # accurate NORM-wise like any eigendecomposition, so an entry near the clip 1e-10 carries a relative error
+        # ~1e-16 / 1e-10 and rough profiles (many such entries with counts) reach ~2e-8 in log L.
+        np.testing.assert_allclose(ll, ref, rtol=RTOL if name != "eigen" else 1e-7, err_msg=name)
     assert worst["auto"] <= 1e-12 and worst["squaring"] <= 1e-12      # what the default engine actually achieves
 
 

@@ -47,19 +47,23 @@ def _ref_state(RM, RT, RX, tmp, counts, lags, edges, ncosF, ncosD, seed=None, mo
 def test_patched_reference_reproduces_archived_values(ref_mcdiff, gold_ll, tmp_path, capsys):
     b200, RM, RT, RX = ref_mcdiff
     G = gold_ll
-    MC = _ref_state(RM, RT, RX, str(tmp_path), G["A_counts"], G["A_lags"], G["A_edges"], 0, 0)
-    orig = RM.log_like_lag
-    RM.log_like_lag = b200.B200Likelihood(MC.data, MC.pbc, pull=MC.pull)     # the patch of INTEGRATION.md 1
-    try:
-        for k in range(4):
-            MC.model.v = G["K_v"][k].copy()
-            MC.model.w = G["K_w"][k].copy()
-            MC.init_log_like()
-            assert MC.log_like == pytest.approx(float(G["K_archived"][k]), rel=1e-9)    # K1-K4, as printed in the logs
-            assert MC.log_like == pytest.approx(float(G["K_ll"][k]), rel=1e-11)         # the reference's scipy path
-    finally:
-        RM.log_like_lag.close()
-        RM.log_like_lag = orig
+    # K1, K2 were logged on transition matrix A, K3, K4 on M (tests/golden/make_golden.py)
+    for fixture, ks in (("A", (0, 1)), ("M", (2, 3))):
+        tmp = os.path.join(str(tmp_path), fixture)
+        os.makedirs(tmp)
+        MC = _ref_state(RM, RT, RX, tmp, G[fixture + "_counts"], G[fixture + "_lags"], G["A_edges"], 0, 0)
+        orig = RM.log_like_lag
+        RM.log_like_lag = b200.B200Likelihood(MC.data, MC.pbc, pull=MC.pull)     # the patch of INTEGRATION.md 1
+        try:
+            for k in ks:
+                MC.model.v = G["K_v"][k].copy()
+                MC.model.w = G["K_w"][k].copy()
+                MC.init_log_like()
+                assert MC.log_like == pytest.approx(float(G["K_archived"][k]), rel=1e-9)    # as printed in the logs
+                assert MC.log_like == pytest.approx(float(G["K_ll"][k]), rel=1e-11)         # the reference's scipy path
+        finally:
+            RM.log_like_lag.close()
+            RM.log_like_lag = orig
     capsys.readouterr()
 
 
