@@ -1258,33 +1258,28 @@ struct Chain {
 #endif
   }
 
-  // ring: the window entries are summed onto the rows they coincide with (rare; out of line)
-  static MCD_NOINLINE void taylor_ring_add(int j, int hf, int n, int m, double sc, const double* x, double* dst, int ld) {
-    for (int k = 0; k < kTH; ++k) {
-      const int d = hf ? k + 1 : -k;
-      if (d < -m || d > m) continue;
-      int i = (j + d) % n;
-      if (i < 0) i += n;
-      dst[(size_t)i * ld + j] += x[k] * sc;
-    }
-  }
-
-  // rows of this lane -> dst[i * ld + j]; add: accumulate (ring), else plain stores
+  // rows of this lane -> dst[i * ld + j]; add: accumulate (ring: window entries that coincide on the ring are
+  // summed; the row of element k walks around the ring one step per element), else plain stores
   MCD_HD void taylor_lane_store(int j, int hf, const TaylorPlan& tp, const double (&x)[kTH], double* dst, int ld, bool add) {
     const int n = P.n, m = tp.m;
     const double sc = tp.scale / s.red[m];
+    const int kmax = hf ? m - 1 : m;                               // last element inside the band
     if (add) {
-      double tmp[kTH];                 // only this copy has its address taken: x itself stays in registers
+      int i = hf ? j + 1 : j;                                      // row of element 0
+      if (i >= n) i -= n;
 #pragma unroll
-      for (int k = 0; k < kTH; ++k) tmp[k] = x[k];
-      taylor_ring_add(j, hf, n, m, sc, tmp, dst, ld);
+      for (int k = 0; k < kTH; ++k) {
+        if (k > kmax) break;
+        dst[(size_t)i * ld + j] += x[k] * sc;
+        if (hf) { if (++i >= n) i = 0; }
+        else { if (--i < 0) i = n - 1; }
+      }
       return;
     }
     // row of element k: i = j - k (lower lane) or j + 1 + k (upper lane), wrapped once for periodic profiles
     const int step = hf ? ld : -ld;
     double* p0 = dst + (size_t)(j + hf) * ld + j;
     const int wrap = P.pbc ? (hf ? -n * ld : n * ld) : 0;
-    const int kmax = hf ? m - 1 : m;                               // last element inside the band
     const int kin = hf ? n - 2 - j : j;                            // last element before the edge of the profile
 #pragma unroll
     for (int k = 0; k < kTH; ++k) {

@@ -19,6 +19,13 @@ size_t mcd128_smem_bytes(int np, int ld);
 int mcd128_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
                          double* gws, cudaStream_t st);
 constexpr int kSmallBins = 56;   // 7 x 7 tiles: at most 4 symmetric warp tasks
+// the radial kernels in the same 128-thread build (three chains per SM)
+size_t mcd128_rad_problem_bytes();
+size_t mcd128_rad_configure(void* rproblem, size_t smem_cap);
+int mcd128_launch_rad_mc_run(const void* rproblem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
+                             double* gws, cudaStream_t st);
+int mcd128_launch_rad_loglike(const void* rproblem, int grid, int B, const double* wrad, double* out_ll, double* out_P,
+                              int* status, size_t smem, double* gws, cudaStream_t st);
 
 static_assert(sizeof(mcd_mc_params) == sizeof(McParams), "mcd_mc_params layout");
 static_assert(sizeof(mcd_chain_io) == sizeof(ChainIO), "mcd_chain_io layout");
@@ -569,6 +576,8 @@ struct mcd_rad_problem {
   double* wrad_basis;   // [n][ncosDrad] or nullptr
   int ncosDrad;
   size_t smem_bytes;
+  RadProblem R128;         // the same problem configured for the 128-thread kernels (small profiles, squaring route)
+  size_t smem128;          // 0: not used
 };
 
 int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* stream, mcd_rad_problem** out) {
@@ -625,6 +634,12 @@ int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* s
   if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) { cudaFree(blob); delete p; return MCD_E_UNSUPPORTED; }
   R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
   p->smem_bytes = rad_smem_bytes(R, R.nbatch);
+  // small profiles on the squaring route: 128-thread CTAs, three per SM (a third of the SM's shared memory each,
+  // minus the 1 KB the hardware reserves per CTA)
+  p->smem128 = 0;
+  p->R128 = R;
+  if (R.plan.ok && R.np <= kSmallBins && mcd128_rad_problem_bytes() == sizeof(RadProblem))
+    p->smem128 = mcd128_rad_configure(&p->R128, (size_t)(227 * 1024) / 4 - 1024);
   *out = p;
   return MCD_OK;
 }
@@ -653,13 +668,18 @@ int mcd_rad_loglike_batch(mcd_handle* h, const mcd_rad_problem* p, int32_t B, co
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const RadProblem& R = p->R;
-  const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
+  const int per_sm = p->smem128 ? 6 : 2;     // two rounds of resident CTAs
+  const int grid = B < per_sm * h->sm_count ? B : per_sm * h->sm_count;
   Scratch ws;
   int rc = ws.alloc((size_t)grid * rad_workspace_doubles(R) * sizeof(double), st);
   if (rc != MCD_OK) return rc;
+  h->launches++;
+  if (p->smem128) {
+    rc = mcd128_launch_rad_loglike(&p->R128, grid, B, wrad, out_ll, out_P, status, p->smem128, ws.p, st);
+    return rc == 0 ? MCD_OK : rc;
+  }
   CUDA_TRY(cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
   mcd_rad_loglike_kernel<<<grid, kThreads, p->smem_bytes, st>>>(R, B, wrad, out_ll, out_P, status, ws.p);
-  h->launches++;
   return (int)cudaGetLastError();
 }
 
@@ -685,9 +705,13 @@ int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_par
   std::memcpy(&mp, params, sizeof(mp));
   std::memcpy(&cio, io, sizeof(cio));
   cio.wrad_basis = p->wrad_basis;   // the library's private copy
+  h->launches++;
+  if (p->smem128) {
+    rc = mcd128_launch_rad_mc_run(&p->R128, &mp, &cio, nchains, nsteps, p->smem128, ws.p, st);
+    return rc == 0 ? MCD_OK : rc;
+  }
   CUDA_TRY(cudaFuncSetAttribute(mcd_rad_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
   mcd_rad_mc_run_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(R, mp, cio, nsteps, ws.p);
-  h->launches++;
   return (int)cudaGetLastError();
 }
 

@@ -674,7 +674,10 @@ __global__ void mcd_rad_pair_counts_kernel(const double* __restrict__ counts, do
   });                                                                                                           \
   RadCtx ctx{R, ex, ch, s, a0, elm, ws_x, ws_lam, ptab, ewr, ab};
 
-__global__ void __launch_bounds__(kThreads, 1)
+#ifndef MCD_RAD_MIN_BLOCKS
+#define MCD_RAD_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kThreads, MCD_RAD_MIN_BLOCKS)
 mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, double* __restrict__ out_ll,
                        double* __restrict__ out_P, int* __restrict__ status, double* gws) {
   MCD_RAD_SETUP();
@@ -695,7 +698,7 @@ mcd_rad_loglike_kernel(RadProblem R, int B, const double* __restrict__ wrad, dou
 }
 
 // Radial Monte-Carlo loop: one CTA per chain (lib/mc.py:29-30, lib/MCState.py:306-340).
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, MCD_RAD_MIN_BLOCKS)
 mcd_rad_mc_run_kernel(RadProblem R, RadMcParams mp, RadChainIO io, int nsteps, double* gws) {
   MCD_RAD_SETUP();
   const long long chain = blockIdx.x;

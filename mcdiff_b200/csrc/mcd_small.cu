@@ -11,7 +11,9 @@
 
 #include <cstring>
 
+#define MCD_RAD_MIN_BLOCKS 4
 #include "mcd_chain.cuh"
+#include "mcd_radial.cuh"
 
 using namespace mcd128;
 
@@ -41,5 +43,47 @@ int mcd128_launch_mc_run(const void* problem, const void* params, const void* io
   cudaError_t e = cudaFuncSetAttribute(mcd128_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   mcd128_mc_run_kernel<<<nchains, kThreads, smem, st>>>(P, mp, cio, nsteps, gws);
+  return (int)cudaGetLastError();
+}
+
+// ---- radial model, small profiles (np <= 56): the same radial kernels with 4 warps per chain and three chains per
+// SM.  A radial product keeps 2-4 warps busy whatever the CTA size, so the 384-thread kernel of mcd_lib.cu spends most
+// of a step in barrier-closed scalar phases with one chain per SM (ncu r02: DMMA pipe 18 %); three independent
+// 128-thread CTAs overlap those phases with each other's MMAs.
+size_t mcd128_rad_problem_bytes() { return sizeof(RadProblem); }
+
+// Picks the lockstep batch for a per-CTA shared-memory budget; returns the dynamic shared memory, 0 if it does not fit.
+size_t mcd128_rad_configure(void* rproblem, size_t smem_cap) {
+  RadProblem R;
+  std::memcpy(&R, rproblem, sizeof(R));
+  int nb = rad_pick_batch(R, smem_cap);
+  if (nb > kThreads / 32) nb = kThreads / 32;
+  if (rad_smem_bytes(R, nb) > smem_cap) return 0;
+  R.nbatch = nb;
+  std::memcpy(rproblem, &R, sizeof(R));
+  return rad_smem_bytes(R, nb);
+}
+
+int mcd128_launch_rad_mc_run(const void* rproblem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
+                             double* gws, cudaStream_t st) {
+  RadProblem R;
+  RadMcParams mp;
+  RadChainIO cio;
+  std::memcpy(&R, rproblem, sizeof(R));
+  std::memcpy(&mp, params, sizeof(mp));
+  std::memcpy(&cio, io, sizeof(cio));
+  cudaError_t e = cudaFuncSetAttribute(mcd_rad_mc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  mcd_rad_mc_run_kernel<<<nchains, kThreads, smem, st>>>(R, mp, cio, nsteps, gws);
+  return (int)cudaGetLastError();
+}
+
+int mcd128_launch_rad_loglike(const void* rproblem, int grid, int B, const double* wrad, double* out_ll, double* out_P,
+                              int* status, size_t smem, double* gws, cudaStream_t st) {
+  RadProblem R;
+  std::memcpy(&R, rproblem, sizeof(R));
+  cudaError_t e = cudaFuncSetAttribute(mcd_rad_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  mcd_rad_loglike_kernel<<<grid, kThreads, smem, st>>>(R, B, wrad, out_ll, out_P, status, gws);
   return (int)cudaGetLastError();
 }
