@@ -24,7 +24,8 @@ namespace MCD_NS {
 constexpr int kMaxLag = 64;   // LagPlan arrays are sized for this
 constexpr int kMaxCoef = 64;
 constexpr int kMaxSweeps = 60;
-constexpr int kTaylorMargin = 33;   // wrap margin of the Taylor coefficient arrays (Chain::taylor_coefs)
+constexpr int kTaylorMargin = 33;
+constexpr int kMaxTasks = 16;       // warp tasks of a symmetric product (more tasks than warps: the product runs in rounds)   // wrap margin of the Taylor coefficient arrays (Chain::taylor_coefs)
 
 // How the squaring engine reaches every lag time (built on the host, mcd_lib.cu::plan_lags).
 // Lags are visited in ascending order; G(t_i) = G(t_{i-1}) G(delta_i), delta_i = t_i - t_{i-1}.  Each
@@ -272,22 +273,37 @@ MCD_HOSTDEV size_t smem_vectors_bytes(int np, bool panels = false) {
   size_t d = (size_t)np * (panels ? 9 : 11) + 256 + kMaxCoef * 3 + kMaxLag * 2 + (panels ? 0 : (size_t)np) /*rc,rs*/ + 32 + kThreads +
              (panels ? 0 : (size_t)6 * (np + 2 * kTaylorMargin)) /*text*/;
   size_t nb = np / 4, h = np / 2;
-  size_t bytes = d * 8 + (panels ? 0 : (size_t)np * 4) /*rp,rq*/ + 64 * (kThreads / 32) /*wti*/ +
-                 (panels ? 0 : nb * (nb + 1) + h * (h - 1)) + 16 * (kThreads / 32) + sizeof(Scalars) + 64 +
+  size_t bytes = d * 8 + (panels ? 0 : (size_t)np * 4) /*rp,rq*/ + 64 * kMaxTasks /*wti*/ +
+                 (panels ? 0 : nb * (nb + 1) + h * (h - 1)) + 16 * kMaxTasks + sizeof(Scalars) + 64 +
                  2 * kThreads + 32 /*hrow, hrem, tord*/;
   return (bytes + 15) & ~(size_t)15;
 }
 MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
+
+// Packed symmetric storage (kMode 3): only the 8 x 8 tiles (a, b), a <= b, of a symmetric matrix are kept, 64
+// contiguous doubles each, row-major inside the tile with the column index XOR-swizzled by the row ((r >> 1) & 1)
+// << 2 -- with that, the m8n8k4 fragment loads of a tile AND of its transpose are both bank-conflict free.
+// Diagonal tiles are stored in full.  91 tiles = 46.6 KB at 104 bins instead of 89.9 KB: two work matrices of TWO
+// chains fit in one SM.
+MCD_HOSTDEV int pk_tile(int a, int b, int nb8) { return a * nb8 - a * (a - 1) / 2 + (b - a); }   // a <= b
+MCD_HOSTDEV int pk_off(int r, int c) { return r * 8 + (c ^ (((r >> 1) & 1) << 2)); }
+MCD_HOSTDEV size_t pk_elems(int np) { return (size_t)(np / 8) * (np / 8 + 1) / 2 * 64; }
+MCD_HOSTDEV size_t pk_index(int i, int j, int nb8) {
+  const int a = i >> 3, b = j >> 3;
+  return a <= b ? (size_t)pk_tile(a, b, nb8) * 64 + pk_off(i & 7, j & 7) : (size_t)pk_tile(b, a, nb8) * 64 + pk_off(j & 7, i & 7);
+}
+MCD_HOSTDEV size_t smem_packed_bytes(int np) { return 2 * pk_elems(np) * 8; }
 // global workspace of one chain of the blocked squaring engine: 3 work matrices + the plan's slots
 MCD_HOSTDEV size_t blocked_ws_doubles(const Problem& P, int nslots) { return (size_t)(3 + nslots) * P.np * P.ld; }
 
 // mat: storage for XT and B2 (2*np*ld doubles; shared or global), vec: shared storage.
-// panels: mat holds the two nbk x lds operand panels of the blocked squaring engine.
-MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels = false) {
+// panels: mat holds the two nbk x lds operand panels of the blocked squaring engine; packed: two packed symmetric
+// matrices (and the slim vector layout of the panel engine).
+MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels = false, bool packed = false) {
   Smem s;
   const int np = P.np;
   s.XT = mat;
-  s.B2 = mat + (panels ? (size_t)P.nbk * P.lds : (size_t)np * P.ld);
+  s.B2 = mat + (packed ? pk_elems(np) : (panels ? (size_t)P.nbk * P.lds : (size_t)np * P.ld));
   double* d = reinterpret_cast<double*>(vec);
   s.a = d; d += np;
   s.b = d; d += np;
@@ -315,7 +331,7 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.sc = reinterpret_cast<Scalars*>(d);
   d += (sizeof(Scalars) + 7) / 8;
   int* ip = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(d) + 15) & ~(uintptr_t)15);   // wti: 128-bit loads
-  s.wti = ip; ip += 16 * (kThreads / 32);
+  s.wti = ip; ip += 16 * kMaxTasks;
   s.rp = ip; ip += panels ? 0 : np / 2;
   s.rq = ip; ip += panels ? 0 : np / 2;
   unsigned char* c = reinterpret_cast<unsigned char*>(ip);
@@ -324,7 +340,7 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
   s.nblk = h * (h - 1) / 2;
   s.tiles = c; c += 2 * s.ntiles;
   s.jblocks = c; c += 2 * s.nblk;
-  s.wtab = c; c += 16 * (kThreads / 32);
+  s.wtab = c; c += 16 * kMaxTasks;
   s.hrow = c; c += kThreads;
   s.hrem = c; c += kThreads;
   s.tord = c;
@@ -339,6 +355,7 @@ template <class Exec, int kMode = 0>
 struct Chain {
   static constexpr bool kBlocked = (kMode == 1);
   static constexpr bool kGeneral = (kMode == 2);
+  static constexpr bool kPacked = (kMode == 3);
   Exec& ex;
   const Problem& P;
   Smem s;
@@ -364,7 +381,7 @@ struct Chain {
       if (tid < 32) s.tord[tid] = (unsigned char)taylor_order(tid, 0);
     });
     ex.single([&]() {
-      const int nb = kBlocked ? 0 : P.np / 4;
+      const int nb = (kBlocked || kPacked) ? 0 : P.np / 4;
       int t = 0;
       for (int pi = 0; pi < nb; pi += 4)
         for (int pj = (pi / 8) * 8; pj < nb; pj += 8)
@@ -381,7 +398,7 @@ struct Chain {
       // two A fragments serve all of its MMAs.  wtab[w] = {nt, na, rowA, rowB, jb[8]}: tiles
       // t < na belong to rowA, na <= t < nt to rowB, t >= nt are padding (computed, not used).
       {
-        const int nb8 = P.nbk / 8, cap = (kThreads >= 512) ? 6 : 8, maxw = kThreads / 32;
+        const int nb8 = P.nbk / 8, cap = (kThreads >= 512) ? 6 : 8, maxw = kMaxTasks;
         unsigned char sib[64], sjb[64], sln[64], used[64];
         int nseg = 0;
         for (int ib = 0; ib < nb8; ++ib)
@@ -405,7 +422,7 @@ struct Chain {
             used[sg] = 1; ++nw;
           }
         const int first_partial = nw;
-        int nsegs_in[kThreads / 32];
+        int nsegs_in[kMaxTasks];
         for (int w = 0; w < maxw; ++w) nsegs_in[w] = 0;
         for (;;) {
           int best = -1;
@@ -433,7 +450,7 @@ struct Chain {
           for (int k = 0; k < 16; ++k) q[k] = (have && k < 12) ? wt[k] : 0;
         }
       }
-      const int h = kBlocked ? 0 : P.np / 2;
+      const int h = (kBlocked || kPacked) ? 0 : P.np / 2;
       int q = 0;
       for (int ka = 0; ka < h; ++ka)
         for (int kb = ka + 1; kb < h; ++kb) {
@@ -879,7 +896,8 @@ struct Chain {
   // keeps their 2-doubles-per-lane accumulators in registers; results are register-staged and
   // written back in place after the barrier, like the DFMA version.
   static constexpr int kTilesPerWarp = (kThreads >= 512) ? 6 : 8;
-  MCD_HD bool dmma_ok() const { return s.sc->mma_tasks > 0; }
+  // the engines that do a product in ONE round need a warp per task (the packed engine runs in rounds)
+  MCD_HD bool dmma_ok() const { return s.sc->mma_tasks > 0 && s.sc->mma_tasks <= Exec::nthr() / 32; }
 
 #if defined(__CUDA_ARCH__)
   static __device__ __forceinline__ double lds64(unsigned addr) {
@@ -1264,13 +1282,26 @@ struct Chain {
     const int n = P.n, m = tp.m;
     const double sc = tp.scale / s.red[m];
     const int kmax = hf ? m - 1 : m;                               // last element inside the band
-    if (add) {
+    if (add || kPacked) {
+      // the row of element k walks around the ring one step per element.  Packed storage keeps T[i][j] only for
+      // tile rows <= tile columns (the mirrored entry is written by the thread of column i).
       int i = hf ? j + 1 : j;                                      // row of element 0
       if (i >= n) i -= n;
+      const int nb8 = P.np >> 3;
 #pragma unroll
       for (int k = 0; k < kTH; ++k) {
         if (k > kmax) break;
-        dst[(size_t)i * ld + j] += x[k] * sc;
+        const bool inside = P.pbc || (hf ? j + 1 + k < n : k <= j);
+        if (inside) {
+          if (kPacked) {
+            if ((i >> 3) <= (j >> 3)) {
+              double* q = dst + pk_index(i, j, nb8);
+              if (add) *q += x[k] * sc; else *q = x[k] * sc;
+            }
+          } else {
+            dst[(size_t)i * ld + j] += x[k] * sc;
+          }
+        }
         if (hf) { if (++i >= n) i = 0; }
         else { if (--i < 0) i = n - 1; }
       }
@@ -1362,8 +1393,9 @@ struct Chain {
   MCD_HD void taylor_band(const double* diag, const double* lo, const double* up, const TaylorPlan& tp, double* ext,
                           double* dst, int ld) {
     const int n = P.n;
+    const int nzero = kPacked ? (int)pk_elems(P.np) : P.np * ld;
     ex.par([&](int tid) {
-      for (int e = tid * 2; e < P.np * ld; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
+      for (int e = tid * 2; e < nzero; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
       taylor_coefs(tid, ext, diag, lo, up, tp);
     });
     MCD_CLK(3);
@@ -1817,6 +1849,306 @@ struct Chain {
       return nan("");
     }
     return ex.sum([&](int tid) { return s.part[tid]; });
+  }
+
+  // ------------------------------------------------------------------------------------
+  // Packed symmetric squaring engine (kPacked, np <= 104): same mathematics as evaluate_sq, the work matrices
+  // in packed tile storage (pk_tile / pk_off) so that TWO chains fit in the shared memory of one SM -- the
+  // scalar phases of one chain (Taylor, epilogues, Metropolis, barriers) overlap the m8n8k4 loops of the other.
+  // 192 threads per chain (two CTAs x 170 registers per thread fill the register file): a product has more warp
+  // tasks (12 at 104 bins) than warps (6) and runs in two full rounds.
+  //   C_IJ = sum_K X_KI^T Y_KJ with 8 x 8 tiles: the A fragment of tile row I at k-block K comes from the stored tile
+  //   (K, I) when K <= I and from the TRANSPOSE of the stored tile (I, K) when K > I (likewise B with J); every
+  //   operand tile keeps a running byte offset (+ 512 (nb8 - K - 1) per step while K < I, + 512 afterwards).
+  // Products never run in place: a result that must replace one of its operands is written to a per-chain
+  // global scratch matrix (L2) and copied back.
+  // ------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+  // k loop of one warp task on packed operands, software pipelined: the 10 fragment loads of step (K, h) are issued
+  // BEFORE the 8 MMAs of the previous step, so that a warp alone on its sub-partition (the other warps of both
+  // resident CTAs may be in scalar phases) still keeps the tensor pipe fed -- the volatile asm statements keep
+  // exactly this order.
+  template <int NA>
+  static __device__ __forceinline__ void pk_mma_loop(unsigned xb, unsigned yb, int nb8, int rowA, int rowB,
+                                                     const int (&jb)[kTilesPerWarp], int fr, int fk,
+                                                     double (&c)[kTilesPerWarp][2]) {
+    // lane offsets (bytes) inside a stored tile: direct (rows = k) and transposed (rows = i) reading, k-halves 0 / 1
+    const int sw_k = ((fk >> 1) & 1) << 2, sw_r = ((fr >> 1) & 1) << 2;
+    const int d0 = (fk * 8 + (fr ^ sw_k)) * 8;                 // direct, h = 0 (h = 1: + 256)
+    const int t0 = (fr * 8 + fk + sw_r) * 8;                   // transposed, h = 0
+    const int th = (4 - 2 * sw_r) * 8;                         // transposed, h = 1 relative to h = 0
+    unsigned pA0 = xb + 512u * (unsigned)rowA, pA1 = xb + 512u * (unsigned)rowB;   // tile (0, Q) has index Q
+    unsigned pB[kTilesPerWarp];
+#pragma unroll
+    for (int t = 0; t < kTilesPerWarp; ++t) pB[t] = yb + 512u * (unsigned)jb[t];
+    double xa0, xa1, xb_[kTilesPerWarp];                      // operands of (K, 0)
+    double ya0, ya1, yb_[kTilesPerWarp];                      // operands of (K, 1)
+    xa0 = lds64(pA0 + d0);
+    xa1 = (NA < kTilesPerWarp) ? lds64(pA1 + d0) : 0.0;
+#pragma unroll
+    for (int t = 0; t < kTilesPerWarp; ++t) xb_[t] = lds64(pB[t] + d0);     // K = 0 <= every block index: direct
+#pragma unroll 1
+    for (int K = 0; K < nb8; ++K) {
+      // ---- loads of (K, 1), MMAs of (K, 0) ----
+      ya0 = lds64(pA0 + ((K <= rowA) ? d0 + 256 : t0 + th));
+      if (NA < kTilesPerWarp) ya1 = lds64(pA1 + ((K <= rowB) ? d0 + 256 : t0 + th));
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) yb_[t] = lds64(pB[t] + ((K <= jb[t]) ? d0 + 256 : t0 + th));
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) {
+        const double a = (t < NA) ? xa0 : xa1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1])
+                     : "d"(a), "d"(xb_[t]));
+      }
+      // ---- advance to K + 1 (the last step stays where it is: its loads are not used), loads of (K + 1, 0), MMAs of (K, 1) ----
+      const int K1 = K + 1;
+      if (K1 < nb8) {
+        const int inc = 512 * (nb8 - K1);
+        pA0 += (K < rowA) ? inc : 512;
+        pA1 += (K < rowB) ? inc : 512;
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) pB[t] += (K < jb[t]) ? inc : 512;
+      }
+      xa0 = lds64(pA0 + ((K1 <= rowA) ? d0 : t0));
+      if (NA < kTilesPerWarp) xa1 = lds64(pA1 + ((K1 <= rowB) ? d0 : t0));
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) xb_[t] = lds64(pB[t] + ((K1 <= jb[t]) ? d0 : t0));
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) {
+        const double a = (t < NA) ? ya0 : ya1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1])
+                     : "d"(a), "d"(yb_[t]));
+      }
+    }
+  }
+#endif
+
+  // element (i, j) of a packed symmetric matrix
+  MCD_HD double pk_get(const double* G, int i, int j) const { return G[pk_index(i, j, P.np >> 3)]; }
+
+  // D <- X Y for packed symmetric commuting operands; D is another packed buffer (shared memory or the global
+  // scratch), never an operand.  cnt != nullptr: likelihood terms of a lag time (as dmma_product).  store: 0 / 1.
+  MCD_HD void pk_product(const double* X, const double* Y, double* D, const int* cnt, const int* nsy, double* Pl,
+                         int store) {
+    const int n = P.n, np = P.np, nb8 = np >> 3;
+    const int ntasks = s.sc->mma_tasks;
+    const int nwarp = Exec::nthr() / 32;
+    for (int base = 0; base < ntasks; base += nwarp) {
+      ex.par([&](int tid) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const WarpTask task = load_task(base + warp, ntasks);
+        const bool active = base + warp < ntasks;
+        const int nt = task.nt, na = task.na, rowA = task.rowA, rowB = task.rowB;
+        double c[kTilesPerWarp][2];
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+        const int fr = lane >> 2, fk = lane & 3;
+        int nsv[kTilesPerWarp][2];
+        if (cnt && active) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+            const i2 q = ld2i(nsy + (size_t)(ib * 8 + fr) * np + jb * 8 + 2 * fk);
+            nsv[t][0] = q.x;
+            nsv[t][1] = q.y;
+          }
+        }
+        if (active) {
+#if defined(__CUDA_ARCH__)
+          const unsigned xb = (unsigned)__cvta_generic_to_shared(X), yb = (unsigned)__cvta_generic_to_shared(Y);
+          switch (na) {
+            case 1: pk_mma_loop<1>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 2: pk_mma_loop<2>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 3: pk_mma_loop<3>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 4: pk_mma_loop<4>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 5: pk_mma_loop<5>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 6: pk_mma_loop<6>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            case 7: pk_mma_loop<7>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+            default: pk_mma_loop<8>(xb, yb, nb8, rowA, rowB, task.jb, fr, fk, c); break;
+          }
+#else
+          for (int t = 0; t < nt; ++t) {
+            const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+            const int i = ib * 8 + fr;
+            for (int e = 0; e < 2; ++e) {
+              const int j = jb * 8 + 2 * fk + e;
+              double acc = 0.0;
+              for (int k = 0; k < np; ++k) acc = fma(pk_get(X, k, i), pk_get(Y, k, j), acc);
+              c[t][e] = acc;
+            }
+          }
+#endif
+        }
+        // likelihood epilogue: as dmma_product (branch-free over the 16 entries, clipped entries redone exactly)
+        if (cnt && nt > 0) {
+          const double gmin = s.sc->gmin;
+          double part = 0.0;
+          bool rare = false;
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const bool valid = (t < nt) && !(ib == jb && j + e < i);
+              const double g = c[t][e];
+              const bool above = g >= gmin;
+              const int ns = valid ? nsv[t][e] : 0;
+              rare |= (ns != 0) && !above;
+              part += (double)(above ? ns : 0) * fast_log(above ? g : 1.0);
+            }
+          }
+          if (rare || Pl) {
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+              const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int jj = j + e;
+                if (!(t < nt) || (ib == jb && jj < i)) continue;
+                if (nsv[t][e] != 0 && !(c[t][e] >= gmin))
+                  part += pair_term_clipped(c[t][e], nsv[t][e], i, jj, cnt, P.np, P.clip, s.ea, s.eb, s.hv);
+                if (Pl && i < n && jj < n) {
+                  Pl[(size_t)i * n + jj] = s.ea[i] * c[t][e] * s.eb[jj];
+                  Pl[(size_t)jj * n + i] = s.ea[jj] * c[t][e] * s.eb[i];
+                }
+              }
+            }
+          }
+          s.part[tid] += part;
+        }
+        if (store) {
+          const int swz = ((fr >> 1) & 1) << 2;
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            if (t < nt) {
+              const int ib = (t < na) ? rowA : rowB, jb = task.jb[t];
+              st2(D + (size_t)pk_tile(ib, jb, nb8) * 64 + fr * 8 + ((2 * fk) ^ swz), c[t][0], c[t][1]);
+            }
+          }
+        }
+      });
+    }
+  }
+
+  // likelihood terms of a packed kernel that already sits in a buffer
+  MCD_HD void pk_buffer_loglike(const double* G, const int* cnt, const int* nsy, double* Pl) {
+    const int n = P.n, np = P.np;
+    ex.par([&](int tid) {
+      double part = 0.0;
+      for (int e = tid; e < n * n; e += Exec::nthr()) {
+        const int i = e / n, j = e - i * n;
+        if (j < i) continue;
+        const double g = pk_get(G, i, j);
+        part += pair_term(g, nsy[(size_t)i * np + j], i, j, cnt);
+        if (Pl) {
+          Pl[(size_t)i * n + j] = s.ea[i] * g * s.eb[j];
+          Pl[(size_t)j * n + i] = s.ea[j] * g * s.eb[i];
+        }
+      }
+      s.part[tid] += part;
+    });
+  }
+
+  MCD_HD void pk_copy(double* dst, const double* src) {
+    const int total = (int)pk_elems(P.np);
+    ex.par([&](int tid) {
+      for (int e = tid * 2; e < total; e += 2 * Exec::nthr()) {
+        const d2 x = ld2(src + e);
+        st2(dst + e, x.x, x.y);
+      }
+    });
+  }
+
+  // exp(t S) by Taylor + squarings in packed storage; same contract as sq_chain
+  MCD_HD double* pk_chain(double t, double gersh, int taylor_m, int epi, double* Pout, double** other, int* nsq_out) {
+    const int np = P.np;
+    TaylorPlan tp;
+    if (!taylor_plan(t, gersh, taylor_m, tp)) return nullptr;
+    const int nsq = tp.nsq;
+    taylor_band<true>(s.a, s.b, s.b, tp, s.B2, s.XT, 0);       // the coefficient arrays live in B2 (free until the first squaring)
+    double* G = s.XT;
+    double* O = s.B2;
+    const int* cnt_e = (epi >= 0) ? P.counts + (size_t)epi * np * np : nullptr;
+    const int* nsy_e = (epi >= 0) ? P.nsym + (size_t)epi * np * np : nullptr;
+    for (int q = 0; q < nsq; ++q) {
+      const bool last = (q + 1 == nsq);
+      pk_product(G, G, O, last ? cnt_e : nullptr, last ? nsy_e : nullptr, last ? Pout : nullptr, 1);
+      double* tmp = G; G = O; O = tmp;
+    }
+    if (nsq == 0 && epi >= 0) pk_buffer_loglike(G, cnt_e, nsy_e, Pout);
+    *other = O;
+    if (nsq_out) *nsq_out += nsq;
+    return G;
+  }
+
+  // log L following LagPlan `pl`.  slots: pl.nslots + 1 packed matrices of this chain in global memory (the last
+  // one is the scratch of products that replace an operand).
+  MCD_HD double evaluate_pk(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* slots,
+                            int taylor_m, double* Pout, int* squarings_out) {
+    const int n = P.n, np = P.np;
+    const size_t nn = (size_t)n * n, slot_elems = pk_elems(np);
+    double* scratch = slots + (size_t)plan_slots(P) * slot_elems;
+    build_S(v, w);
+    const double gersh = s.sc->gersh;
+    ex.par([&](int tid) { s.part[tid] = 0.0; });
+    int nsq = 0;
+    bool bad = false;
+    double* R = nullptr;
+    double* O = nullptr;
+    const int l0 = pl.order[0];
+    const bool fast = pl.fast != 0;
+    for (int c = 0; c < pl.nchain && !bad; ++c) {
+      const bool is_first_lag = (c == pl.nchain - 1);
+      const double t = lagt[pl.chain_a[c]] - (pl.chain_b[c] >= 0 ? lagt[pl.chain_b[c]] : 0.0);
+      double* other = nullptr;
+      double* G = pk_chain(t, gersh, taylor_m, is_first_lag ? l0 : -1,
+                           (is_first_lag && Pout) ? Pout + (size_t)l0 * nn : nullptr, &other, &nsq);
+      if (!G) { bad = true; break; }
+      if (!fast && pl.chain_slot[c] >= 0) pk_copy(slots + (size_t)pl.chain_slot[c] * slot_elems, G);
+      R = G;
+      O = other;
+    }
+    // fast plan (t_i = (i+1) t_0): G0 stays in R, O receives G(2 t_0); with three or four lags G(3 t_0) = G(2 t_0) G(t_0)
+    // and G(4 t_0) = G(2 t_0)^2 are needed for their likelihood terms only.  Longer progressions and general plans
+    // replace an operand: product into the scratch, copy back.
+    double* G0 = R;
+    int in_O = -1;
+    for (int i = 1; i < P.nlag && !bad; ++i) {
+      const int l = pl.order[i];
+      const int* cnt = P.counts + (size_t)l * np * np;
+      const int* nsy = P.nsym + (size_t)l * np * np;
+      double* Pl = Pout ? Pout + (size_t)l * nn : nullptr;
+      if (!fast && pl.op_slot[i] < 0) {
+        pk_buffer_loglike(R, cnt, nsy, Pl);
+      } else if (fast) {
+        const bool last = (i + 1 == P.nlag);
+        if (i == 1) pk_product(G0, G0, O, cnt, nsy, Pl, last ? 0 : 1);
+        else if (i == 2 && P.nlag <= 4) pk_product(O, G0, nullptr, cnt, nsy, Pl, 0);
+        else if (i == 3 && P.nlag == 4) pk_product(O, O, nullptr, cnt, nsy, Pl, 0);
+        else {
+          pk_product(O, G0, scratch, cnt, nsy, Pl, last ? 0 : 1);
+          if (!last) pk_copy(O, scratch);
+        }
+      } else {
+        if (in_O != pl.op_slot[i]) {
+          pk_copy(O, slots + (size_t)pl.op_slot[i] * slot_elems);
+          in_O = pl.op_slot[i];
+        }
+        pk_product(R, O, scratch, cnt, nsy, Pl, 1);
+        pk_copy(R, scratch);
+      }
+      if (!fast && pl.park[i] >= 0) pk_copy(slots + (size_t)pl.park[i] * slot_elems, R);
+    }
+    if (squarings_out) *squarings_out = bad ? -1 : nsq;
+    if (bad) {
+      ex.single([&]() { s.sc->status |= ST_NONFINITE; });
+      return nan("");
+    }
+    return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
   }
 
   // ------------------------------------------------------------------------------------
@@ -2364,6 +2696,8 @@ struct Chain {
           ll_new = evaluate_blk(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
         } else if constexpr (kGeneral) {
           ll_new = evaluate_gen(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
+        } else if constexpr (kPacked) {
+          ll_new = evaluate_pk(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
         } else if (mp.method >= 2) {
           ll_new = evaluate_sq(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, mp.method == 2, nullptr, &sw);
         } else {

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -19,6 +20,12 @@ size_t mcd128_smem_bytes(int np, int ld);
 int mcd128_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
                          double* gws, cudaStream_t st);
 constexpr int kSmallBins = 56;   // 7 x 7 tiles: at most 4 symmetric warp tasks
+// mcd_pk.cu: 256-thread CTAs with packed symmetric work matrices, two chains per SM (kSmallBins < np <= 104)
+size_t mcdpk_problem_bytes();
+size_t mcdpk_smem_bytes(int np);
+size_t mcdpk_scratch_doubles(const void* problem);
+int mcdpk_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
+                         double* gws, cudaStream_t st);
 // the radial kernels in the same 128-thread build (three chains per SM)
 size_t mcd128_rad_problem_bytes();
 size_t mcd128_rad_configure(void* rproblem, size_t smem_cap);
@@ -540,6 +547,21 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
                                   (int)p->blk_smem_bytes));
     mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   } else if (p->in_smem) {
+    // Packed symmetric engine (mcd_pk.cu), two chains per SM: OPT-IN (MCDIFF_B200_PACKED=1).  Measured on B200 at
+    // 100 bins x 4 lags (profiles/prof_pair.py): a packed chain alone costs 138 us per MC step against 94 us for the
+    // full-storage kernel (8 warps and two product rounds instead of 12 warps and one, per-tile address selects in the k
+    // loop); two resident chains overlap by 1.36x -> 1.46e6 MC steps/s at 296 chains, 1.33e6 at 1024, against 1.58e6.
+    const size_t smem_pk = mcdpk_smem_bytes(P.np);
+    const char* want_pk = getenv("MCDIFF_B200_PACKED");
+    if (want_pk && want_pk[0] == '1' && mp.method == MCD_METHOD_SQUARING && P.np > kSmallBins &&
+        mcdpk_problem_bytes() == sizeof(Problem) && smem_pk <= (size_t)(227 * 1024) / 2 - 1024) {
+      int rc = ws.alloc((size_t)nchains * mcdpk_scratch_doubles(&P) * sizeof(double), st);
+      if (rc != MCD_OK) return rc;
+      rc = mcdpk_launch_mc_run(&P, &mp, &cio, nchains, nsteps, smem_pk, ws.p, st);
+      if (rc != MCD_OK) return rc;
+      h->launches++;
+      return MCD_OK;
+    }
     if (mp.method >= MCD_METHOD_SQUARING) {
       int rc = ws.alloc((size_t)nchains * plan_slots(P) * P.np * P.ld * sizeof(double), st);
       if (rc != MCD_OK) return rc;

@@ -17,6 +17,8 @@
 using namespace mcd;
 
 namespace {
+// emulator-only method code: the packed symmetric engine, which the library selects by itself (mcd_mc_run, 57 <= np <= 104)
+constexpr int kEmulPacked = 4;
 struct HostProblem {
   Problem P;
   std::vector<int> counts, nsym;
@@ -118,6 +120,29 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     }
     return 0;
   }
+  if (method == kEmulPacked) {   // packed symmetric engine (mcd_pk.cu): slim vector layout, packed work matrices
+    Smem s = carve(P, mat.data(), vec.data(), true, true);
+    HostExec ex(store.data());
+    Chain<HostExec, 3> ch(ex, P, s);
+    ch.build_tables();
+    std::vector<double> slots((size_t)(kMaxSlots + 1) * pk_elems(P.np));
+    for (int b = 0; b < B; ++b) {
+      for (int i = 0; i < P.np; ++i) {
+        s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
+        s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
+      }
+      for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
+      s.sc->status = 0;
+      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;
+      int sw = 0;
+      double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
+      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
+                                               : ch.evaluate_pk(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], slots.data(), 0, Pb, &sw);
+      if (status) status[b] = (int)s.sc->status;
+      if (sweeps) sweeps[b] = sw;
+    }
+    return 0;
+  }
   Smem s = carve(P, mat.data(), vec.data());
   HostExec ex(store.data());
   Chain<HostExec> ch(ex, P, s);
@@ -177,6 +202,17 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
       HostExec ex(store.data());
       Chain<HostExec, 1> ch(ex, P, s);
       ch.run(mp, cio, c, nsteps, ws.data());
+    }
+    return 0;
+  }
+  if (mp.method == kEmulPacked) {
+    mp.method = MCD_METHOD_SQUARING;
+    std::vector<double> slots((size_t)(kMaxSlots + 1) * pk_elems(P.np));
+    for (int c = 0; c < nchains; ++c) {
+      Smem s = carve(P, mat.data(), vec.data(), true, true);
+      HostExec ex(store.data());
+      Chain<HostExec, 3> ch(ex, P, s);
+      ch.run(mp, cio, c, nsteps, slots.data());
     }
     return 0;
   }

@@ -304,3 +304,100 @@ def test_time_offset_without_time_offset_moves(method):
     np.testing.assert_allclose(llt[0], ref["ll_try"], rtol=1e-10)
     np.testing.assert_allclose(ch.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
     assert ch.scal[0, K.S_T0] == tau and not ch.counters[0, K.C_STATUS]
+
+
+# ---- packed symmetric engine (mcd_pk.cu: 192 threads, tile-packed work matrices, two chains per SM) ---------------
+PACKED = 4      # emulator-only method code (the library picks this engine by itself for 57 <= np <= 104)
+
+
+def test_packed_engine_likelihoods(gold_ll):
+    """Likelihoods and propagators of the packed engine, compiled as the library compiles it (192 threads: products
+    run in two rounds), on the reference fixtures: one lag, four lags (fast plan), non-periodic, odd size."""
+    G = gold_ll
+    H.use_threads(256)
+    try:
+        pA = H.HostProblem(G["A_counts"], G["A_lags"], True)
+        ll, P, st, _ = H.loglike_batch(pA, G["K_v"][:2], G["K_w"][:2], want_P=True, method=PACKED)
+        assert not st.any()
+        np.testing.assert_allclose(ll, G["K_ll"][:2], rtol=1e-12)
+        assert np.max(np.abs(P[1, 0] - G["K2_P"])) < 1e-13
+        pP = H.HostProblem(G["P_counts"], G["P_lags"], True)
+        ll, _, st, _ = H.loglike_batch(pP, G["rand_v"][:3], G["rand_wP"][:3], method=PACKED)
+        np.testing.assert_allclose(ll, G["rand_ll_P"][:3], rtol=1e-12)
+        pC = H.HostProblem(G["C_counts"], G["C_lags"], False)
+        ll, P, st, _ = H.loglike_batch(pC, G["C_v"][:2], G["C_w"][:2], want_P=True, method=PACKED)
+        np.testing.assert_allclose(ll, G["C_ll"][:2], rtol=1e-12)
+        assert np.max(np.abs(P[0, 0] - G["C_P0"])) < 1e-12
+    finally:
+        H.use_threads(None)
+
+
+@pytest.mark.parametrize("n,lags,pbc", [(61, [3.0, 6.0, 9.0, 12.0, 15.0, 18.0], True),     # long progression: scratch + copy back
+                                        (72, [2.0, 3.0, 5.0, 10.0], True),                  # general plan with slots
+                                        (100, [4.0, 4.0, 8.0], False),                      # duplicate lag time
+                                        (97, [10.0], True)])
+def test_packed_engine_plans(n, lags, pbc):
+    from oracle import mcdiff_oracle as O
+    lags = np.array(lags)
+    counts = O.synthetic_counts(n, lags, seed=n, total=2.0e5, dz=0.7)[0]
+    if not pbc:
+        counts = counts.copy()
+        counts[:, 0, n - 1] = 0
+        counts[:, n - 1, 0] = 0
+    rng = np.random.default_rng(n)
+    v = rng.normal(0.0, 0.6, (2, n))
+    w = -0.5 + rng.normal(0.0, 0.3, (2, n if pbc else n - 1))
+    H.use_threads(256)
+    try:
+        prob = H.HostProblem(counts, lags, pbc)
+        ll, P, st, _ = H.loglike_batch(prob, v, w, want_P=True, method=PACKED)
+        assert not st.any()
+        ref = np.array([O.log_like_lag(v[b], w[b], lags, counts, pbc) for b in range(2)])
+        np.testing.assert_allclose(ll, ref, rtol=1e-11)
+        for l, lag in enumerate(lags):
+            assert np.max(np.abs(P[0, l] - O.propagator(v[0], w[0], lag, pbc))) < 1e-12
+        if len(lags) > 1 and pbc:
+            shift = np.array([0.7, -0.4])
+            lt = lags[None, :] + shift[:, None]
+            ll_s, _, st_s, _ = H.loglike_batch(prob, v, w, lagtimes=lt, method=PACKED)
+            assert not st_s.any()
+            ref_s = np.array([O.log_like_lag(v[b], w[b], lt[b], counts, pbc) for b in range(2)])
+            np.testing.assert_allclose(ll_s, ref_s, rtol=1e-11)
+    finally:
+        H.use_threads(None)
+
+
+def test_packed_engine_mc_replay(gold_replay):
+    """The MC loop on the packed engine against a reference trajectory (cosine model on A, 110 steps) and, with
+    time-offset moves, against the oracle replay at the BASELINE shape."""
+    from oracle import mcdiff_oracle as O
+    H.use_threads(256)
+    try:
+        case, g, ch, dec, llt, smp = _run_case(gold_replay, "cosA", PACKED, 110)
+        assert np.array_equal(dec[0] >> 2, g("move")[:110])
+        assert np.array_equal(dec[0] & 1, g("accepted")[:110])
+        np.testing.assert_allclose(ch.scal[0, K.S_LL], g("ll_after")[109], rtol=1e-11)
+        assert ch.counters[0, K.C_STATUS] == 0
+        n, nsteps = 100, 24
+        lags = np.array([10.0, 20.0, 30.0, 40.0])
+        counts = O.synthetic_counts(n, lags, seed=11, total=2.0e5, dz=0.5)[0]
+        vb, wb = O.cos_basis_center(n, 6), O.cos_basis_border(n, n, 4)
+        wc0 = np.zeros(4)
+        wc0[0] = 1.0
+        w0 = wb @ wc0
+        cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=0.2, dw=0.2, dtimezero=0.3, temp=1.0,
+                            nmc=nsteps, num_mc_update=8.0, move_timezero=True)
+        tu, ti = O.make_tape(np.random.default_rng(2), nsteps, cfg)
+        ref = O.replay(cfg, np.zeros(n), w0, tu, ti, v_coeff0=np.zeros(6), w_coeff0=wc0)
+        prob = H.HostProblem(counts, lags, True, v_basis=vb, w_basis=wb)
+        ll0 = O.log_like_lag(np.zeros(n), w0, lags, counts, True)
+        chn = H.HostChains(prob, 1, np.zeros(n), w0, np.zeros(6), wc0, ll0=ll0, dv=0.2, dw=0.2, dt0=0.3)
+        mp = K.McParams()
+        mp.num_mc_update, mp.dtemp, mp.min_lt, mp.move_timezero = 8.0, 0.0, 10.0, 1
+        mp.sample_every, mp.refresh_every, mp.use_tape, mp.method = 100, 16, 1, PACKED
+        dec, _, _ = chn.run(nsteps, mp, tu, ti)
+        assert np.array_equal(dec[0] & 1, ref["accepted"])
+        assert np.array_equal((dec[0] >> 1) & 1, ref["accepted_t0"])
+        np.testing.assert_allclose(chn.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
+    finally:
+        H.use_threads(None)

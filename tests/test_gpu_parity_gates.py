@@ -209,3 +209,38 @@ def test_config3_shape_mc_replay(engine):
     assert prob.squaring_ok and not prob.in_smem                          # the blocked engine ran it
     assert ndec == 4 * 48
     assert 0 < int((dec & 1).sum()) < dec.size
+
+
+def test_packed_engine_two_chains_per_sm(engine, monkeypatch):
+    """The opt-in packed symmetric engine (mcd_pk.cu, MCDIFF_B200_PACKED=1: tile-packed work matrices, 256 threads, two
+    chains per SM): decisions identical to the oracle replay at the BASELINE shape with time-offset moves (general
+    plan: slots + scratch), and identical to the default full-storage kernel on a longer run."""
+    from mcdiff_b200 import _capi as K
+    from mcdiff_b200.engine import ChainBatch
+    from oracle import mcdiff_oracle as O
+    counts, lags, edges, F, w_true = O.synthetic_counts()
+    monkeypatch.setenv("MCDIFF_B200_PACKED", "1")
+    ndec, dec, prob = _device_vs_replay(engine, counts, lags, 10, 6, float(np.mean(w_true)), 0.05, 0.05, 0.2,
+                                        nch=3, nsteps=60, nupd=20.0, move_t0=True, seed=77, off=5,
+                                        chunks=(25, 35), method=0)
+    assert ndec == 3 * 60 * 2 and prob.in_smem
+
+    def run(packed):
+        monkeypatch.setenv("MCDIFF_B200_PACKED", "1" if packed else "0")
+        n = counts.shape[-1]
+        ch = ChainBatch(prob, 300)                                  # more chains than SMs: two resident per SM
+        wc0 = np.zeros(6)
+        wc0[0] = float(np.mean(w_true))
+        wb = O.cos_basis_border(n, n, 6)
+        ch.set_state(np.zeros(n), wb @ wc0, np.zeros(10), wc0, dv=0.05, dw=0.05)
+        ch.init_log_like()
+        mp = K.McParams()
+        mp.num_mc_update, mp.min_lt, mp.sample_every, mp.refresh_every, mp.seed = 100.0, 10.0, 100, 512, 5
+        d, _, _ = ch.run(150, mp, record=True)
+        return d.cpu().numpy(), ch.host_state()
+
+    d1, s1 = run(True)
+    d0, s0 = run(False)
+    assert np.array_equal(d1, d0)
+    np.testing.assert_allclose(s1["scal"][:, 0], s0["scal"][:, 0], rtol=1e-12)
+    assert not s1["counters"][:, 6].any()
