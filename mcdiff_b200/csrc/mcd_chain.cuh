@@ -1151,6 +1151,7 @@ struct Chain {
   // the periodic LINE (the covering space: the extended coefficient arrays are periodic) and the entries are
   // then summed over the rows that coincide on the ring -- in a fixed order, lower lane first.
   static constexpr int kTH = 32;              // window elements per lane
+  static constexpr int kTChunk = 4;           // elements per skip-able chunk of a sweep (8: same time, more spills)
   static constexpr int kTM = kTaylorMargin;   // >= kTH + 1
   MCD_HOSTDEV static size_t taylor_ext_doubles(int n) { return (size_t)6 * (n + 2 * kTM); }
 
@@ -1198,28 +1199,26 @@ struct Chain {
     // element k: own row i, inner neighbour (towards the centre), outer neighbour
     //   lower lane: i = j - k,     inner = row i+1 (coefficient U[i]),   outer = row i-1 (L[i-1])  -> reversed arrays
     //   upper lane: i = j + 1 + k, inner = row i-1 (coefficient L[i-1]), outer = row i+1 (U[i])
-    const double* MCD_RESTRICT pa;
-    const double* MCD_RESTRICT pin;
-    const double* MCD_RESTRICT pout;
-    if (hf == 0) {
-      const int br = ne - 1 - (j + kTM);   // reversed index of row j
-      pa = ext + 3 * ne + br; pin = ext + 4 * ne + br; pout = ext + 5 * ne + br + 1;
-    } else {
-      const int bu = j + kTM + 1;          // index of row j + 1
-      pa = ext + bu; pin = ext + 2 * ne + bu - 1; pout = ext + ne + bu;
-    }
-    const double cen = (hf == 0) ? 1.0 : 0.0;
+    // (selects, not branches: the two lanes of a pair sit in the same warp and must stay converged for the shuffles)
+    const int br = ne - 1 - (j + kTM);     // reversed index of row j
+    const int bu = j + kTM + 1;            // index of row j + 1
+    const double* MCD_RESTRICT pa = ext + (hf ? bu : 3 * ne + br);
+    const double* MCD_RESTRICT pin = ext + (hf ? 2 * ne + bu - 1 : 4 * ne + br);
+    const double* MCD_RESTRICT pout = ext + (hf ? ne + bu : 5 * ne + br + 1);
+    const double cen = hf ? 0.0 : 1.0;
 #pragma unroll
     for (int k = 0; k < kTH; ++k) x[k] = (k == 0) ? cen : 0.0;
-    // The coefficient loads of a chunk of 4 elements are issued one chunk AHEAD of their use (pinned in place on
+    // The coefficient loads of a chunk of kTChunk elements are issued one chunk AHEAD of their use (pinned in place on
     // the device: the compiler otherwise sinks each load next to its first use and every element waits ~30 cycles
-    // for shared memory -- measured 1 500 cycles per sweep instead of ~400).
+    // for shared memory -- measured 1 500 cycles per sweep instead of ~400).  Chunks the band has not reached are
+    // skipped (uniform branch).
+    constexpr int CH = kTChunk;
     for (int tt = 1; tt < m; tt += 2) {
       const double K1 = cen * s.red[tt], K2 = cen * s.red[tt + 1];
       double ca = ldc(pa), cin = ldc(pin), cout = ldc(pout);    // coefficients of element k (start: k = 0)
-      double fa[4], fo[4], fi[4];                               // coefficients of elements k0+1 .. k0+4 (next in use)
+      double fa[CH], fo[CH], fi[CH];                            // coefficients of elements k0+1 .. k0+CH (next in use)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < CH; ++q) {
         fa[q] = ldc(pa + 1 + q); fo[q] = ldc(pout + 1 + q);
         fi[q] = kSym ? 0.0 : ldc(pin + 1 + q);
       }
@@ -1229,18 +1228,19 @@ struct Chain {
       yc = fma(cin, swap(x[0]), yc);
       yc = fma(cout, x[1], yc);
       const double yp0 = swap(yc);
+      MCD_CLK(19);
 #pragma unroll
-      for (int k0 = 0; k0 < kTH; k0 += 4) {
+      for (int k0 = 0; k0 < kTH; k0 += CH) {
         if (tt + 1 >= k0) {                                     // the band has reached this chunk (uniform)
-          double ga[4], go[4], gi[4];                           // one chunk ahead (clamped to the window)
+          double ga[CH], go[CH], gi[CH];                        // one chunk ahead (clamped to the window)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int e = (k0 + 5 + q < kTH) ? k0 + 5 + q : kTH - 1;
+          for (int q = 0; q < CH; ++q) {
+            const int e = (k0 + CH + 1 + q < kTH) ? k0 + CH + 1 + q : kTH - 1;
             ga[q] = ldc(pa + e); go[q] = ldc(pout + e);
             gi[q] = kSym ? 0.0 : ldc(pin + e);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < CH; ++q) {
             const int k = k0 + q;
             // pass tt of element k+1
             double na = 0.0, nin = 0.0, nout = 0.0, yn = 0.0;
@@ -1259,9 +1259,10 @@ struct Chain {
             ym = yc; yc = yn; ca = na; cin = nin; cout = nout;
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { fa[q] = ga[q]; fo[q] = go[q]; fi[q] = gi[q]; }
+          for (int q = 0; q < CH; ++q) { fa[q] = ga[q]; fo[q] = go[q]; fi[q] = gi[q]; }
         }
       }
+      MCD_CLK(20);
     }
   }
 

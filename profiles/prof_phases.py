@@ -14,7 +14,7 @@ NAMES = {0: "proposal (Philox, thread 0)", 1: "trial profile (basis . coeff)", 2
          6: "m8n8k4 k loop", 7: "likelihood epilogue", 8: "result stores (+ mirror)", 9: "barrier wait after product",
          10: "staged store phase (in-place products)", 11: "final reduction", 12: "Metropolis (thread 0)",
          13: "commit, records, adaptation", 14: "Taylor sweeps (thread 0)", 15: "Taylor band stores (thread 0)",
-         16: "squaring count, Taylor order, h", 17: "between products (loop control, call)", 18: "task decode"}
+         16: "squaring count, Taylor order, h", 17: "between products (loop control, call)", 18: "task decode", 19: "Taylor sweep prologue (loads, centre exchange)", 20: "Taylor sweep chunks"}
 counts, lags, edges, F, w_true = O.synthetic_counts()
 n = 100
 vb, wb = O.cos_basis_center(n, 10), O.cos_basis_border(n, n, 6)
@@ -33,5 +33,5 @@ ch.run(nsteps, mp); torch.cuda.synchronize()
 eng.lib.mcd_debug_phase_clocks(out)
 tot = float(sum(out))
 print("cycles per MC step (CTA 0, thread 0): %.0f" % (tot / nsteps))
-for i in range(19):
+for i in range(21):
     print("%2d %-48s %9.0f cycles/step  %5.1f %%" % (i, NAMES[i], out[i] / nsteps, 100.0 * out[i] / tot))
