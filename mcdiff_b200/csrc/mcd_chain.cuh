@@ -293,8 +293,8 @@ MCD_HOSTDEV size_t pk_index(int i, int j, int nb8) {
   return a <= b ? (size_t)pk_tile(a, b, nb8) * 64 + pk_off(i & 7, j & 7) : (size_t)pk_tile(b, a, nb8) * 64 + pk_off(j & 7, i & 7);
 }
 MCD_HOSTDEV size_t smem_packed_bytes(int np) { return 2 * pk_elems(np) * 8; }
-// global workspace of one chain of the blocked squaring engine: 3 work matrices + the plan's slots
-MCD_HOSTDEV size_t blocked_ws_doubles(const Problem& P, int nslots) { return (size_t)(3 + nslots) * P.np * P.ld; }
+// global workspace of one chain of the blocked squaring engine: 3 packed work matrices + the plan's slots
+MCD_HOSTDEV size_t blocked_ws_doubles(const Problem& P, int nslots) { return (size_t)(3 + nslots) * pk_elems(P.np); }
 
 // mat: storage for XT and B2 (2*np*ld doubles; shared or global), vec: shared storage.
 // panels: mat holds the two nbk x lds operand panels of the blocked squaring engine; packed: two packed symmetric
@@ -356,6 +356,7 @@ struct Chain {
   static constexpr bool kBlocked = (kMode == 1);
   static constexpr bool kGeneral = (kMode == 2);
   static constexpr bool kPacked = (kMode == 3);
+  static constexpr bool kPackedDst = (kMode == 1 || kMode == 3);   // the Taylor polynomial is written in packed tile storage
   Exec& ex;
   const Problem& P;
   Smem s;
@@ -1283,7 +1284,7 @@ struct Chain {
     const int n = P.n, m = tp.m;
     const double sc = tp.scale / s.red[m];
     const int kmax = hf ? m - 1 : m;                               // last element inside the band
-    if (add || kPacked) {
+    if (add || kPackedDst) {
       // the row of element k walks around the ring one step per element.  Packed storage keeps T[i][j] only for
       // tile rows <= tile columns (the mirrored entry is written by the thread of column i).
       int i = hf ? j + 1 : j;                                      // row of element 0
@@ -1294,7 +1295,7 @@ struct Chain {
         if (k > kmax) break;
         const bool inside = P.pbc || (hf ? j + 1 + k < n : k <= j);
         if (inside) {
-          if (kPacked) {
+          if (kPackedDst) {
             if ((i >> 3) <= (j >> 3)) {
               double* q = dst + pk_index(i, j, nb8);
               if (add) *q += x[k] * sc; else *q = x[k] * sc;
@@ -1394,7 +1395,7 @@ struct Chain {
   MCD_HD void taylor_band(const double* diag, const double* lo, const double* up, const TaylorPlan& tp, double* ext,
                           double* dst, int ld) {
     const int n = P.n;
-    const int nzero = kPacked ? (int)pk_elems(P.np) : P.np * ld;
+    const int nzero = kPackedDst ? (int)pk_elems(P.np) : P.np * ld;
     ex.par([&](int tid) {
       for (int e = tid * 2; e < nzero; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
       taylor_coefs(tid, ext, diag, lo, up, tp);
@@ -2162,49 +2163,104 @@ struct Chain {
   // C_10 is stored as its transpose.  The K = 0 partial sums are parked in the destination and
   // picked up again by the same lane at K = 1, which also carries the likelihood epilogue.
   // ------------------------------------------------------------------------------------
-  // Stage one or two nbk x nbk panels (block (K, I) of a workspace matrix) into shared memory with
-  // 16-byte cp.async copies: every thread issues all of its chunks back to back, so the L2 latency
-  // is paid once per panel instead of once per element.
-  MCD_HD void blk_load(double* dA, const double* GA, int KA, int IA, double* dB, const double* GB, int KB, int IB) {
-    const int nbk = P.nbk, lds = P.lds, ldg = P.ld, half = nbk / 2;
-    const double* sa = dA ? GA + (size_t)KA * nbk * ldg + IA * nbk : nullptr;
-    const double* sb = dB ? GB + (size_t)KB * nbk * ldg + IB * nbk : nullptr;
+  // Workspace matrices are symmetric and live in PACKED tile storage in global memory (pk_tile / pk_off over the
+  // whole np x np matrix): 180 KB instead of 353 KB per matrix at 208 bins, so that the three work matrices of all
+  // resident chains (148 x 540 KB = 80 MB) stay inside the 126 MB L2 -- with full squares (157 MB) ncu showed 9 MB of
+  // DRAM traffic per MC step and chain.  The shared-memory panels keep the plain row-major layout of the m8n8k4 loop:
+  //   block (K, I), K < I : every tile is stored -> 16-byte cp.async copies (un-swizzling is a chunk permutation);
+  //   block (K, K)        : stored tiles a <= b as above, their mirror images through registers;
+  //   block (K, I), K > I : the stored block (I, K) is staged as it is and the panel is flagged TRANSPOSED: the
+  //                         fragment loads then walk rows instead of columns (both patterns are conflict free at
+  //                         pitch lds = 4 mod 8).
+  // Returns the transposed flag.
+  MCD_HD bool blk_stage(double* dst, const double* G, int K, int I) {
     ex.par([&](int tid) {
-#if defined(__CUDA_ARCH__)
-      const unsigned a0 = dA ? (unsigned)__cvta_generic_to_shared(dA) : 0u;
-      const unsigned b0 = dB ? (unsigned)__cvta_generic_to_shared(dB) : 0u;
-      // (row, 16-byte column chunk) of this thread's chunks advance incrementally: one integer division per
-      // call instead of one per chunk (a runtime division is ~75 dependent cycles)
-      const int dr = Exec::nthr() / half, dc = Exec::nthr() - dr * half;
-      int r = tid / half, c = tid - r * half;
-      for (; r < nbk; ) {
-        const unsigned so = (unsigned)(r * lds + 2 * c) * 8u;
-        if (sa) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0 + so), "l"(sa + (size_t)r * ldg + 2 * c) : "memory");
-        if (sb) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b0 + so), "l"(sb + (size_t)r * ldg + 2 * c) : "memory");
-        r += dr;
-        c += dc;
-        if (c >= half) { c -= half; ++r; }
-      }
-      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#else
-      for (int e = tid; e < nbk * half; e += Exec::nthr()) {
-        const int r = e / half, c = (e - r * half) * 2;
-        if (sa) { const d2 x = ld2(sa + (size_t)r * ldg + c); st2(dA + r * lds + c, x.x, x.y); }
-        if (sb) { const d2 y = ld2(sb + (size_t)r * ldg + c); st2(dB + r * lds + c, y.x, y.y); }
-      }
-#endif
+      blk_stage_issue(tid, dst, G, K, I);
+      blk_stage_wait();
     });
     MCD_CLK(25);
+    return K > I;
+  }
+  // the copies of one thread, asynchronous on the device (cp.async); blk_stage_wait + a barrier complete them
+  MCD_HD void blk_stage_issue(int tid, double* dst, const double* G, int K, int I) {
+    const int nbk = P.nbk, lds = P.lds, t13 = nbk >> 3, nb8 = P.np >> 3;
+    const bool tr = K > I;
+    const int bi = tr ? I : K, bj = tr ? K : I;
+    const bool diag = (bi == bj);
+    // one item = one row (8 doubles = four 16-byte chunks) of one tile
+    const int nitems = t13 * t13 * 8;
+    for (int e = tid; e < nitems; e += Exec::nthr()) {
+      const int tile = e >> 3, r = e & 7;
+      const int ta = tile / t13, tb = tile - ta * t13;
+      if (diag && ta > tb) continue;
+      const double* src = G + (size_t)pk_tile(bi * t13 + ta, bj * t13 + tb, nb8) * 64 + r * 8;
+      double* drow = dst + (size_t)(ta * 8 + r) * lds + tb * 8;
+      const int sw = ((r >> 1) & 1) << 1;                       // stored chunk cs holds logical chunk cs ^ sw
+#if defined(__CUDA_ARCH__)
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared(drow);
+#pragma unroll
+      for (int cs = 0; cs < 4; ++cs)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (unsigned)(((cs ^ sw) * 2) * 8)), "l"(src + 2 * cs) : "memory");
+#else
+      for (int cs = 0; cs < 4; ++cs) { drow[(cs ^ sw) * 2] = src[2 * cs]; drow[(cs ^ sw) * 2 + 1] = src[2 * cs + 1]; }
+#endif
+      if (diag && ta < tb) {                                     // mirror image of the tile row: column r of tile (tb, ta)
+#pragma unroll
+        for (int cs = 0; cs < 4; ++cs) {
+          const d2 x = ld2(src + 2 * cs);
+          const int c = (cs ^ sw) * 2;
+          dst[(size_t)(tb * 8 + c) * lds + ta * 8 + r] = x.x;
+          dst[(size_t)(tb * 8 + c + 1) * lds + ta * 8 + r] = x.y;
+        }
+      }
+    }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  }
+  MCD_HD void blk_stage_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
   }
 
-  // One block: D (+)= A^T B.  sym: diagonal block (upper tiles, mirrored inside the block on the final
-  // pass); otherwise the full block, whose transpose goes to Dt on the final pass.  (i_off, j_off):
-  // position of the block in the full matrix (likelihood epilogue).
-  MCD_HD void blk_mma(const double* A, const double* B, bool sym, double* D, double* Dt, bool first, bool fin,
-                      int i_off, int j_off, const int* cnt, const int* nsy, double* Pl) {
-    const int n = P.n, np = P.np, ldg = P.ld, lds = P.lds, nbk = P.nbk, nb8 = nbk / 8;
-    const int ncg = (nb8 + 3) / 4, nrp = (nb8 + 1) / 2;
-    const int ntask = sym ? s.sc->mma_tasks : ncg * nrp;
+#if defined(__CUDA_ARCH__)
+  // k loop of one warp task with separate strides for the two operands (a transposed panel is walked along its rows)
+  template <int NA>
+  static __device__ __forceinline__ void mma_loop2(unsigned pa, unsigned pb, int stepA, int stepB, int nk4, int offA0,
+                                                   int offA1, const int (&offB)[kTilesPerWarp], double (&c)[kTilesPerWarp][2]) {
+#pragma unroll 2
+    for (int it = 0; it < nk4; ++it) {
+      const double a0 = lds64(pa + offA0);
+      const double a1 = (NA < kTilesPerWarp) ? lds64(pa + offA1) : 0.0;
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) {
+        const double b = lds64(pb + offB[t]);
+        const double a = (t < NA) ? a0 : a1;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1])
+                     : "d"(a), "d"(b));
+      }
+      pa += stepA;
+      pb += stepB;
+    }
+  }
+#endif
+
+  // One block: D_IJ (+)= A^T B, where the panel A holds block (K, I) of X (or, trA, its transpose (I, K)) and B block
+  // (K, J) of Y (trB: (J, K)).  sym: diagonal block (upper tiles only).  D: packed global matrix, (bI, bJ) the block.
+  // The partial sums over K are parked in D and picked up again by the same lane; the last K carries the epilogue.
+  // pf_dst != nullptr: the copies of block (pfK, pfI) of pf_G into the panel pf_dst (not an operand of this call) are
+  // issued before the k loops and completed behind them -- staging overlaps the MMAs.
+  MCD_HD void blk_mma(const double* A, bool trA, const double* B, bool trB, bool sym, double* D, int bI, int bJ, bool first,
+                      bool fin, const int* cnt, const int* nsy, double* Pl, double* pf_dst = nullptr,
+                      const double* pf_G = nullptr, int pfK = 0, int pfI = 0) {
+    const int n = P.n, np = P.np, lds = P.lds, nbk = P.nbk, nb8 = nbk / 8, gnb8 = np >> 3;
+    const int i_off = bI * nbk, j_off = bJ * nbk;
+    // full block: the nb8 x nb8 tiles in row-major order, cut into runs of kTilesPerWarp -- a run touches at most two
+    // tile rows (nb8 >= kTilesPerWarp), which is what the two A fragments of the k loop serve; 22 tasks = two rounds
+    // of 12 warps at 13 x 13 tiles (2-row x 4-column patches needed 28 tasks = three rounds)
+    const int ntask = sym ? s.sc->mma_tasks : (nb8 * nb8 + kTilesPerWarp - 1) / kTilesPerWarp;
     const int nwarp = Exec::nthr() / 32;
     const bool epi = fin && cnt != nullptr;
     for (int base = 0; base < ntask; base += nwarp) {
@@ -2212,55 +2268,67 @@ struct Chain {
         const int warp = tid >> 5, lane = tid & 31;
         const int q = base + warp;
         const bool active = q < ntask;
+        if (pf_dst && base == 0) blk_stage_issue(tid, pf_dst, pf_G, pfK, pfI);
         int nt = 0, na = 1, rowA = 0, rowB = 0;
         int jbs[kTilesPerWarp];
         if (sym) {
-          const unsigned char* wt = s.wtab + 16 * warp;
+          const unsigned char* wt = s.wtab + 16 * (active ? q : 0);
           if (active) { nt = wt[0]; na = wt[1]; rowA = wt[2]; rowB = wt[3]; }
 #pragma unroll
           for (int t = 0; t < kTilesPerWarp; ++t) jbs[t] = active ? wt[4 + t] : 0;
         } else {
-          const int rp = active ? q / ncg : 0, cg = active ? q - rp * ncg : 0;
-          const int col0 = 4 * cg, ncol = (nb8 - col0 < 4) ? nb8 - col0 : 4;
-          const bool two = 2 * rp + 1 < nb8;
-          rowA = 2 * rp; rowB = two ? rowA + 1 : rowA;
-          na = ncol; nt = active ? (two ? 2 * ncol : ncol) : 0;
+          const int t0 = active ? q * kTilesPerWarp : 0;
+          const int left = nb8 * nb8 - t0;
+          nt = active ? (left < kTilesPerWarp ? left : kTilesPerWarp) : 0;
+          rowA = t0 / nb8;
+          const int c0 = t0 - rowA * nb8;
+          na = (nb8 - c0 < nt) ? nb8 - c0 : nt;              // tiles left in the first row
+          rowB = (na < nt) ? rowA + 1 : rowA;
 #pragma unroll
-          for (int t = 0; t < kTilesPerWarp; ++t) jbs[t] = col0 + ((t < nt) ? (t < na ? t : t - na) : 0);
+          for (int t = 0; t < kTilesPerWarp; ++t) jbs[t] = (t < na) ? c0 + t : ((t < nt) ? t - na : 0);
+          if (na == 0) na = 1;
         }
         const int fr = lane >> 2, fk = lane & 3;
+        const int swz = ((fr >> 1) & 1) << 2;
         double c[kTilesPerWarp][2];
         int nsv[kTilesPerWarp][2];
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
           const int ib = (t < na) ? rowA : rowB;
-          const int i = ib * 8 + fr, j = jbs[t] * 8 + 2 * fk;
           c[t][0] = 0.0; c[t][1] = 0.0;
-          if (!first && t < nt) { const d2 x = ld2(D + (size_t)i * ldg + j); c[t][0] = x.x; c[t][1] = x.y; }
+          if (!first && t < nt) {
+            const d2 x = ld2(D + (size_t)pk_tile(bI * nb8 + ib, bJ * nb8 + jbs[t], gnb8) * 64 + fr * 8 + ((2 * fk) ^ swz));
+            c[t][0] = x.x; c[t][1] = x.y;
+          }
           nsv[t][0] = 0; nsv[t][1] = 0;
           if (epi && t < nt) {
-            const int* qn = nsy + (size_t)(i_off + i) * np + j_off + j;
+            const int* qn = nsy + (size_t)(i_off + ib * 8 + fr) * np + j_off + jbs[t] * 8 + 2 * fk;
             nsv[t][0] = qn[0]; nsv[t][1] = qn[1];
           }
         }
         MCD_CLK(5);
         if (active) {
 #if defined(__CUDA_ARCH__)
+          // normal panel: element (k, i) at k * lds + i -> lane base fk * lds + fr, 4 lds doubles per k step, tile row/column
+          // offset 8 doubles; transposed panel: element (k, i) at i * lds + k -> lane base fr * lds + fk, 4 doubles per
+          // k step, tile offset 8 lds doubles
+          const unsigned pa = (unsigned)__cvta_generic_to_shared(A) + (unsigned)(trA ? fr * lds + fk : fk * lds + fr) * 8u;
+          const unsigned pb = (unsigned)__cvta_generic_to_shared(B) + (unsigned)(trB ? fr * lds + fk : fk * lds + fr) * 8u;
+          const int stepA = trA ? 32 : 4 * lds * 8, stepB = trB ? 32 : 4 * lds * 8;
+          const int tileA = trA ? 8 * lds * 8 : 64, tileB = trB ? 8 * lds * 8 : 64;
           int offB[kTilesPerWarp];
 #pragma unroll
-          for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = jbs[t] * 64;
-          const unsigned ax = (unsigned)__cvta_generic_to_shared(A) + (unsigned)(fk * lds + fr) * 8u;
-          const unsigned ay = (unsigned)__cvta_generic_to_shared(B) + (unsigned)(fk * lds + fr) * 8u;
-          const int pitch4 = 4 * lds * 8, nk4 = nbk / 4;
+          for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = jbs[t] * tileB;
+          const int nk4 = nbk / 4;
           switch (na) {
-            case 1: mma_loop<1>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 2: mma_loop<2>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 3: mma_loop<3>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 4: mma_loop<4>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 5: mma_loop<5>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 6: mma_loop<6>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            case 7: mma_loop<7>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
-            default: mma_loop<8>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
+            case 1: mma_loop2<1>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 2: mma_loop2<2>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 3: mma_loop2<3>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 4: mma_loop2<4>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 5: mma_loop2<5>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 6: mma_loop2<6>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            case 7: mma_loop2<7>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
+            default: mma_loop2<8>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
           }
 #else
           for (int t = 0; t < nt; ++t) {
@@ -2269,7 +2337,8 @@ struct Chain {
             for (int e = 0; e < 2; ++e) {
               const int j = jbs[t] * 8 + 2 * fk + e;
               double acc = c[t][e];
-              for (int k = 0; k < nbk; ++k) acc = fma(A[k * lds + i], B[k * lds + j], acc);
+              for (int k = 0; k < nbk; ++k)
+                acc = fma(trA ? A[i * lds + k] : A[k * lds + i], trB ? B[j * lds + k] : B[k * lds + j], acc);
               c[t][e] = acc;
             }
           }
@@ -2315,23 +2384,15 @@ struct Chain {
           s.part[tid] += part;
         }
         MCD_CLK(7);
+        // one 8 x 8 tile = 512 contiguous bytes per warp and tile; no mirror images in packed storage
 #pragma unroll
         for (int t = 0; t < kTilesPerWarp; ++t) {
           if (t < nt) {
-            const int ib = (t < na) ? rowA : rowB, jb = jbs[t];
-            const int i = ib * 8 + fr, j = jb * 8 + 2 * fk;
-            st2(D + (size_t)i * ldg + j, c[t][0], c[t][1]);
-            if (fin) {
-              if (!sym) {
-                Dt[(size_t)j * ldg + i] = c[t][0];
-                Dt[(size_t)(j + 1) * ldg + i] = c[t][1];
-              } else if (ib != jb) {
-                D[(size_t)j * ldg + i] = c[t][0];
-                D[(size_t)(j + 1) * ldg + i] = c[t][1];
-              }
-            }
+            const int ib = (t < na) ? rowA : rowB;
+            st2(D + (size_t)pk_tile(bI * nb8 + ib, bJ * nb8 + jbs[t], gnb8) * 64 + fr * 8 + ((2 * fk) ^ swz), c[t][0], c[t][1]);
           }
         }
+        if (pf_dst && base + nwarp >= ntask) blk_stage_wait();      // last round: the prefetched panel is complete at the barrier
         MCD_CLK(8);
       });
       MCD_CLK(9);
@@ -2345,30 +2406,53 @@ struct Chain {
   // staged, X_K,I+1, is the next I's A (pointer swap): 1 + nblk (nblk-1)/2 panel loads per K (2 for nblk = 2).
   // General product: J alternates direction from one I to the next, so the B panel at the turn is reused.
   MCD_HD void blk_product(const double* Xg, const double* Yg, double* Dg, const int* cnt, const int* nsy, double* Pl) {
-    const int nbk = P.nbk, ldg = P.ld, nblk = P.nblk;
+    const int nblk = P.nblk;
     const bool same = (Xg == Yg);
+    if (same && nblk == 2) {
+      // squaring with 2 x 2 blocks: b0 = X_K0, b1 = X_K1.  C_00 needs b0 only (X_K1 is staged into b1 meanwhile),
+      // C_01 needs both, C_11 needs b1 only (X_K+1,0 is staged into b0 meanwhile): every copy but the first overlaps MMAs.
+      double* b0 = s.XT;
+      double* b1 = s.B2;
+      bool t0 = blk_stage(b0, Xg, 0, 0);
+      for (int K = 0; K < 2; ++K) {
+        const bool first = (K == 0), fin = (K == 1);
+        blk_mma(b0, t0, b0, t0, true, Dg, 0, 0, first, fin, cnt, nsy, Pl, b1, Xg, K, 1);
+        const bool t1 = K > 1;
+        blk_mma(b0, t0, b1, t1, false, Dg, 0, 1, first, fin, cnt, nsy, Pl);
+        if (K == 0) {
+          blk_mma(b1, t1, b1, t1, true, Dg, 1, 1, first, fin, cnt, nsy, Pl, b0, Xg, 1, 0);
+          t0 = true;                       // block (1, 0) = the stored block (0, 1), transposed
+        } else {
+          blk_mma(b1, t1, b1, t1, true, Dg, 1, 1, first, fin, cnt, nsy, Pl);
+        }
+      }
+      return;
+    }
     for (int K = 0; K < nblk; ++K) {
       double* A = s.XT;
       double* B = s.B2;
+      bool trA = false, trB = false;
       bool have_A = false;     // squaring: A already holds X_KI (it was the previous I's last B panel)
       int b_has = -1;          // general product: column block of Y currently staged in B
       for (int I = 0; I < nblk; ++I) {
-        if (!have_A) blk_load(A, Xg, K, I, nullptr, nullptr, 0, 0);
+        if (!have_A) trA = blk_stage(A, Xg, K, I);
         have_A = false;
         const bool down = same || (I & 1);
         for (int q = 0; q < nblk - I; ++q) {
           const int J = down ? nblk - 1 - q : I + q;
           const double* Bp = B;
-          if (same && J == I) Bp = A;
+          bool trBp = trB;
+          if (same && J == I) { Bp = A; trBp = trA; }
           else if (same || b_has != J) {
-            blk_load(nullptr, nullptr, 0, 0, B, Yg, K, J);
+            trB = blk_stage(B, Yg, K, J);
+            trBp = trB;
             b_has = J;
           }
-          blk_mma(A, Bp, I == J, Dg + (size_t)I * nbk * ldg + J * nbk, Dg + (size_t)J * nbk * ldg + I * nbk, K == 0,
-                  K == nblk - 1, I * nbk, J * nbk, cnt, nsy, Pl);
+          blk_mma(A, trA, Bp, trBp, I == J, Dg, I, J, K == 0, K == nblk - 1, cnt, nsy, Pl);
         }
         if (same && I + 1 < nblk) {   // B holds X_K,I+1
           double* tmp = A; A = B; B = tmp;
+          trA = trB;
           have_A = true;
         }
       }
@@ -2377,13 +2461,13 @@ struct Chain {
 
   // likelihood terms of a kernel sitting in the global workspace (pairs i <= j)
   MCD_HD void blk_buffer_loglike(const double* G, const int* cnt, const int* nsy, double* Pl) {
-    const int n = P.n, np = P.np, ldg = P.ld;
+    const int n = P.n, np = P.np;
     ex.par([&](int tid) {
       double part = 0.0;
       for (int e = tid; e < n * n; e += Exec::nthr()) {
         const int i = e / n, j = e - i * n;
         if (j < i) continue;
-        const double g = G[(size_t)i * ldg + j];
+        const double g = pk_get(G, i, j);
         part += pair_term(g, nsy[(size_t)i * np + j], i, j, cnt);
         if (Pl) {
           Pl[(size_t)i * n + j] = s.ea[i] * g * s.eb[j];
@@ -2394,21 +2478,13 @@ struct Chain {
     });
   }
 
-  MCD_HD void blk_copy(double* dst, const double* src) {
-    const int total = P.np * P.ld;
-    ex.par([&](int tid) {
-      for (int e = tid * 2; e < total; e += 2 * Exec::nthr()) {
-        const d2 x = ld2(src + e);
-        st2(dst + e, x.x, x.y);
-      }
-    });
-  }
+  MCD_HD void blk_copy(double* dst, const double* src) { pk_copy(dst, src); }
 
   // log L with the blocked engine.  ws: blocked_ws_doubles(P, pl.nslots) doubles of this chain.
   MCD_HD double evaluate_blk(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* ws,
                              int taylor_m, double* Pout, int* squarings_out) {
     const int n = P.n, np = P.np, ldg = P.ld;
-    const size_t nn = (size_t)n * n, melems = (size_t)np * ldg;
+    const size_t nn = (size_t)n * n, melems = pk_elems(np);
     double* buf[3] = {ws, ws + melems, ws + 2 * melems};
     double* slots = ws + 3 * melems;
     build_S(v, w);
