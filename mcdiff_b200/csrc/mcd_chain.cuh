@@ -1523,7 +1523,12 @@ struct Chain {
         const double* Y;
         double* D;
         int store;
-        if (fast) {
+        if (fast && P.nlag <= 4) {
+          // t, 2t, 3t, 4t: O = G(2t) is stored once, G(3t) = G(2t) G(t) and G(4t) = G(2t)^2 are needed for their
+          // likelihood terms only -- no in-place product (register staging, a second barrier phase) at all
+          X = (i == 1) ? G0 : O; Y = (i == 3) ? O : G0; D = O;
+          store = (i == 1 && P.nlag > 2) ? 1 : 0;
+        } else if (fast) {
           X = (i == 1) ? G0 : O; Y = G0; D = O;
           store = (i + 1 < P.nlag) ? (i == 1 ? 1 : 2) : 0;
         } else {
@@ -2154,14 +2159,14 @@ struct Chain {
   }
 
   // ------------------------------------------------------------------------------------
-  // Blocked squaring engine (kBlocked, kMaxSmemBins < n <= 2 kMaxSmemBins).
-  // The np x np matrices (np = 2 nbk) live in a per-CTA global workspace that stays in L2; a product
-  //   C_IJ = sum_K X_KI^T Y_KJ      (I, J, K in {0, 1}; X, Y symmetric and commuting)
+  // Blocked squaring engine (kBlocked, kMaxSmemBins < n <= kMaxBlocks kMaxSmemBins).
+  // The np x np matrices (np = nblk nbk) live in a per-CTA global workspace that stays in L2; a product
+  //   C_IJ = sum_K X_KI^T Y_KJ      (I <= J; X, Y symmetric and commuting)
   // is done block by block with the nbk x nbk operand panels staged in the two shared-memory buffers
-  // and the m8n8k4 loop of the in-smem engine.  Diagonal blocks use the symmetric warp tasks of
-  // build_tables, the off-diagonal block C_01 is cut into tasks of 2 tile rows x 4 tile columns;
-  // C_10 is stored as its transpose.  The K = 0 partial sums are parked in the destination and
-  // picked up again by the same lane at K = 1, which also carries the likelihood epilogue.
+  // and an m8n8k4 loop like that of the in-smem engine.  Diagonal blocks use the symmetric warp tasks of
+  // build_tables, an off-diagonal block is cut into row-major runs of 8 tiles.  The partial sums over K
+  // are parked in the destination and picked up again by the same lane at the next K; the last K carries
+  // the likelihood epilogue.
   // ------------------------------------------------------------------------------------
   // Workspace matrices are symmetric and live in PACKED tile storage in global memory (pk_tile / pk_off over the
   // whole np x np matrix): 180 KB instead of 353 KB per matrix at 208 bins, so that the three work matrices of all

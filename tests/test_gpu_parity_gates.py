@@ -204,10 +204,10 @@ def test_config3_shape_mc_replay(engine):
     lags = np.array([5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0])
     counts = O.synthetic_counts(200, lags, seed=3, total=1.0e6, dz=0.5)[0]
     ndec, dec, prob = _device_vs_replay(engine, counts, lags, 12, 8, -np.log(0.25), 0.05, 0.05, 0.1,
-                                        nch=4, nsteps=48, nupd=16.0, move_t0=False, seed=33, off=7,
-                                        chunks=(30, 18), method=0)
+                                        nch=4, nsteps=28, nupd=12.0, move_t0=False, seed=33, off=7,
+                                        chunks=(18, 10), method=0)
     assert prob.squaring_ok and not prob.in_smem                          # the blocked engine ran it
-    assert ndec == 4 * 48
+    assert ndec == 4 * 28
     assert 0 < int((dec & 1).sum()) < dec.size
 
 
