@@ -1396,19 +1396,27 @@ struct Chain {
                           double* dst, int ld) {
     const int n = P.n;
     const int nzero = kPackedDst ? (int)pk_elems(P.np) : P.np * ld;
+    // a cluster shares dst (global): every CTA clears and fills its share, with a cluster barrier in between
+    const int cs = ex.csize, cr = ex.crank;
+    const int zper = ((nzero / 2 + cs - 1) / cs) * 2;
+    const int z_lo = cr * zper, z_hi = (z_lo + zper < nzero) ? z_lo + zper : nzero;
+    const int cper = (n + cs - 1) / cs;
+    const int c_lo = cr * cper, c_hi = (c_lo + cper < n) ? c_lo + cper : n;
     ex.par([&](int tid) {
-      for (int e = tid * 2; e < nzero; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
+      for (int e = z_lo + tid * 2; e < z_hi; e += 2 * Exec::nthr()) st2(dst + e, 0.0, 0.0);
       taylor_coefs(tid, ext, diag, lo, up, tp);
     });
+    ex.cluster_sync();
     MCD_CLK(3);
     ex.par([&](int tid) {
       const int per = Exec::nthr() / 2;
-      for (int j0 = 0; j0 < n; j0 += per) {
-        if (j0 + ((tid >> 5) << 4) >= n) break;          // the whole warp is past the last column
+      for (int j0 = c_lo; j0 < c_hi; j0 += per) {
+        if (j0 + ((tid >> 5) << 4) >= c_hi) break;       // the whole warp is past the last column
         const int j = j0 + pair_col(tid);
-        taylor_pair<kSym>(tid, j < n, j < n ? j : n - 1, ext, tp, dst, ld);
+        taylor_pair<kSym>(tid, j < c_hi, j < c_hi ? j : c_hi - 1, ext, tp, dst, ld);
       }
     });
+    ex.cluster_sync();
   }
 
   // lagt must be an arithmetic progression lagt[l] = (l+1) lagt[0] (checked on the host).
@@ -1932,8 +1940,14 @@ struct Chain {
   }
 #endif
 
-  // element (i, j) of a packed symmetric matrix
-  MCD_HD double pk_get(const double* G, int i, int j) const { return G[pk_index(i, j, P.np >> 3)]; }
+  // element (i, j) of a packed symmetric matrix (global workspace matrices are read past L1: the other CTA of a
+  // cluster may have written them)
+  MCD_HD double pk_get(const double* G, int i, int j) const {
+#if defined(__CUDA_ARCH__)
+    if (kBlocked) return __ldcg(G + pk_index(i, j, P.np >> 3));
+#endif
+    return G[pk_index(i, j, P.np >> 3)];
+  }
 
   // D <- X Y for packed symmetric commuting operands; D is another packed buffer (shared memory or the global
   // scratch), never an operand.  cnt != nullptr: likelihood terms of a lag time (as dmma_product).  store: 0 / 1.
@@ -2209,13 +2223,46 @@ struct Chain {
 #else
       for (int cs = 0; cs < 4; ++cs) { drow[(cs ^ sw) * 2] = src[2 * cs]; drow[(cs ^ sw) * 2 + 1] = src[2 * cs + 1]; }
 #endif
-      if (diag && ta < tb) {                                     // mirror image of the tile row: column r of tile (tb, ta)
+    }
+    if (diag) {
+      // mirror images of the tiles above the diagonal (column r of tile (tb, ta) = row r of tile (ta, tb)), through
+      // registers: the loads of three tile rows are issued together (L2 latency paid once per group), then their
+      // scattered stores
+      constexpr int GRP = 3;
+      for (int e0 = tid; e0 < nitems; e0 += GRP * Exec::nthr()) {
+        d2 x[GRP][4];
+        int ta_[GRP], tb_[GRP], r_[GRP];
+        bool on[GRP];
 #pragma unroll
-        for (int cs = 0; cs < 4; ++cs) {
-          const d2 x = ld2(src + 2 * cs);
-          const int c = (cs ^ sw) * 2;
-          dst[(size_t)(tb * 8 + c) * lds + ta * 8 + r] = x.x;
-          dst[(size_t)(tb * 8 + c + 1) * lds + ta * 8 + r] = x.y;
+        for (int g = 0; g < GRP; ++g) {
+          const int e = e0 + g * Exec::nthr();
+          const int tile = e >> 3;
+          r_[g] = e & 7;
+          ta_[g] = tile / t13; tb_[g] = tile - ta_[g] * t13;
+          on[g] = e < nitems && ta_[g] < tb_[g];
+          if (on[g]) {
+            const double* src = G + (size_t)pk_tile(bi * t13 + ta_[g], bj * t13 + tb_[g], nb8) * 64 + r_[g] * 8;
+#pragma unroll
+            for (int cs = 0; cs < 4; ++cs) {
+#if defined(__CUDA_ARCH__)
+              const double2 xg = __ldcg(reinterpret_cast<const double2*>(src + 2 * cs));
+              x[g][cs] = d2{xg.x, xg.y};
+#else
+              x[g][cs] = ld2(src + 2 * cs);
+#endif
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < GRP; ++g) {
+          if (!on[g]) continue;
+          const int sw = ((r_[g] >> 1) & 1) << 1;
+#pragma unroll
+          for (int cs = 0; cs < 4; ++cs) {
+            const int c = (cs ^ sw) * 2;
+            dst[(size_t)(tb_[g] * 8 + c) * lds + ta_[g] * 8 + r_[g]] = x[g][cs].x;
+            dst[(size_t)(tb_[g] * 8 + c + 1) * lds + ta_[g] * 8 + r_[g]] = x[g][cs].y;
+          }
         }
       }
     }
@@ -2259,21 +2306,25 @@ struct Chain {
   // issued before the k loops and completed behind them -- staging overlaps the MMAs.
   MCD_HD void blk_mma(const double* A, bool trA, const double* B, bool trB, bool sym, double* D, int bI, int bJ, bool first,
                       bool fin, const int* cnt, const int* nsy, double* Pl, double* pf_dst = nullptr,
-                      const double* pf_G = nullptr, int pfK = 0, int pfI = 0) {
+                      const double* pf_G = nullptr, int pfK = 0, int pfI = 0, int share = 0, int nshare = 1) {
     const int n = P.n, np = P.np, lds = P.lds, nbk = P.nbk, nb8 = nbk / 8, gnb8 = np >> 3;
     const int i_off = bI * nbk, j_off = bJ * nbk;
     // full block: the nb8 x nb8 tiles in row-major order, cut into runs of kTilesPerWarp -- a run touches at most two
     // tile rows (nb8 >= kTilesPerWarp), which is what the two A fragments of the k loop serve; 22 tasks = two rounds
     // of 12 warps at 13 x 13 tiles (2-row x 4-column patches needed 28 tasks = three rounds)
-    const int ntask = sym ? s.sc->mma_tasks : (nb8 * nb8 + kTilesPerWarp - 1) / kTilesPerWarp;
+    const int ntask_all = sym ? s.sc->mma_tasks : (nb8 * nb8 + kTilesPerWarp - 1) / kTilesPerWarp;
+    // share / nshare: this call does the tasks [task_lo, ntask) only (a CTA's part of a block split over a cluster)
+    const int tper = (ntask_all + nshare - 1) / nshare;
+    const int task_lo = share * tper;
+    const int ntask = (task_lo + tper < ntask_all) ? task_lo + tper : ntask_all;
     const int nwarp = Exec::nthr() / 32;
     const bool epi = fin && cnt != nullptr;
-    for (int base = 0; base < ntask; base += nwarp) {
+    for (int base = task_lo; base < ntask; base += nwarp) {
       ex.par([&](int tid) {
         const int warp = tid >> 5, lane = tid & 31;
         const int q = base + warp;
         const bool active = q < ntask;
-        if (pf_dst && base == 0) blk_stage_issue(tid, pf_dst, pf_G, pfK, pfI);
+        if (pf_dst && base == task_lo) blk_stage_issue(tid, pf_dst, pf_G, pfK, pfI);
         int nt = 0, na = 1, rowA = 0, rowB = 0;
         int jbs[kTilesPerWarp];
         if (sym) {
@@ -2413,6 +2464,34 @@ struct Chain {
   MCD_HD void blk_product(const double* Xg, const double* Yg, double* Dg, const int* cnt, const int* nsy, double* Pl) {
     const int nblk = P.nblk;
     const bool same = (Xg == Yg);
+    if (ex.csize == 2 && nblk == 2) {
+      // Two SMs per chain: CTA r owns the diagonal block C_rr and half of the tasks of C_01; after the product a
+      // cluster barrier publishes Dg.  Panels: b[i] holds the column-block i operand.
+      const int r = ex.crank, o = 1 - r;
+      double* b[2] = {s.XT, s.B2};
+      for (int K = 0; K < 2; ++K) {
+        const bool first = (K == 0), fin = (K == 1);
+        if (same) {
+          // b[i] = X_Ki.  C_01 = X_K0^T X_K1 first (both panels), then C_rr on b[r] while X_K+1,o streams into b[o].
+          bool t[2];
+          if (K == 0) { t[r] = blk_stage(b[r], Xg, 0, r); t[o] = blk_stage(b[o], Xg, 0, o); }
+          else { t[o] = (1 > o); t[r] = blk_stage(b[r], Xg, 1, r); }            // X_1o was prefetched during K = 0
+          blk_mma(b[0], t[0], b[1], t[1], false, Dg, 0, 1, first, fin, cnt, nsy, Pl, nullptr, nullptr, 0, 0, r, 2);
+          if (K == 0) blk_mma(b[r], t[r], b[r], t[r], true, Dg, r, r, first, fin, cnt, nsy, Pl, b[o], Xg, 1, o);
+          else blk_mma(b[r], t[r], b[r], t[r], true, Dg, r, r, first, fin, cnt, nsy, Pl);
+        } else {
+          // C_rr = X_Kr^T Y_Kr, then the CTA's half of C_01 = X_K0^T Y_K1: b[0] <- X panels, b[1] <- Y panels
+          bool tx = blk_stage(b[0], Xg, K, r);
+          bool ty = blk_stage(b[1], Yg, K, r);
+          blk_mma(b[0], tx, b[1], ty, true, Dg, r, r, first, fin, cnt, nsy, Pl);
+          if (r == 0) ty = blk_stage(b[1], Yg, K, 1);     // X_K0 stays, Y_K1 comes
+          else tx = blk_stage(b[0], Xg, K, 0);            // Y_K1 stays, X_K0 comes
+          blk_mma(b[0], tx, b[1], ty, false, Dg, 0, 1, first, fin, cnt, nsy, Pl, nullptr, nullptr, 0, 0, r, 2);
+        }
+      }
+      ex.cluster_sync();
+      return;
+    }
     if (same && nblk == 2) {
       // squaring with 2 x 2 blocks: b0 = X_K0, b1 = X_K1.  C_00 needs b0 only (X_K1 is staged into b1 meanwhile),
       // C_01 needs both, C_11 needs b1 only (X_K+1,0 is staged into b0 meanwhile): every copy but the first overlaps MMAs.
@@ -2525,9 +2604,12 @@ struct Chain {
         blk_product(G, G, O, last ? cnt_e : nullptr, last ? nsy_e : nullptr, last ? Pl0 : nullptr);
         double* tmp = G; G = O; O = tmp;
       }
-      if (nsq == 0 && is_first_lag) blk_buffer_loglike(G, cnt_e, nsy_e, Pl0);
+      if (nsq == 0 && is_first_lag && ex.crank == 0) blk_buffer_loglike(G, cnt_e, nsy_e, Pl0);
       nsq_total += nsq;
-      if (!fast && pl.chain_slot[c] >= 0) blk_copy(slots + (size_t)pl.chain_slot[c] * melems, G);
+      if (!fast && pl.chain_slot[c] >= 0) {
+        if (ex.crank == 0) blk_copy(slots + (size_t)pl.chain_slot[c] * melems, G);
+        ex.cluster_sync();
+      }
       R = G;
     }
     // ---- remaining lags: R <- R G(delta_i), out of place into one of the two buffers that do not
@@ -2544,7 +2626,7 @@ struct Chain {
         const int* nsy = P.nsym + (size_t)l * np * np;
         double* Pl = Pout ? Pout + (size_t)l * nn : nullptr;
         if (!fast && pl.op_slot[i] < 0) {
-          blk_buffer_loglike(R, cnt, nsy, Pl);
+          if (ex.crank == 0) blk_buffer_loglike(R, cnt, nsy, Pl);
         } else {
           const double* Y = fast ? G0 : slots + (size_t)pl.op_slot[i] * melems;
           double* D = fr[which];
@@ -2553,7 +2635,10 @@ struct Chain {
           R = D;
           which ^= 1;
         }
-        if (!fast && pl.park[i] >= 0) blk_copy(slots + (size_t)pl.park[i] * melems, R);
+        if (!fast && pl.park[i] >= 0) {
+          if (ex.crank == 0) blk_copy(slots + (size_t)pl.park[i] * melems, R);
+          ex.cluster_sync();
+        }
       }
     }
     if (squarings_out) *squarings_out = bad ? -1 : nsq_total;
@@ -2561,7 +2646,19 @@ struct Chain {
       ex.single([&]() { s.sc->status |= ST_NONFINITE; });
       return nan("");
     }
-    return s.sc->lin + ex.sum([&](int tid) { return s.part[tid]; });
+    const double mine = ex.sum([&](int tid) { return s.part[tid]; });
+    if (ex.csize == 1) return s.sc->lin + mine;
+    // cluster: the CTAs exchange their partial sums through the tail of the workspace and add them in rank order
+    double* xch = ws + blocked_ws_doubles(P, plan_slots(P));
+    ex.single([&]() { xch[ex.crank] = mine; });
+    ex.cluster_sync();
+    double tot = s.sc->lin;
+#if defined(__CUDA_ARCH__)
+    for (int q = 0; q < ex.csize; ++q) tot += __ldcg(xch + q);
+#else
+    for (int q = 0; q < ex.csize; ++q) tot += xch[q];
+#endif
+    return tot;
   }
 
   // Full likelihood of the profile (v, w) at lag times lagt.
@@ -2834,13 +2931,13 @@ struct Chain {
               for (int i = tid; i < np; i += Exec::nthr()) s.v[i] = s.vt[i];
               if (ncosF > 0) {
                 for (int c = tid; c < ncosF; c += Exec::nthr()) s.vc[c] = s.ct[c];
-                if (tid == 0) io.naccv_coeff[chain * ncosF + idx] += 1;
+                if (tid == 0 && ex.crank == 0) io.naccv_coeff[chain * ncosF + idx] += 1;
               }
             } else {
               for (int i = tid; i < np; i += Exec::nthr()) s.w[i] = s.wt[i];
               if (ncosD > 0) {
                 for (int c = tid; c < ncosD; c += Exec::nthr()) s.wc[c] = s.ct[c];
-                if (tid == 0) io.naccw_coeff[chain * ncosD + idx] += 1;
+                if (tid == 0 && ex.crank == 0) io.naccw_coeff[chain * ncosD + idx] += 1;
               }
             }
           });
@@ -2853,6 +2950,7 @@ struct Chain {
       // ---- per-step records, sampling (lib/log.py:35-58), adaptation (lib/MCState.py:371-393) ----
       ex.par([&](int tid) {
         const long long j = sc->step + 1;
+        if (ex.crank != 0) return;          // the CTAs of a cluster hold identical copies of the chain: rank 0 reports
         if (tid == 0) {
           if (io.decisions)
             io.decisions[(size_t)chain * nsteps + it] =
@@ -2890,6 +2988,7 @@ struct Chain {
     MCD_CLK_END();
     // ---- store chain state ----
     ex.par([&](int tid) {
+      if (ex.crank != 0) return;
       for (int i = tid; i < n; i += Exec::nthr()) io.v[chain * n + i] = s.v[i];
       for (int i = tid; i < dim_w; i += Exec::nthr()) io.w[chain * dim_w + i] = s.w[i];
       for (int i = tid; i < ncosF; i += Exec::nthr()) io.vcoef[chain * ncosF + i] = s.vc[i];

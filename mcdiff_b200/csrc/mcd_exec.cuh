@@ -136,9 +136,19 @@ struct DeviceExec {
   int tid;
   double* red;  // shared scratch, >= 32 doubles
   double regs_[kMaxRegs];
+  // A chain may be shared by the CTAs of a thread-block cluster (blocked engine: two SMs per chain).  Every CTA runs
+  // the same control flow on the same data; crank / csize say which share of the parallel work is this CTA's.
+  int crank = 0, csize = 1;
 
   __device__ DeviceExec(double* red_scratch) : tid(threadIdx.x), red(red_scratch) {}
   static __device__ __forceinline__ int nthr() { return kThreads; }
+  // Barrier over all threads of the cluster; global-memory writes before it are visible to every CTA behind it.
+  __device__ __forceinline__ void cluster_sync() {
+    if (csize > 1) {
+      __threadfence();
+      asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+  }
 
   template <class F>
   __device__ __forceinline__ void par(F f) {
@@ -219,8 +229,10 @@ struct DeviceExec {
 #if !defined(__CUDACC__)
 struct HostExec {
   double* store;  // kThreads * kMaxRegs doubles
+  int crank = 0, csize = 1;   // the emulation runs a chain as ONE CTA
   explicit HostExec(double* s) : store(s) {}
   static int nthr() { return kThreads; }
+  void cluster_sync() {}
   template <class F>
   void par(F f) {
     for (int t = 0; t < kThreads; ++t) f(t);

@@ -167,6 +167,25 @@ mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
   ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * blocked_ws_doubles(P, plan_slots(P)));
 }
 
+// The same engine with TWO SMs per chain (2 x 2 blocks, i.e. 105 <= n <= 208): a thread-block cluster of two CTAs
+// shares the chain's global workspace; CTA r owns the diagonal block C_rr and half of the off-diagonal block of every
+// product, half of the Taylor columns, and both keep identical copies of the chain state (Chain::run, ex.crank).
+// 74 chains are resident instead of 148: their workspaces (40 MB) sit comfortably in L2, a product is two rounds of
+// warp tasks instead of four, and 512 chains are 6.9 waves of 74 instead of 3.5 waves of 148.  Opt-in (mcd_mc_run).
+constexpr size_t kClusterTail = 8;   // doubles behind a chain's workspace: the partial sums the two CTAs exchange
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
+  DeviceExec ex(s.red);
+  ex.crank = (int)(blockIdx.x & 1);
+  ex.csize = 2;
+  Chain<DeviceExec, 1> ch(ex, P, s);
+  const long long chain = (long long)(blockIdx.x >> 1);
+  ch.run(mp, io, chain, nsteps, gws + (size_t)chain * (blocked_ws_doubles(P, plan_slots(P)) + kClusterTail));
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
                        const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
@@ -541,11 +560,22 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
     mcd_mc_run_gen_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
   } else if (p->blocked && mp.method >= MCD_METHOD_SQUARING) {
     if (mp.method != MCD_METHOD_SQUARING) return MCD_E_UNSUPPORTED;   // tensor-core products only
-    int rc = ws.alloc((size_t)nchains * blocked_ws_doubles(P, plan_slots(P)) * sizeof(double), st);
+    // two SMs per chain (thread-block cluster): OPT-IN, MCDIFF_B200_CLUSTER=1.  Measured at 200 bins x 8 lags
+    // (profiles/prof_c3_cluster.py): a chain runs 1.6x faster on two SMs, not 2x -- each CTA still stages every operand
+    // panel of its blocks, so the copies weigh twice as much -- 1.05e5 against 1.26e5 MC steps/s for one SM per chain.
+    const char* want_cl = getenv("MCDIFF_B200_CLUSTER");
+    const bool cluster = P.nblk == 2 && want_cl && want_cl[0] == '1';
+    int rc = ws.alloc((size_t)nchains * (blocked_ws_doubles(P, plan_slots(P)) + (cluster ? kClusterTail : 0)) * sizeof(double), st);
     if (rc != MCD_OK) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)p->blk_smem_bytes));
-    mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    if (cluster) {
+      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)p->blk_smem_bytes));
+      mcd_mc_run_blk2_kernel<<<2 * nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)p->blk_smem_bytes));
+      mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    }
   } else if (p->in_smem) {
     // Packed symmetric engine (mcd_pk.cu), two chains per SM: OPT-IN (MCDIFF_B200_PACKED=1).  Measured on B200 at
     // 100 bins x 4 lags (profiles/prof_pair.py): a packed chain alone costs 138 us per MC step against 94 us for the

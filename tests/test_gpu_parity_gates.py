@@ -244,3 +244,39 @@ def test_packed_engine_two_chains_per_sm(engine, monkeypatch):
     assert np.array_equal(d1, d0)
     np.testing.assert_allclose(s1["scal"][:, 0], s0["scal"][:, 0], rtol=1e-12)
     assert not s1["counters"][:, 6].any()
+
+
+def test_blocked_engine_on_a_two_cta_cluster(engine, monkeypatch):
+    """The opt-in cluster kernel of the blocked engine (MCDIFF_B200_CLUSTER=1: two SMs per chain, the CTAs split the
+    blocks of every product and the Taylor columns, partial sums exchanged through the workspace) makes the decisions
+    of the default one-SM kernel, step for step, at config 3's shape with time-offset moves (general plan)."""
+    from mcdiff_b200 import _capi as K
+    from mcdiff_b200.engine import ChainBatch, DeviceProblem
+    from oracle import mcdiff_oracle as O
+    lags = np.array([5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0])
+    counts = O.synthetic_counts(200, lags, seed=3, total=1.0e6, dz=0.5)[0]
+    n = 200
+    vb, wb = O.cos_basis_center(n, 12), O.cos_basis_border(n, n, 8)
+    prob = DeviceProblem(engine, counts, lags, True, v_basis=vb, w_basis=wb)
+    assert prob.squaring_ok and not prob.in_smem
+    wc0 = np.zeros(8)
+    wc0[0] = -np.log(0.25)
+
+    def run(cluster, move_t0):
+        monkeypatch.setenv("MCDIFF_B200_CLUSTER", "1" if cluster else "0")
+        ch = ChainBatch(prob, 5)
+        ch.set_state(np.zeros(n), wb @ wc0, np.zeros(12), wc0, dv=0.1, dw=0.1, dtimezero=0.2)
+        ch.init_log_like()
+        mp = K.McParams()
+        mp.num_mc_update, mp.min_lt, mp.sample_every, mp.refresh_every, mp.seed = 10.0, 5.0, 100, 512, 3
+        mp.move_timezero = int(move_t0)
+        d, ll, _ = ch.run(24, mp, record=True)
+        return d.cpu().numpy(), ll.cpu().numpy(), ch.host_state()
+
+    for move_t0 in (False, True):
+        d1, l1, s1 = run(True, move_t0)
+        d0, l0, s0 = run(False, move_t0)
+        assert np.array_equal(d1, d0)
+        np.testing.assert_allclose(l1, l0, rtol=1e-12)
+        np.testing.assert_allclose(s1["scal"], s0["scal"], rtol=1e-12)
+        assert not s1["counters"][:, 6].any() and 0 < int((d1 & 1).sum()) < d1.size
