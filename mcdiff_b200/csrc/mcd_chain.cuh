@@ -351,7 +351,8 @@ MCD_HD Smem carve(const Problem& P, double* mat, unsigned char* vec, bool panels
 // kMode: 0 = symmetric engines (eigen / squaring in shared memory), 1 = blocked squaring engine
 // (104 < n <= 208), 2 = general engine for the non-reversible --pull generator.  The mode is a template
 // parameter so that every kernel only carries the code of its own likelihood evaluation.
-template <class Exec, int kMode = 0>
+// kCluster: the chain is shared by the two CTAs of a thread-block cluster (blocked engine only, see blk_product).
+template <class Exec, int kMode = 0, bool kCluster = false>
 struct Chain {
   static constexpr bool kBlocked = (kMode == 1);
   static constexpr bool kGeneral = (kMode == 2);
@@ -1944,7 +1945,7 @@ struct Chain {
   // cluster may have written them)
   MCD_HD double pk_get(const double* G, int i, int j) const {
 #if defined(__CUDA_ARCH__)
-    if (kBlocked) return __ldcg(G + pk_index(i, j, P.np >> 3));
+    if (kBlocked && kCluster) return __ldcg(G + pk_index(i, j, P.np >> 3));
 #endif
     return G[pk_index(i, j, P.np >> 3)];
   }
@@ -2192,6 +2193,8 @@ struct Chain {
   //                         fragment loads then walk rows instead of columns (both patterns are conflict free at
   //                         pitch lds = 4 mod 8).
   // Returns the transposed flag.
+  // global workspace data another CTA of the cluster may have written is read past L1
+#define MCD_LD_PEER(p) (kCluster ? __ldcg(p) : *(p))
   MCD_HD bool blk_stage(double* dst, const double* G, int K, int I) {
     ex.par([&](int tid) {
       blk_stage_issue(tid, dst, G, K, I);
@@ -2223,46 +2226,23 @@ struct Chain {
 #else
       for (int cs = 0; cs < 4; ++cs) { drow[(cs ^ sw) * 2] = src[2 * cs]; drow[(cs ^ sw) * 2 + 1] = src[2 * cs + 1]; }
 #endif
-    }
-    if (diag) {
-      // mirror images of the tiles above the diagonal (column r of tile (tb, ta) = row r of tile (ta, tb)), through
-      // registers: the loads of three tile rows are issued together (L2 latency paid once per group), then their
-      // scattered stores
-      constexpr int GRP = 3;
-      for (int e0 = tid; e0 < nitems; e0 += GRP * Exec::nthr()) {
-        d2 x[GRP][4];
-        int ta_[GRP], tb_[GRP], r_[GRP];
-        bool on[GRP];
+      if (diag && ta < tb) {                                     // mirror image of the tile row: column r of tile (tb, ta)
+        // the four loads first (one L2 round trip per tile row), then the eight scattered stores
+        d2 x[4];
 #pragma unroll
-        for (int g = 0; g < GRP; ++g) {
-          const int e = e0 + g * Exec::nthr();
-          const int tile = e >> 3;
-          r_[g] = e & 7;
-          ta_[g] = tile / t13; tb_[g] = tile - ta_[g] * t13;
-          on[g] = e < nitems && ta_[g] < tb_[g];
-          if (on[g]) {
-            const double* src = G + (size_t)pk_tile(bi * t13 + ta_[g], bj * t13 + tb_[g], nb8) * 64 + r_[g] * 8;
-#pragma unroll
-            for (int cs = 0; cs < 4; ++cs) {
+        for (int cs = 0; cs < 4; ++cs) {
 #if defined(__CUDA_ARCH__)
-              const double2 xg = __ldcg(reinterpret_cast<const double2*>(src + 2 * cs));
-              x[g][cs] = d2{xg.x, xg.y};
+          const double2 xg = MCD_LD_PEER(reinterpret_cast<const double2*>(src + 2 * cs));
+          x[cs] = d2{xg.x, xg.y};
 #else
-              x[g][cs] = ld2(src + 2 * cs);
+          x[cs] = ld2(src + 2 * cs);
 #endif
-            }
-          }
         }
 #pragma unroll
-        for (int g = 0; g < GRP; ++g) {
-          if (!on[g]) continue;
-          const int sw = ((r_[g] >> 1) & 1) << 1;
-#pragma unroll
-          for (int cs = 0; cs < 4; ++cs) {
-            const int c = (cs ^ sw) * 2;
-            dst[(size_t)(tb_[g] * 8 + c) * lds + ta_[g] * 8 + r_[g]] = x[g][cs].x;
-            dst[(size_t)(tb_[g] * 8 + c + 1) * lds + ta_[g] * 8 + r_[g]] = x[g][cs].y;
-          }
+        for (int cs = 0; cs < 4; ++cs) {
+          const int c = (cs ^ sw) * 2;
+          dst[(size_t)(tb * 8 + c) * lds + ta * 8 + r] = x[cs].x;
+          dst[(size_t)(tb * 8 + c + 1) * lds + ta * 8 + r] = x[cs].y;
         }
       }
     }
@@ -2464,9 +2444,9 @@ struct Chain {
   MCD_HD void blk_product(const double* Xg, const double* Yg, double* Dg, const int* cnt, const int* nsy, double* Pl) {
     const int nblk = P.nblk;
     const bool same = (Xg == Yg);
-    if (ex.csize == 2 && nblk == 2) {
-      // Two SMs per chain: CTA r owns the diagonal block C_rr and half of the tasks of C_01; after the product a
-      // cluster barrier publishes Dg.  Panels: b[i] holds the column-block i operand.
+    if constexpr (kCluster) {
+      // Two SMs per chain (nblk == 2): CTA r owns the diagonal block C_rr and half of the tasks of C_01; after the
+      // product a cluster barrier publishes Dg.  Panels: b[i] holds the column-block i operand.
       const int r = ex.crank, o = 1 - r;
       double* b[2] = {s.XT, s.B2};
       for (int K = 0; K < 2; ++K) {
@@ -2492,47 +2472,45 @@ struct Chain {
       ex.cluster_sync();
       return;
     }
-    if (same && nblk == 2) {
-      // squaring with 2 x 2 blocks: b0 = X_K0, b1 = X_K1.  C_00 needs b0 only (X_K1 is staged into b1 meanwhile),
-      // C_01 needs both, C_11 needs b1 only (X_K+1,0 is staged into b0 meanwhile): every copy but the first overlaps MMAs.
-      double* b0 = s.XT;
-      double* b1 = s.B2;
-      bool t0 = blk_stage(b0, Xg, 0, 0);
-      for (int K = 0; K < 2; ++K) {
-        const bool first = (K == 0), fin = (K == 1);
-        blk_mma(b0, t0, b0, t0, true, Dg, 0, 0, first, fin, cnt, nsy, Pl, b1, Xg, K, 1);
-        const bool t1 = K > 1;
-        blk_mma(b0, t0, b1, t1, false, Dg, 0, 1, first, fin, cnt, nsy, Pl);
-        if (K == 0) {
-          blk_mma(b1, t1, b1, t1, true, Dg, 1, 1, first, fin, cnt, nsy, Pl, b0, Xg, 1, 0);
-          t0 = true;                       // block (1, 0) = the stored block (0, 1), transposed
-        } else {
-          blk_mma(b1, t1, b1, t1, true, Dg, 1, 1, first, fin, cnt, nsy, Pl);
-        }
-      }
-      return;
-    }
+    // ONE call site of blk_mma (the kernel is instruction-cache sensitive: every site inlines the eight k-loop
+    // variants and the epilogue).  A squaring with 2 x 2 blocks takes the blocks in the order (0,0), (0,1), (1,1):
+    // C_00 needs X_K0 only, so X_K1 streams into the other panel meanwhile; C_11 needs X_K1 only, so X_K+1,0 streams
+    // in meanwhile -- every copy but the first overlaps MMAs.
+    const bool pipelined = same && nblk == 2;
+    double* A = s.XT;
+    double* B = s.B2;
+    bool trA = false, trB = false;
+    bool have_A = false;       // A already holds X_KI (squarings: it was staged or prefetched as a B panel)
     for (int K = 0; K < nblk; ++K) {
-      double* A = s.XT;
-      double* B = s.B2;
-      bool trA = false, trB = false;
-      bool have_A = false;     // squaring: A already holds X_KI (it was the previous I's last B panel)
       int b_has = -1;          // general product: column block of Y currently staged in B
       for (int I = 0; I < nblk; ++I) {
         if (!have_A) trA = blk_stage(A, Xg, K, I);
         have_A = false;
-        const bool down = same || (I & 1);
+        const bool down = !pipelined && (same || (I & 1));
         for (int q = 0; q < nblk - I; ++q) {
           const int J = down ? nblk - 1 - q : I + q;
           const double* Bp = B;
           bool trBp = trB;
-          if (same && J == I) { Bp = A; trBp = trA; }
-          else if (same || b_has != J) {
+          double* pf = nullptr;
+          int pfK = 0, pfI = 0;
+          if (same && J == I) {
+            Bp = A; trBp = trA;
+            if (pipelined && I == 0) { pf = B; pfK = K; pfI = 1; }
+            else if (pipelined && K + 1 < nblk) { pf = B; pfK = K + 1; pfI = 0; }
+          } else if (!(pipelined && b_has == J) && (same || b_has != J)) {
             trB = blk_stage(B, Yg, K, J);
             trBp = trB;
             b_has = J;
           }
-          blk_mma(A, trA, Bp, trBp, I == J, Dg, I, J, K == 0, K == nblk - 1, cnt, nsy, Pl);
+          blk_mma(A, trA, Bp, trBp, I == J, Dg, I, J, K == 0, K == nblk - 1, cnt, nsy, Pl, pf, Xg, pfK, pfI);
+          if (pf) {
+            if (I == 0) { b_has = 1; trB = pfK > 1; }                  // B = X_K1
+            else {                                                       // B = X_K+1,0: the next K's first A
+              double* tmp = A; A = B; B = tmp;
+              trA = true;
+              have_A = true;
+            }
+          }
         }
         if (same && I + 1 < nblk) {   // B holds X_K,I+1
           double* tmp = A; A = B; B = tmp;

@@ -181,7 +181,7 @@ mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* g
   DeviceExec ex(s.red);
   ex.crank = (int)(blockIdx.x & 1);
   ex.csize = 2;
-  Chain<DeviceExec, 1> ch(ex, P, s);
+  Chain<DeviceExec, 1, true> ch(ex, P, s);
   const long long chain = (long long)(blockIdx.x >> 1);
   ch.run(mp, io, chain, nsteps, gws + (size_t)chain * (blocked_ws_doubles(P, plan_slots(P)) + kClusterTail));
 }
