@@ -50,7 +50,7 @@ STRONG_CHAINS = 4096
 METRIC = "MC steps/sec (all chains, 100 bins x 4 lags)"
 UNIT = "MC steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 chains x 200 steps), ncu --set full, see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {"mcd_mc_run_kernel<true>": 3954944 + 56320}
+NCU_DRAM_BYTES_PER_LAUNCH = {"mcd_mc_run_kernel<true>": 3954944 + 56320, "mcd_mc_run_sq_kernel": 3954944 + 56320}
 
 
 def flops_per_mc_step(n, L):
@@ -566,7 +566,8 @@ def run_gpu(args):
                    nref, "mcdiff.mc.do_mc_cycles of the unmodified reference (baseline/_ref)" if kind == "reference"
                    else "oracle port of lib/mc.py (baseline/_ref not installed)"),
                "cpu_model": cpu_model_string(), "host_cores": os.cpu_count()}
-    kname = "mcd_mc_run_kernel<true>"
+    # the tensor-core squaring engine has its own (leaner) kernel; the other engines share mcd_mc_run_kernel<true>
+    kname = "mcd_mc_run_sq_kernel" if engine_name == "squaring_dmma" else "mcd_mc_run_kernel<true>"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

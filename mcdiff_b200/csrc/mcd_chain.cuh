@@ -357,6 +357,7 @@ struct Chain {
   static constexpr bool kBlocked = (kMode == 1);
   static constexpr bool kGeneral = (kMode == 2);
   static constexpr bool kPacked = (kMode == 3);
+  static constexpr bool kTensorOnly = (kMode == 4);   // mode 0 without the eigen engine and the DFMA products: the production kernel
   static constexpr bool kPackedDst = (kMode == 1 || kMode == 3);   // the Taylor polynomial is written in packed tile storage
   Exec& ex;
   const Problem& P;
@@ -383,7 +384,7 @@ struct Chain {
       if (tid < 32) s.tord[tid] = (unsigned char)taylor_order(tid, 0);
     });
     ex.single([&]() {
-      const int nb = (kBlocked || kPacked) ? 0 : P.np / 4;
+      const int nb = (kBlocked || kPacked || kTensorOnly) ? 0 : P.np / 4;
       int t = 0;
       for (int pi = 0; pi < nb; pi += 4)
         for (int pj = (pi / 8) * 8; pj < nb; pj += 8)
@@ -452,7 +453,7 @@ struct Chain {
           for (int k = 0; k < 16; ++k) q[k] = (have && k < 12) ? wt[k] : 0;
         }
       }
-      const int h = (kBlocked || kPacked) ? 0 : P.np / 2;
+      const int h = (kBlocked || kPacked || kTensorOnly) ? 0 : P.np / 2;
       int q = 0;
       for (int ka = 0; ka < h; ++ka)
         for (int kb = ka + 1; kb < h; ++kb) {
@@ -1489,7 +1490,7 @@ struct Chain {
   // slots: per-CTA global scratch of pl.nslots work matrices (only read/written when pl.fast == 0).
   MCD_HD double evaluate_sq(const double* v, const double* w, const double* lagt, const LagPlan& pl, double* slots,
                             int taylor_m, bool tensor, double* Pout, int* squarings_out) {
-    const bool use_mma = tensor && dmma_ok();
+    const bool use_mma = kTensorOnly || (tensor && dmma_ok());
     const int n = P.n, np = P.np;
     const size_t nn = (size_t)n * n, slot_elems = (size_t)np * P.ld;
     build_S(v, w);
@@ -2855,6 +2856,8 @@ struct Chain {
           ll_new = evaluate_gen(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
         } else if constexpr (kPacked) {
           ll_new = evaluate_pk(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, nullptr, &sw);
+        } else if constexpr (kTensorOnly) {
+          ll_new = evaluate_sq(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, true, nullptr, &sw);
         } else if (mp.method >= 2) {
           ll_new = evaluate_sq(vtry, wtry, lagp, plan, sq_slots, mp.taylor_m, mp.method == 2, nullptr, &sw);
         } else {

@@ -102,6 +102,19 @@ mcd_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
   ch.run(mp, io, (long long)blockIdx.x, nsteps, slots);
 }
 
+// The production kernel of the in-shared-memory engine: tensor-core squaring only (Chain<Exec, 4>), i.e. the body of
+// mcd_mc_run_kernel<true> without the eigen engine and the DFMA products it selects at run time -- a third less
+// code in a kernel whose phases evict each other from the instruction cache.
+__global__ void __launch_bounds__(kThreads, 1)
+mcd_mc_run_sq_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
+  Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
+  DeviceExec ex(s.red);
+  Chain<DeviceExec, 4> ch(ex, P, s);
+  ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * plan_slots(P) * P.np * P.ld);
+}
+
 // Thread 0, inside ex.single (see shifted_lags_ok).
 __device__ __forceinline__ void check_shifted_lags(const Problem& P, const double* lag, Scalars* sc) {
   if (!shifted_lags_ok(P, lag)) sc->status |= MCD_ST_BAD_LAGS;
@@ -603,9 +616,15 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
       h->launches++;
       return MCD_OK;
     }
-    CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)p->smem_bytes));
-    mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    if (mp.method == MCD_METHOD_SQUARING) {
+      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_sq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)p->smem_bytes));
+      mcd_mc_run_sq_kernel<<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)p->smem_bytes));
+      mcd_mc_run_kernel<true><<<nchains, kThreads, p->smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+    }
   } else {
     const int ntiles = (P.np / 4) * (P.np / 4 + 1) / 2;
     if (ntiles > kThreads) mp.refresh_every = 1;  // always cold: warm product needs one tile per thread

@@ -23,7 +23,7 @@ mcd128_mc_run_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws
   const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes);
   DeviceExec ex(s.red);
-  Chain<DeviceExec> ch(ex, P, s);
+  Chain<DeviceExec, 4> ch(ex, P, s);   // tensor-core squaring only (mcd_mc_run launches this kernel for MCD_METHOD_SQUARING)
   ch.run(mp, io, (long long)blockIdx.x, nsteps, gws + (size_t)blockIdx.x * plan_slots(P) * P.np * P.ld);
 }
 
