@@ -12,6 +12,7 @@
  *                             update_movewidth / update_temp      (lib/MCState.py:205-304,371-393)
  *                           + Logger.log sampling                 (lib/log.py:35-58)
  *   mcd_rad_loglike_batch <-> mcdiff.twod.rad_log_like_lag        (lib/twod.py:13-32)
+ *   mcd_traj_counts[_rad] <-> mcdiff.tools.extract.transition_matrix_add1 / count_2D  (lib/tools/extract.py:71-156)
  *
  * Conventions
  *   - plain C, no exceptions, no stdout; every function returns 0 on success, a negative
@@ -245,6 +246,29 @@ typedef struct {
 
 int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_params* params,
                    const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream);
+
+/* ---- trajectory -> transition counts (the step before the likelihood path) ------------------
+ *
+ *   mcd_traj_counts      <->  mcdiff.tools.extract.transition_matrix_add1   (lib/tools/extract.py:71-90), applied to every
+ *                             particle column and every shift as examples/create-transition-matrix/extract_Tmat.py:36-50
+ *                             does, including its periodic fold  z - zpbc * floor(z / zpbc + 0.5)  (:45)
+ *   mcd_traj_counts_rad  <->  mcdiff.tools.extract.count_2D                 (lib/tools/extract.py:127-156)
+ *
+ * x (and y, z): coordinates [nframes][ncols] (one column per particle), row-major fp64.  period > 0 folds the binned
+ * coordinate into [-period/2, period/2) first, 0 bins it as it is.  edges[nedges] / redges[nredges]: increasing bin
+ * edges; bins follow numpy.digitize (bin k = number of edges <= x, so 0 and nedges are the two outside bins, NaN
+ * lands in bin nedges).  shifts_host[nshifts]: HOST array of frame shifts, 1 <= shift < nframes, nshifts <= 64.
+ * counts is ACCUMULATED INTO (the reference's A += 1; zero it for a fresh matrix), int64:
+ *   mcd_traj_counts:      [nshifts][nedges+1][nedges+1],           counts[l][end][start]
+ *   mcd_traj_counts_rad:  [nshifts][nredges][nedges+1][nedges+1],  counts[l][r-1][end][start] with
+ *                         r = digitize(sqrt(dx^2 + dy^2), redges) and r = 0 wrapping to the last radial bin (B[-1]).
+ * Asynchronous on `stream`; the bin-index scratch (1-2 bytes per coordinate) is a stream-ordered allocation. */
+int mcd_traj_counts(mcd_handle* h, const double* x, int64_t nframes, int64_t ncols, double period,
+                    const double* edges, int32_t nedges, const int32_t* shifts_host, int32_t nshifts,
+                    int64_t* counts, void* stream);
+int mcd_traj_counts_rad(mcd_handle* h, const double* x, const double* y, const double* z, int64_t nframes,
+                        int64_t ncols, double period, const double* edges, int32_t nedges, const double* redges,
+                        int32_t nredges, const int32_t* shifts_host, int32_t nshifts, int64_t* counts, void* stream);
 
 /* FP64 FMA micro-benchmark: fills *tflops with the measured dense DFMA rate of the device
  * (the roofline denominator bench.py reports against).  Synchronous. */

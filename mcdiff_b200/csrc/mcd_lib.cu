@@ -9,6 +9,7 @@
 #include <new>
 
 #include "../../include/mcdiff_b200.h"
+#include "mcd_handle.h"
 #include "mcd_chain.cuh"
 #include "mcd_radial.cuh"
 
@@ -41,12 +42,6 @@ static_assert((int)MCD_ST_NONFINITE == (int)ST_NONFINITE && (int)MCD_ST_NAN_TRIA
               (int)MCD_ST_BAD_LAGS == (int)ST_BAD_LAGS,
               "status bits");
 
-struct mcd_handle {
-  int device;
-  int sm_count;
-  int max_smem_optin;
-  long long launches;
-};
 
 // Per-call scratch (LagPlan slots, blocked-engine work matrices, eigen work matrices, radial kernels) is a
 // STREAM-ORDERED allocation: cudaMallocAsync on the caller's stream before the launch, cudaFreeAsync behind it.
@@ -76,6 +71,7 @@ struct mcd_problem {
   int blocked;      // squaring engine runs blocked (kMaxSmemBins < n <= 2 kMaxSmemBins)
   size_t smem_bytes;
   size_t blk_smem_bytes;
+  mutable int max_cl2_plus1;   // 1 + co-resident two-CTA clusters of the blocked MC kernel (0: not asked yet)
 };
 
 #define CUDA_TRY(x)                          \
@@ -187,7 +183,7 @@ mcd_mc_run_blk_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gw
 // warp tasks instead of four, and 512 chains are 6.9 waves of 74 instead of 3.5 waves of 148.  Opt-in (mcd_mc_run).
 constexpr size_t kClusterTail = 8;   // doubles behind a chain's workspace: the partial sums the two CTAs exchange
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws) {
+mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* gws, int chain0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
@@ -195,8 +191,8 @@ mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* g
   ex.crank = (int)(blockIdx.x & 1);
   ex.csize = 2;
   Chain<DeviceExec, 1, true> ch(ex, P, s);
-  const long long chain = (long long)(blockIdx.x >> 1);
-  ch.run(mp, io, chain, nsteps, gws + (size_t)chain * (blocked_ws_doubles(P, plan_slots(P)) + kClusterTail));
+  const long long local = (long long)(blockIdx.x >> 1);   // chain0: first chain of this launch (tail of a split launch)
+  ch.run(mp, io, chain0 + local, nsteps, gws + (size_t)local * (blocked_ws_doubles(P, plan_slots(P)) + kClusterTail));
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -543,6 +539,35 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   return (int)cudaGetLastError();
 }
 
+// How many two-CTA clusters of the blocked MC kernel the device hosts at once (GPC sizes decide; <= sm_count / 2).
+static int max_blk2_clusters(mcd_handle* h, const mcd_problem* p) {
+  if (p->max_cl2_plus1 > 0) return p->max_cl2_plus1 - 1;
+  p->max_cl2_plus1 = 1;
+  if (cudaFuncSetAttribute(mcd_mc_run_blk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->blk_smem_bytes) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)h->sm_count, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = p->blk_smem_bytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, mcd_mc_run_blk2_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  p->max_cl2_plus1 = ncl + 1;
+  return ncl;
+}
+
 int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params, const mcd_chain_io* io,
                int32_t nchains, int32_t nsteps, void* stream) {
   if (!h || !p || !params || !io || nchains < 0 || nsteps < 0) return MCD_E_ARG;
@@ -576,18 +601,38 @@ int mcd_mc_run(mcd_handle* h, const mcd_problem* p, const mcd_mc_params* params,
     // two SMs per chain (thread-block cluster): OPT-IN, MCDIFF_B200_CLUSTER=1.  Measured at 200 bins x 8 lags
     // (profiles/prof_c3_cluster.py): a chain runs 1.6x faster on two SMs, not 2x -- each CTA still stages every operand
     // panel of its blocks, so the copies weigh twice as much -- 1.05e5 against 1.26e5 MC steps/s for one SM per chain.
+    //
+    // What the cluster kernel IS used for by default: the last, partly filled wave.  One CTA per SM means nchains
+    // chains run in ceil(nchains / 148) waves of equal length; when the last wave holds no more chains than the
+    // device can host as two-CTA clusters, those chains go to the cluster kernel, launched behind the full waves on
+    // the same stream: 512 chains = 3 waves + 68 chains on 136 SMs at 1.6x = 3.6 wave times instead of 4.  Both
+    // kernels produce bit-identical chains (test_cluster_kernel_equals_single), so the split is invisible to callers.
+    // MCDIFF_B200_CLUSTER=1 forces every chain onto clusters, =0 disables the split.
     const char* want_cl = getenv("MCDIFF_B200_CLUSTER");
-    const bool cluster = P.nblk == 2 && want_cl && want_cl[0] == '1';
-    int rc = ws.alloc((size_t)nchains * (blocked_ws_doubles(P, plan_slots(P)) + (cluster ? kClusterTail : 0)) * sizeof(double), st);
+    const bool can_cl = P.nblk == 2;
+    int ncl = 0;   // chains [nchains - ncl, nchains) run on two SMs each
+    if (can_cl && want_cl && want_cl[0] == '1') {
+      ncl = nchains;
+    } else if (can_cl && !(want_cl && want_cl[0] == '0')) {
+      const int tail = nchains % h->sm_count;
+      if (tail > 0 && tail <= max_blk2_clusters(h, p)) ncl = tail;
+    }
+    const int nsingle = nchains - ncl;
+    const size_t ws1 = blocked_ws_doubles(P, plan_slots(P));
+    int rc = ws.alloc(((size_t)nsingle * ws1 + (size_t)ncl * (ws1 + kClusterTail)) * sizeof(double), st);
     if (rc != MCD_OK) return rc;
-    if (cluster) {
-      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)p->blk_smem_bytes));
-      mcd_mc_run_blk2_kernel<<<2 * nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
-    } else {
+    if (nsingle > 0) {
       CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)p->blk_smem_bytes));
-      mcd_mc_run_blk_kernel<<<nchains, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+      mcd_mc_run_blk_kernel<<<nsingle, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps, ws.p);
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (ncl > 0) {
+      CUDA_TRY(cudaFuncSetAttribute(mcd_mc_run_blk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)p->blk_smem_bytes));
+      mcd_mc_run_blk2_kernel<<<2 * ncl, kThreads, p->blk_smem_bytes, st>>>(P, mp, cio, nsteps,
+                                                                           ws.p + (size_t)nsingle * ws1, nsingle);
+      if (nsingle > 0) h->launches++;
     }
   } else if (p->in_smem) {
     // Packed symmetric engine (mcd_pk.cu), two chains per SM: OPT-IN (MCDIFF_B200_PACKED=1).  Measured on B200 at

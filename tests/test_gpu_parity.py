@@ -327,9 +327,15 @@ def test_blocked_squaring_engine(engine, n, lags, pbc):
         prob.loglike(v, w, method=METHODS["squaring_dfma"])
 
 
-def test_blocked_engine_mc_matches_oracle(engine):
+@pytest.mark.parametrize("cluster", ["0", "auto"])
+def test_blocked_engine_mc_matches_oracle(engine, monkeypatch, cluster):
     """MC loop on the blocked engine (n = 120, cosine model, time-offset moves, a lag set that
-    needs a parked operand), device Philox: every chain's decisions equal the oracle replay."""
+    needs a parked operand), device Philox: every chain's decisions equal the oracle replay.
+    cluster "0": one SM per chain; "auto": a batch smaller than a wave runs on two-CTA clusters (mcd_mc_run)."""
+    if cluster == "0":
+        monkeypatch.setenv("MCDIFF_B200_CLUSTER", "0")
+    else:
+        monkeypatch.delenv("MCDIFF_B200_CLUSTER", raising=False)
     from mcdiff_b200.engine import DeviceProblem, ChainBatch
     from mcdiff_b200 import philox
     from oracle import mcdiff_oracle as O

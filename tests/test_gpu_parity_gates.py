@@ -198,8 +198,14 @@ def test_ten_thousand_decisions_equal_the_oracle_replay(engine):
     assert int(((dec >> 1) & 1).sum()) > 0
 
 
-def test_config3_shape_mc_replay(engine):
-    """200 bins x 8 lags {5..40}, CosinusModel ncosF 12 / ncosD 8 (BASELINE.json config 3) on the blocked engine."""
+@pytest.mark.parametrize("cluster", ["0", "auto"])
+def test_config3_shape_mc_replay(engine, monkeypatch, cluster):
+    """200 bins x 8 lags {5..40}, CosinusModel ncosF 12 / ncosD 8 (BASELINE.json config 3) on the blocked engine:
+    one SM per chain ("0") and the default, which puts a batch smaller than a wave on two-CTA clusters ("auto")."""
+    if cluster == "0":
+        monkeypatch.setenv("MCDIFF_B200_CLUSTER", "0")
+    else:
+        monkeypatch.delenv("MCDIFF_B200_CLUSTER", raising=False)
     from oracle import mcdiff_oracle as O
     lags = np.array([5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0])
     counts = O.synthetic_counts(200, lags, seed=3, total=1.0e6, dz=0.5)[0]
@@ -280,3 +286,45 @@ def test_blocked_engine_on_a_two_cta_cluster(engine, monkeypatch):
         np.testing.assert_allclose(l1, l0, rtol=1e-12)
         np.testing.assert_allclose(s1["scal"], s0["scal"], rtol=1e-12)
         assert not s1["counters"][:, 6].any() and 0 < int((d1 & 1).sum()) < d1.size
+
+
+def test_blocked_engine_tail_wave_on_clusters(engine, monkeypatch):
+    """Default launch of the blocked engine with more chains than SMs: the full waves run one SM per chain, the chains
+    of the last, partly filled wave on two-CTA clusters behind them (mcd_mc_run).  Every chain must come out exactly as
+    from a launch without the split (MCDIFF_B200_CLUSTER=0)."""
+    import torch
+    from mcdiff_b200 import _capi as K
+    from mcdiff_b200.engine import ChainBatch, DeviceProblem
+    from oracle import mcdiff_oracle as O
+    lags = np.array([5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0])
+    counts = O.synthetic_counts(200, lags, seed=3, total=1.0e6, dz=0.5)[0]
+    n = 200
+    vb, wb = O.cos_basis_center(n, 12), O.cos_basis_border(n, n, 8)
+    prob = DeviceProblem(engine, counts, lags, True, v_basis=vb, w_basis=wb)
+    wc0 = np.zeros(8)
+    wc0[0] = -np.log(0.25)
+    nch = torch.cuda.get_device_properties(0).multi_processor_count + 7
+
+    def run(split):
+        if split:
+            monkeypatch.delenv("MCDIFF_B200_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("MCDIFF_B200_CLUSTER", "0")
+        ch = ChainBatch(prob, nch)
+        ch.set_state(np.zeros(n), wb @ wc0, np.zeros(12), wc0, dv=0.1, dw=0.1)
+        ch.init_log_like()
+        mp = K.McParams()
+        mp.num_mc_update, mp.min_lt, mp.sample_every, mp.refresh_every, mp.seed = 5.0, 5.0, 100, 512, 11
+        launches = engine.launch_count()
+        d, ll, _ = ch.run(10, mp, record=True)
+        return d.cpu().numpy(), ll.cpu().numpy(), ch.host_state(), engine.launch_count() - launches
+
+    d1, l1, s1, k1 = run(True)
+    d0, l0, s0, k0 = run(False)
+    assert (k1, k0) == (2, 1)                                             # the split really launched two kernels
+    assert np.array_equal(d1, d0)
+    np.testing.assert_allclose(l1, l0, rtol=1e-12)
+    np.testing.assert_allclose(s1["scal"], s0["scal"], rtol=1e-12)
+    for key in ("v", "w"):
+        np.testing.assert_allclose(s1[key], s0[key], rtol=0, atol=0)
+    assert not s1["counters"][:, 6].any() and 0 < int((d1 & 1).sum()) < d1.size
