@@ -13,6 +13,7 @@
  *                           + Logger.log sampling                 (lib/log.py:35-58)
  *   mcd_rad_loglike_batch <-> mcdiff.twod.rad_log_like_lag        (lib/twod.py:13-32)
  *   mcd_traj_counts[_rad] <-> mcdiff.tools.extract.transition_matrix_add1 / count_2D  (lib/tools/extract.py:71-156)
+ *   mcd_propagator_batch  <-> scipy.linalg.expm(rate * t) of the permeability analyses (lib/permeability/mfpt.py:364-475)
  *
  * Conventions
  *   - plain C, no exceptions, no stdout; every function returns 0 on success, a negative
@@ -246,6 +247,22 @@ typedef struct {
 
 int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_params* params,
                    const mcd_rad_chain_io* io, int32_t nchains, int32_t nsteps, void* stream);
+
+/* ---- propagators with absorbing boundaries (the permeability analyses) -----------------
+ *
+ *   mcd_propagator_batch <->  scipy.linalg.expm(rate * t) on the rate matrices of
+ *                             mcdiff.utils.init_rate_matrix(n, v, w, pbc, st=, end=, side=)   (lib/utils.py:28-74)
+ *                             as lib/permeability/mfpt.py:364,373,475 (exit-time distributions over a time grid),
+ *                             lib/permeability/perm.py:391 (transient partitioning) and lib/MCState.py:353 call it.
+ *
+ * p: a problem created with ONE lag time (its counts are not used; zeros will do).  Item b of the batch is the
+ * generator R(v[b], w[b]) - diag(sink[b]) at time times[b]:  out_P[b] = exp(times[b] * (R - diag(sink[b]))), [B][n][n],
+ * out_P[b][i][j] = probability of j -> i.  sink[B][n] (or NULL) holds the rates into the absorbing neighbours that the
+ * reference obtains by cutting rows/columns st+1..end-1 out of the periodic matrix: sink[0] = rate into bin st,
+ * sink[n-1] = rate into bin end, 0 elsewhere (any non-negative vector is accepted).  Tensor-core scaling and squaring
+ * on the symmetrised generator, same kernels as mcd_loglike_batch.  status[B] or NULL as in mcd_loglike_batch. */
+int mcd_propagator_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
+                         const double* sink, const double* times, double* out_P, int32_t* status, void* stream);
 
 /* ---- trajectory -> transition counts (the step before the likelihood path) ------------------
  *

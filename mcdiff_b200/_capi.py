@@ -79,8 +79,8 @@ EXPORTS = (
     "mcd_version", "mcd_error_string", "mcd_create", "mcd_destroy", "mcd_problem_create",
     "mcd_problem_destroy", "mcd_problem_info", "mcd_loglike_batch", "mcd_mc_run",
     "mcd_rad_problem_create", "mcd_rad_problem_destroy", "mcd_rad_problem_info",
-    "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_traj_counts", "mcd_traj_counts_rad", "mcd_fp64_peak",
-    "mcd_launch_count",
+    "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_propagator_batch", "mcd_traj_counts", "mcd_traj_counts_rad",
+    "mcd_fp64_peak", "mcd_launch_count",
 )
 
 _lib = None
@@ -119,6 +119,7 @@ def load():
     lib.mcd_rad_loglike_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, C.c_void_p]
     lib.mcd_rad_mc_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RadMcParams), C.POINTER(RadChainIO), C.c_int32,
                                    C.c_int32, C.c_void_p]
+    lib.mcd_propagator_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_void_p]
     lib.mcd_traj_counts.argtypes = [C.c_void_p, c_dp, C.c_int64, C.c_int64, C.c_double, c_dp, C.c_int32,
                                     C.POINTER(C.c_int32), C.c_int32, c_dp, C.c_void_p]
     lib.mcd_traj_counts_rad.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, C.c_int64, C.c_int64, C.c_double, c_dp, C.c_int32,
@@ -128,8 +129,8 @@ def load():
     lib.mcd_launch_count.argtypes = [C.c_void_p]
     for f in ("mcd_create", "mcd_destroy", "mcd_problem_create", "mcd_problem_destroy", "mcd_problem_info",
               "mcd_loglike_batch", "mcd_mc_run", "mcd_rad_problem_create", "mcd_rad_problem_destroy",
-              "mcd_rad_problem_info", "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_traj_counts",
-              "mcd_traj_counts_rad", "mcd_fp64_peak"):
+              "mcd_rad_problem_info", "mcd_rad_loglike_batch", "mcd_rad_mc_run", "mcd_propagator_batch",
+              "mcd_traj_counts", "mcd_traj_counts_rad", "mcd_fp64_peak"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib

@@ -361,6 +361,9 @@ struct Chain {
   static constexpr bool kPackedDst = (kMode == 1 || kMode == 3);   // the Taylor polynomial is written in packed tile storage
   Exec& ex;
   const Problem& P;
+  // optional absorbing rates subtracted from the diagonal of the generator (mcd_propagator_batch: the cut rate matrices
+  // of lib/utils.py:56-74); null everywhere on the likelihood / MC path
+  const double* sink_ = nullptr;
   Smem s;
 
   MCD_HD Chain(Exec& e, const Problem& p, const Smem& sm) : ex(e), P(p), s(sm) {}
@@ -384,7 +387,9 @@ struct Chain {
       if (tid < 32) s.tord[tid] = (unsigned char)taylor_order(tid, 0);
     });
     ex.single([&]() {
-      const int nb = (kBlocked || kPacked || kTensorOnly) ? 0 : P.np / 4;
+      // 4x4 tile table: DFMA products, and buffer_loglike of every full-storage engine (the tensor-only kernel needs it for
+      // duplicate lag times and for kernels that need no squaring)
+      const int nb = (kBlocked || kPacked) ? 0 : P.np / 4;
       int t = 0;
       for (int pi = 0; pi < nb; pi += 4)
         for (int pj = (pi / 8) * 8; pj < nb; pj += 8)
@@ -478,7 +483,7 @@ struct Chain {
           else if (pbc) ru = exp(w[n - 1] - 0.5 * (v[0] - vi));
           if (i > 0) rd = exp(w[i - 1] + 0.5 * (vi - v[i - 1]));
           else if (pbc) rd = exp(w[n - 1] + 0.5 * (vi - v[n - 1]));
-          s.a[i] = -rd - ru;
+          s.a[i] = sink_ ? -rd - ru - sink_[i] : -rd - ru;
           s.b[i] = (i < dim_w) ? exp(w[i]) : 0.0;
           s.ea[i] = exp(-0.5 * vi);
           s.eb[i] = exp(0.5 * vi);

@@ -119,8 +119,8 @@ __device__ __forceinline__ void check_shifted_lags(const Problem& P, const doubl
 template <bool kSmemMat>
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, const double* __restrict__ w,
-                   const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
-                   int* __restrict__ status, double* gws) {
+                   const double* __restrict__ lagtimes, const double* __restrict__ sink, double* __restrict__ out_ll,
+                   double* __restrict__ out_P, int* __restrict__ status, double* gws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t mat_bytes = smem_matrix_bytes(P.np, P.ld);
   double* mat = kSmemMat ? reinterpret_cast<double*>(smem_raw)
@@ -133,6 +133,7 @@ mcd_loglike_kernel(Problem P, int method, int B, const double* __restrict__ v, c
   ch.build_tables();
   const int n = P.n, np = P.np, dim_w = P.dim_w;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    ch.sink_ = sink ? sink + (size_t)b * n : nullptr;
     ex.par([&](int tid) {
       for (int i = tid; i < np; i += kThreads) {
         s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
@@ -197,8 +198,8 @@ mcd_mc_run_blk2_kernel(Problem P, McParams mp, ChainIO io, int nsteps, double* g
 
 __global__ void __launch_bounds__(kThreads, 1)
 mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const double* __restrict__ w,
-                       const double* __restrict__ lagtimes, double* __restrict__ out_ll, double* __restrict__ out_P,
-                       int* __restrict__ status, double* gws) {
+                       const double* __restrict__ lagtimes, const double* __restrict__ sink, double* __restrict__ out_ll,
+                       double* __restrict__ out_P, int* __restrict__ status, double* gws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t mat_bytes = smem_matrix_bytes(P.nbk, P.lds);
   Smem s = carve(P, reinterpret_cast<double*>(smem_raw), smem_raw + mat_bytes, true);
@@ -210,6 +211,7 @@ mcd_loglike_blk_kernel(Problem P, int B, const double* __restrict__ v, const dou
   const int nsl = plan_slots(P);
   double* ws = gws + (size_t)blockIdx.x * blocked_ws_doubles(P, nsl);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    ch.sink_ = sink ? sink + (size_t)b * n : nullptr;
     ex.par([&](int tid) {
       for (int i = tid; i < np; i += kThreads) {
         s.v[i] = (i < n) ? v[(size_t)b * n + i] : 0.0;
@@ -486,9 +488,10 @@ int mcd_problem_info(const mcd_problem* p, int32_t* np, int64_t* basis_elems, in
   return MCD_OK;
 }
 
-int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
-                      const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
-                      void* stream) {
+// mcd_loglike_batch and mcd_propagator_batch: the same kernels, the latter with absorbing rates on the diagonal.
+static int loglike_impl(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v, const double* w,
+                        const double* lagtimes, const double* sink, double* out_ll, double* out_P, int32_t* status,
+                        void* stream) {
   if (!h || !p || B < 0 || !v || !w || !out_ll) return MCD_E_ARG;
   if (method == MCD_METHOD_AUTO)
     method = (p->squaring_ok && (!lagtimes || p->P.use_pull)) ? MCD_METHOD_SQUARING : MCD_METHOD_EIGEN;
@@ -500,7 +503,7 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
   const Problem& P = p->P;
   Scratch ws;
   if (P.use_pull) {
-    if (method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA) return MCD_E_UNSUPPORTED;
+    if (method == MCD_METHOD_EIGEN || method == MCD_METHOD_SQUARING_DFMA || sink) return MCD_E_UNSUPPORTED;
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
     int rc = ws.alloc((size_t)grid * plan_slots(P) * P.np * P.ld * sizeof(double), st);
     if (rc != MCD_OK) return rc;
@@ -514,7 +517,7 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->blk_smem_bytes));
-    mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, lagtimes, out_ll, out_P, status,
+    mcd_loglike_blk_kernel<<<grid, kThreads, p->blk_smem_bytes, st>>>(P, B, v, w, lagtimes, sink, out_ll, out_P, status,
                                                                       ws.p);
   } else if (p->in_smem) {
     const int grid = B < 8 * h->sm_count ? B : 8 * h->sm_count;
@@ -524,7 +527,7 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
     }
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
+    mcd_loglike_kernel<true><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, sink, out_ll, out_P,
                                                                      status, ws.p);
   } else {
     const int grid = B < 2 * h->sm_count ? B : 2 * h->sm_count;
@@ -532,11 +535,30 @@ int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32
     if (rc != MCD_OK) return rc;
     CUDA_TRY(cudaFuncSetAttribute(mcd_loglike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)p->smem_bytes));
-    mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, out_ll, out_P,
+    mcd_loglike_kernel<false><<<grid, kThreads, p->smem_bytes, st>>>(P, method, B, v, w, lagtimes, sink, out_ll, out_P,
                                                                       status, ws.p);
   }
   h->launches++;
   return (int)cudaGetLastError();
+}
+
+int mcd_loglike_batch(mcd_handle* h, const mcd_problem* p, int32_t method, int32_t B, const double* v,
+                      const double* w, const double* lagtimes, double* out_ll, double* out_P, int32_t* status,
+                      void* stream) {
+  return loglike_impl(h, p, method, B, v, w, lagtimes, nullptr, out_ll, out_P, status, stream);
+}
+
+int mcd_propagator_batch(mcd_handle* h, const mcd_problem* p, int32_t B, const double* v, const double* w,
+                         const double* sink, const double* times, double* out_P, int32_t* status, void* stream) {
+  if (!h || !p || B < 0 || !v || !w || !times || !out_P) return MCD_E_ARG;
+  if (p->P.nlag != 1) return MCD_E_ARG;                        // one time per item: a problem created with one lag
+  if (p->P.use_pull || !p->squaring_ok) return MCD_E_UNSUPPORTED;
+  if (B == 0) return MCD_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Scratch ll;   // the kernels also form sum N log P of the problem's counts (zeros for a propagator problem): discarded
+  int rc = ll.alloc((size_t)B * sizeof(double), (cudaStream_t)stream);
+  if (rc != MCD_OK) return rc;
+  return loglike_impl(h, p, MCD_METHOD_SQUARING, B, v, w, times, sink, ll.p, out_P, status, stream);
 }
 
 // How many two-CTA clusters of the blocked MC kernel the device hosts at once (GPC sizes decide; <= sm_count / 2).

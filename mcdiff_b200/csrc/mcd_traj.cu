@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/mcdiff_b200.h"
 #include "mcd_handle.h"
@@ -43,10 +44,10 @@ struct Shifts {
 // guess: index from the uniform-grid formula (exact for most inputs), verified against the edges and corrected by a
 // binary search when it is off -- the result never depends on the guess.
 __device__ __forceinline__ int digitize(double x, const double* __restrict__ e, int ne, double e0, double inv_dx) {
-  if (x != x) return ne;
-  double g = (x - e0) * inv_dx + 1.0;
-  int k = (g < 0.0) ? 0 : (g > (double)ne ? ne : (int)g);
+  // the conversion saturates (and maps NaN to 0), so the clamp is integer work
+  const int k = min(max(__double2int_rz((x - e0) * inv_dx + 1.0), 0), ne);
   if ((k == 0 || e[k - 1] <= x) && (k == ne || e[k] > x)) return k;
+  if (x != x) return ne;
   int lo = 0, hi = ne;   // e[j] <= x for j < lo, e[j] > x for j >= hi
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -57,8 +58,19 @@ __device__ __forceinline__ int digitize(double x, const double* __restrict__ e, 
 }
 
 // traj = z - zpbc * floor(z / zpbc + 0.5)   (extract_Tmat.py:45), rounded operation by operation like numpy does
-__device__ __forceinline__ double fold(double x, double period) {
-  return __dsub_rn(x, __dmul_rn(period, floor(__dadd_rn(__ddiv_rn(x, period), 0.5))));
+// The division is the expensive part (a ~25-instruction FP64 sequence): q' = x * (1/period) differs from the correctly
+// rounded quotient by a few ulp, which changes floor(q + 0.5) only when q + 0.5 sits within ~1e-12 (relative) of an
+// integer -- those rare coordinates take the exact division, everything else the multiplication.
+__device__ __forceinline__ double fold(double x, double period, double inv_period) {
+  const double t = __dadd_rn(__dmul_rn(x, inv_period), 0.5);
+  double f = floor(t);
+  const double frac = t - f;                       // exact for finite t, in [0, 1)
+  // safe <=> 1e-9 < frac < 1 - 2^-20 and |t| < 2^20 (the two quotients differ by < |t| 5e-16): compared on the high
+  // words (monotonic for non-negative doubles) so that the test runs on the integer pipe, not the FP64 pipe
+  const unsigned hf = (unsigned)__double2hiint(frac), ht = (unsigned)__double2hiint(t) & 0x7fffffffu;
+  const bool safe = hf > 0x3e112e0bu && hf < 0x3feffffeu && ht < 0x41300000u;
+  if (!safe) f = floor(__dadd_rn(__ddiv_rn(x, period), 0.5));   // also NaN / inf (hf or ht out of range)
+  return __dsub_rn(x, __dmul_rn(period, f));
 }
 
 template <typename BinT>
@@ -102,6 +114,7 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
   const double e0 = se[0];
   const double inv_dx = (ne > 1 && se[ne - 1] > e0) ? (double)(ne - 1) / (se[ne - 1] - e0) : 0.0;
   const bool do_fold = period > 0.0;
+  const double inv_period = do_fold ? 1.0 / period : 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (kVec) {
@@ -114,14 +127,14 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
       double v[4] = {a.x, a.y, b.x, b.y};
       int k[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) k[e] = digitize(do_fold ? fold(v[e], period) : v[e], se, ne, e0, inv_dx);
+      for (int e = 0; e < 4; ++e) k[e] = digitize(do_fold ? fold(v[e], period, inv_period) : v[e], se, ne, e0, inv_dx);
       out[p] = P::make(k[0], k[1], k[2], k[3]);
     }
     for (long long i = (npack << 2) + t0; i < N; i += stride)
-      bins[i] = (BinT)digitize(do_fold ? fold(x[i], period) : x[i], se, ne, e0, inv_dx);
+      bins[i] = (BinT)digitize(do_fold ? fold(x[i], period, inv_period) : x[i], se, ne, e0, inv_dx);
   } else {
     for (long long i = t0; i < N; i += stride)
-      bins[i] = (BinT)digitize(do_fold ? fold(x[i], period) : x[i], se, ne, e0, inv_dx);
+      bins[i] = (BinT)digitize(do_fold ? fold(x[i], period, inv_period) : x[i], se, ne, e0, inv_dx);
   }
 }
 
@@ -130,15 +143,16 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
 // once; otherwise every pair is a 64-bit atomic on the output (L2).
 template <typename BinT, bool kSmem>
 __global__ void __launch_bounds__(kCntThreads, 1)
-mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int L, int gl, int H,
+mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int L, int gl, int nl2, int H,
                       unsigned long long* __restrict__ out) {
   using P = Pack4<BinT>;
   extern __shared__ unsigned hist[];
   const int l0 = blockIdx.y * gl;
   const int nl = min(gl, L - l0);
+  const int ns = kSmem ? max(nl - nl2, 0) : 0;   // shifts [0, ns) of the group: shared-memory cells, the rest: L2 atomics
   const int HH = H * H;
   if (kSmem) {
-    for (int c = threadIdx.x; c < nl * HH; c += blockDim.x) hist[c] = 0u;
+    for (int c = threadIdx.x; c < ns * HH; c += blockDim.x) hist[c] = 0u;
     __syncthreads();
   }
   const long long npack = (N + 3) >> 2;
@@ -154,7 +168,7 @@ mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int
       for (int e = 0; e < 4; ++e) {
         if (j + e < N) {
           const int cell = P::get(e4, e) * H + P::get(s4, e);   // A[end, start] += 1  (extract.py:86-87)
-          if (kSmem) atomicAdd(&hist[k * HH + cell], 1u);
+          if (k < ns) atomicAdd(&hist[k * HH + cell], 1u);
           else atomicAdd(&out[(size_t)(l0 + k) * HH + cell], 1ull);
         }
       }
@@ -162,7 +176,7 @@ mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int
   }
   if (kSmem) {
     __syncthreads();
-    for (int c = threadIdx.x; c < nl * HH; c += blockDim.x) {
+    for (int c = threadIdx.x; c < ns * HH; c += blockDim.x) {
       const unsigned v = hist[c];
       if (v) atomicAdd(&out[(size_t)l0 * HH + c], (unsigned long long)v);
     }
@@ -256,14 +270,19 @@ int counts_impl(mcd_handle* h, const double* x, long long nframes, long long nco
     if (S > need) S = need < 1 ? 1 : need;
     TRAJ_TRY(cudaFuncSetAttribute(mcd_traj_count_kernel<BinT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(gl * hist)));
-    mcd_traj_count_kernel<BinT, true><<<dim3((unsigned)S, (unsigned)G), kCntThreads, gl * hist, st>>>(
-        (const BinT*)bins.p, N, sh, L, gl, H, counts);
+    // experiment knobs (profiles/prof_traj.py): shifts per group accumulated in L2 instead of shared memory, CTA size
+    const char* env2 = getenv("MCDIFF_B200_TRAJ_L2");
+    const char* envt = getenv("MCDIFF_B200_TRAJ_THREADS");
+    const int nl2 = env2 ? atoi(env2) : 0;
+    const int nthr = envt ? atoi(envt) : kCntThreads;
+    mcd_traj_count_kernel<BinT, true><<<dim3((unsigned)S, (unsigned)G), nthr, gl * hist, st>>>(
+        (const BinT*)bins.p, N, sh, L, gl, nl2, H, counts);
   } else {
     long long S = (npack + kCntThreads - 1) / kCntThreads;
     if (S > 2LL * h->sm_count) S = 2LL * h->sm_count;
     if (S < 1) S = 1;
-    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, 1), kCntThreads, 0, st>>>((const BinT*)bins.p, N, sh, L, L, H,
-                                                                                      counts);
+    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, 1), kCntThreads, 0, st>>>((const BinT*)bins.p, N, sh, L, L, 0,
+                                                                                      H, counts);
   }
   TRAJ_TRY(cudaGetLastError());
   h->launches++;

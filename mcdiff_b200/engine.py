@@ -178,6 +178,47 @@ class DeviceProblem:
         return ll, Pn, st
 
 
+class PropagatorProblem(DeviceProblem):
+    """`scipy.linalg.expm(t * rate)` for batches of rate matrices `init_rate_matrix(n, v, w, pbc)` with optional
+    absorbing rates on the diagonal (mcd_propagator_batch; lib/permeability/mfpt.py:364-475, perm.py:391).
+    A one-lag DeviceProblem with empty counts: the kernels are the likelihood kernels, the counts are not used."""
+
+    def __init__(self, eng: Engine, n: int, pbc: bool):
+        super().__init__(eng, np.zeros((1, int(n), int(n)), dtype=np.int64), [1.0], pbc)
+        if not self.squaring_ok:
+            raise K.McdError("no squaring engine for %d bins" % n)
+
+    def propagators_device(self, d_v, d_w, d_times, d_sink=None):
+        """Device tensors v [B][n], w [B][dim_w], times [B], sink [B][n] or None -> P [B][n][n], status [B]."""
+        eng = self.eng
+        B = d_v.shape[0]
+        P = torch.empty((B, self.n, self.n), dtype=torch.float64, device=eng.device)
+        status = torch.empty(B, dtype=torch.int32, device=eng.device)
+        K.check(eng.lib.mcd_propagator_batch(eng.handle, self.ptr, B, _dev(d_v), _dev(d_w), _dev(d_sink), _dev(d_times),
+                                             _dev(P), _dev(status), eng.stream_ptr()), "mcd_propagator_batch")
+        return P, status
+
+    def propagators(self, v, w, times, sink=None):
+        """Host arrays in, host arrays out.  v, w (and sink) may be one profile (broadcast over the times) or [B][..]."""
+        eng = self.eng
+        times = np.atleast_1d(np.asarray(times, dtype=np.float64))
+        B = times.size
+
+        def rows(a, width):
+            a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+            if a.shape[1] != width or a.shape[0] not in (1, B):
+                raise ValueError("profile shapes do not match the problem / the number of times")
+            return np.ascontiguousarray(np.broadcast_to(a, (B, width)))
+
+        with torch.cuda.device(eng.device):
+            d_v = eng.to_device(rows(v, self.n), torch.float64)
+            d_w = eng.to_device(rows(w, self.dim_w), torch.float64)
+            d_s = None if sink is None else eng.to_device(rows(sink, self.n), torch.float64)
+            d_t = eng.to_device(times, torch.float64)
+            P, status = self.propagators_device(d_v, d_w, d_t, d_s)
+            return to_host(P), to_host(status)
+
+
 class ChainBatch:
     """State of C independent chains on one GPU (what MCState + model hold per chain)."""
 

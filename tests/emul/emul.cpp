@@ -64,7 +64,49 @@ void make_problem(const mcd_problem_desc* d, HostProblem& hp) {
 }
 }  // namespace
 
+// emulator-only method code: Chain<Exec, 4>, the tensor-only build of the full-storage engine
+constexpr int kEmulTensorOnly = 5;
+
+// absorbing rates of the next emul_loglike_batch call ([B][n], as mcd_propagator_batch's sink), or null
+static const double* g_sink = nullptr;
+
+template <int kMode>
+static int loglike_full(const Problem& P, int method, int B, const double* v, const double* w, const double* lagtimes,
+                        double* out_ll, double* out_P, int* status, int* sweeps, std::vector<double>& mat,
+                        std::vector<unsigned char>& vec, std::vector<double>& store) {
+  Smem s = carve(P, mat.data(), vec.data());
+  HostExec ex(store.data());
+  Chain<HostExec, kMode> ch(ex, P, s);
+  ch.build_tables();
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < P.np; ++i) {
+      s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
+      s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
+    }
+    for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
+    s.sc->status = 0;
+    ch.sink_ = g_sink ? g_sink + (size_t)b * P.n : nullptr;
+    int sw = 0;
+    double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
+    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
+    if (method >= MCD_METHOD_SQUARING) {   // as mcd_loglike_kernel: shifted lag times walk plan[1], anything else is flagged
+      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;
+      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
+                                               : ch.evaluate_sq(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], slots.data(), 0,
+                                                                method == MCD_METHOD_SQUARING, Pb, &sw);
+    } else {
+      out_ll[b] = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
+    }
+    if (status) status[b] = (int)s.sc->status;
+    if (sweeps) sweeps[b] = sw;
+  }
+  return 0;
+}
+
+
 extern "C" {
+
+void emul_set_sink(const double* sink) { g_sink = sink; }
 
 int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const double* v, const double* w,
                        const double* lagtimes, double* out_ll, double* out_P, int* status, int* sweeps) {
@@ -110,6 +152,7 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
       }
       for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
       s.sc->status = 0;
+      ch.sink_ = g_sink ? g_sink + (size_t)b * P.n : nullptr;
       if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;   // as mcd_loglike_blk_kernel
       int sw = 0;
       double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
@@ -143,32 +186,9 @@ int emul_loglike_batch(const mcd_problem_desc* d, int method, int B, const doubl
     }
     return 0;
   }
-  Smem s = carve(P, mat.data(), vec.data());
-  HostExec ex(store.data());
-  Chain<HostExec> ch(ex, P, s);
-  ch.build_tables();
-  for (int b = 0; b < B; ++b) {
-    for (int i = 0; i < P.np; ++i) {
-      s.v[i] = i < P.n ? v[(size_t)b * P.n + i] : 0.0;
-      s.w[i] = i < P.dim_w ? w[(size_t)b * P.dim_w + i] : 0.0;
-    }
-    for (int l = 0; l < P.nlag; ++l) s.lag[l] = lagtimes ? lagtimes[(size_t)b * P.nlag + l] : P.lagtimes[l];
-    s.sc->status = 0;
-    int sw = 0;
-    double* Pb = out_P ? out_P + (size_t)b * P.nlag * P.n * P.n : nullptr;
-    std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
-    if (method >= MCD_METHOD_SQUARING) {   // as mcd_loglike_kernel: shifted lag times walk plan[1], anything else is flagged
-      if (lagtimes && !shifted_lags_ok(P, s.lag)) s.sc->status |= ST_BAD_LAGS;
-      out_ll[b] = (s.sc->status & ST_BAD_LAGS) ? nan("")
-                                               : ch.evaluate_sq(s.v, s.w, s.lag, P.plan[lagtimes ? 1 : 0], slots.data(), 0,
-                                                                method == MCD_METHOD_SQUARING, Pb, &sw);
-    } else {
-      out_ll[b] = ch.evaluate(s.v, s.w, s.lag, 1, Pb, &sw);
-    }
-    if (status) status[b] = (int)s.sc->status;
-    if (sweeps) sweeps[b] = sw;
-  }
-  return 0;
+  if (method == kEmulTensorOnly)   // the production kernel of the in-shared-memory engine (mcd_mc_run_sq_kernel, mcd_small.cu)
+    return loglike_full<4>(P, MCD_METHOD_SQUARING, B, v, w, lagtimes, out_ll, out_P, status, sweeps, mat, vec, store);
+  return loglike_full<0>(P, method, B, v, w, lagtimes, out_ll, out_P, status, sweeps, mat, vec, store);
 }
 
 int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mcd_chain_io* io, int nchains,
@@ -212,6 +232,17 @@ int emul_mc_run(const mcd_problem_desc* d, const mcd_mc_params* params, const mc
       Smem s = carve(P, mat.data(), vec.data(), true, true);
       HostExec ex(store.data());
       Chain<HostExec, 3> ch(ex, P, s);
+      ch.run(mp, cio, c, nsteps, slots.data());
+    }
+    return 0;
+  }
+  if (mp.method == kEmulTensorOnly) {
+    mp.method = MCD_METHOD_SQUARING;
+    for (int c = 0; c < nchains; ++c) {
+      Smem s = carve(P, mat.data(), vec.data());
+      HostExec ex(store.data());
+      Chain<HostExec, 4> ch(ex, P, s);
+      std::vector<double> slots((size_t)kMaxSlots * P.np * P.ld);
       ch.run(mp, cio, c, nsteps, slots.data());
     }
     return 0;

@@ -93,6 +93,20 @@ def loglike_batch(prob: HostProblem, v, w, lagtimes=None, want_P=False, method=1
     return out, P, status, sweeps
 
 
+def propagator_batch(prob: HostProblem, v, w, sink, times):
+    """Host twin of mcd_propagator_batch: exp(t (R - diag(sink))) per item on the tensor-core squaring route of the
+    chain body (a one-lag problem; per-item time and absorbing rates)."""
+    assert len(prob.lagtimes) == 1
+    sk = None if sink is None else np.ascontiguousarray(np.atleast_2d(sink), dtype=np.float64)
+    lib().emul_set_sink(C.c_void_p(ptr(sk)))
+    try:
+        _, P, status, _ = loglike_batch(prob, v, w, lagtimes=np.asarray(times, dtype=np.float64)[:, None], want_P=True,
+                                        method=2)
+    finally:
+        lib().emul_set_sink(C.c_void_p(None))
+    return P[:, 0], status
+
+
 class HostChains:
     """Host-memory twin of mcdiff_b200.engine.ChainState for the emulator."""
 

@@ -401,3 +401,74 @@ def test_packed_engine_mc_replay(gold_replay):
         np.testing.assert_allclose(chn.scal[0, K.S_LL], ref["ll"], rtol=1e-11)
     finally:
         H.use_threads(None)
+
+
+# ---- tensor-only build of the full-storage engine (Chain<Exec, 4>: mcd_mc_run_sq_kernel, mcd128_mc_run_kernel) ------
+TENSOR_ONLY = 5  # emulator-only method code
+
+
+@pytest.mark.parametrize("threads", [None, 128])
+@pytest.mark.parametrize("n,lags,pbc", [(5, [1.0, 2.0, 3.0, 5.0, 10.0], True),      # general plan with slots (fuzz case)
+                                        (24, [4.0, 4.0, 8.0], False),               # duplicate lag: buffer_loglike
+                                        (40, [1.0e-4, 2.0e-4], True),               # kernels that need no squaring
+                                        (56, [10.0, 20.0, 30.0, 40.0], True)])
+def test_tensor_only_engine_plans(threads, n, lags, pbc):
+    """Every branch of evaluate_sq in the production build: parked operands, duplicate lag times and squaring-free
+    kernels take their likelihood terms from buffer_loglike, which walks the 4x4 tile table -- the table has to exist
+    in this build too (it did not: illegal addresses on the GPU, found by the randomised sweep)."""
+    from oracle import mcdiff_oracle as O
+    lags = np.array(lags)
+    counts = O.synthetic_counts(n, np.maximum(lags, 1.0), seed=n, total=1.0e5, dz=0.7)[0]
+    if not pbc:
+        counts = counts.copy()
+        counts[:, 0, n - 1] = 0
+        counts[:, n - 1, 0] = 0
+    rng = np.random.default_rng(n)
+    v = rng.normal(0.0, 0.6, (2, n))
+    w = -0.5 + rng.normal(0.0, 0.3, (2, n if pbc else n - 1))
+    H.use_threads(threads)
+    try:
+        prob = H.HostProblem(counts, lags, pbc)
+        ll, P, st, _ = H.loglike_batch(prob, v, w, want_P=True, method=TENSOR_ONLY)
+        assert not st.any()
+        ref = np.array([O.log_like_lag(v[b], w[b], lags, counts, pbc) for b in range(2)])
+        np.testing.assert_allclose(ll, ref, rtol=1e-11)
+        for l, lag in enumerate(lags):
+            assert np.max(np.abs(P[0, l] - O.propagator(v[0], w[0], lag, pbc))) < 1e-12
+        if pbc and len(lags) > 2:
+            lt = lags[None, :] + np.array([0.3, -0.2])[:, None]                 # time-offset trial: plan[1]
+            ll_s, _, st_s, _ = H.loglike_batch(prob, v, w, lagtimes=lt, method=TENSOR_ONLY)
+            assert not st_s.any()
+            ref_s = np.array([O.log_like_lag(v[b], w[b], lt[b], counts, pbc) for b in range(2)])
+            np.testing.assert_allclose(ll_s, ref_s, rtol=1e-11)
+    finally:
+        H.use_threads(None)
+
+
+def test_tensor_only_engine_mc_replay():
+    """The MC loop of the production build on the host: general lag plan + time-offset moves at n = 5 (the failing
+    configuration of the randomised GPU sweep) against the oracle replay, 128-thread build."""
+    from mcdiff_b200 import _capi as K, philox
+    from oracle import mcdiff_oracle as O
+    n, lags, seed, nsteps = 5, np.array([1.0, 2.0, 3.0, 5.0, 10.0]), 736475806, 25
+    rng = np.random.default_rng(6)
+    counts = (rng.poisson(3.0, size=(len(lags), n, n)) * 30).astype(np.int64)
+    v0, w0 = np.zeros(n), np.full(n, -1.0)
+    H.use_threads(128)
+    try:
+        prob = H.HostProblem(counts, lags, True)
+        ll0 = O.log_like_lag(v0, w0, lags, counts, True)
+        ch = H.HostChains(prob, 2, v0, w0, ll0=ll0, dv=0.3, dw=0.3, dt0=0.3)
+        mp = K.McParams()
+        mp.num_mc_update, mp.min_lt, mp.move_timezero = 10.0, 1.0, 1
+        mp.sample_every, mp.refresh_every, mp.seed, mp.method = 100, 512, seed, TENSOR_ONLY
+        dec, _ = ch.run(nsteps, mp)[:2]
+        cfg = O.ChainConfig(counts, lags, True, dv=0.3, dw=0.3, dtimezero=0.3, temp=1.0, nmc=nsteps, num_mc_update=10.0,
+                            move_timezero=True)
+        for c in range(2):
+            tu, ti = philox.chain_tape(seed, c, 0, nsteps, n, n, 0, 0)
+            out = O.replay(cfg, v0, w0, tu, ti)
+            assert np.array_equal(dec[c] & 1, out["accepted"]) and np.array_equal((dec[c] >> 1) & 1, out["accepted_t0"])
+            assert abs(ch.scal[c][0] - out["ll"]) <= 1e-9 * abs(out["ll"])
+    finally:
+        H.use_threads(None)
