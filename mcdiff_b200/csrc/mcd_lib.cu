@@ -404,7 +404,8 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   const size_t b_wb = align256((size_t)dim_w * d->ncosD * 8);
   const size_t b_sv = d->spring_k > 0.0 ? align256((size_t)dim_w * dim_w * 8) : 0;
   unsigned char* blob = nullptr;
-  cudaError_t e = cudaMalloc(&blob, b_lag + 2 * b_cnt + b_rv + b_vb + b_wb + b_sv + 256);
+  // stream-ordered allocation from the device pool: cudaMalloc / cudaFree cost tens of milliseconds per problem here
+  cudaError_t e = cudaMallocAsync((void**)&blob, b_lag + 2 * b_cnt + b_rv + b_vb + b_wb + b_sv + 256, st);
   if (e != cudaSuccess) { delete p; return (int)e; }
   p->blob = blob;
   unsigned char* q = blob;
@@ -425,7 +426,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
   if (d->spring_k > 0.0)
     cudaMemcpyAsync(sv, d->string_vecs, (size_t)dim_w * dim_w * 8, cudaMemcpyDeviceToDevice, st);
   e = cudaGetLastError();
-  if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
+  if (e != cudaSuccess) { cudaFreeAsync(blob, st); delete p; return (int)e; }
 
   Problem& P = p->P;
   P.dim_w = dim_w; P.pbc = d->pbc ? 1 : 0; P.nlag = d->nlag;
@@ -447,7 +448,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     double hl[kMaxLag];
     e = cudaMemcpyAsync(hl, d->lagtimes, (size_t)d->nlag * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
+    if (e != cudaSuccess) { cudaFreeAsync(blob, st); delete p; return (int)e; }
     plan_lags(hl, d->nlag, false, &P.plan[0]);
     plan_lags(hl, d->nlag, true, &P.plan[1]);
     p->blk_smem_bytes = smem_matrix_bytes(P.nbk, P.lds) + smem_vectors_bytes(np, true);
@@ -455,7 +456,7 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
     p->squaring_ok = (p->in_smem || p->blocked) && P.plan[0].ok && P.plan[1].ok;
     // --pull: only the general squaring engine applies (periodic, work matrices in shared memory, a LagPlan)
     if (P.use_pull && !(P.pbc && p->in_smem && P.plan[0].ok && P.plan[1].ok)) {
-      cudaFree(blob);
+      cudaFreeAsync(blob, st);
       delete p;
       return MCD_E_UNSUPPORTED;
     }
@@ -472,7 +473,8 @@ int mcd_problem_create(mcd_handle* h, const mcd_problem_desc* d, void* stream, m
 int mcd_problem_destroy(mcd_problem* p) {
   if (!p) return MCD_OK;
   cudaSetDevice(p->h->device);
-  cudaFree(p->blob);
+  cudaDeviceSynchronize();          // as cudaFree would: no kernel of any stream still reads the problem
+  cudaFreeAsync(p->blob, nullptr);  // back to the pool (no driver unmap)
   delete p;
   return MCD_OK;
 }
@@ -739,7 +741,7 @@ int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* s
   const size_t b_be = align256((size_t)R.lmax * R.dim_rad * 8), b_z = align256((size_t)R.lmax * 8);
   const size_t b_wb = align256((size_t)n * d->ncosDrad * 8);
   unsigned char* blob = nullptr;
-  cudaError_t e = cudaMalloc(&blob, b_v + b_w + b_lag + b_cnt + b_pc + b_be + b_z + b_wb + 256);
+  cudaError_t e = cudaMallocAsync((void**)&blob, b_v + b_w + b_lag + b_cnt + b_pc + b_be + b_z + b_wb + 256, st);
   if (e != cudaSuccess) { delete p; return e == cudaErrorMemoryAllocation ? MCD_E_NOMEM : (int)e; }
   p->blob = blob;
   unsigned char* q = blob;
@@ -764,12 +766,12 @@ int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* s
   e = cudaMemcpyAsync(hl, dl, (size_t)R.nlag * 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { cudaFree(blob); delete p; return (int)e; }
+  if (e != cudaSuccess) { cudaFreeAsync(blob, st); delete p; return (int)e; }
   R.v = dv; R.w = dw; R.lagtimes = dl; R.counts = dc; R.pcounts = dp; R.bessels = db; R.b0zeros = dz;
   p->wrad_basis = d->ncosDrad > 0 ? dwb : nullptr;
   p->ncosDrad = d->ncosDrad;
   plan_lags(hl, R.nlag, false, &R.plan);
-  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) { cudaFree(blob); delete p; return MCD_E_UNSUPPORTED; }
+  if (rad_smem_bytes(R, 1) > (size_t)h->max_smem_optin) { cudaFreeAsync(blob, st); delete p; return MCD_E_UNSUPPORTED; }
   R.nbatch = R.plan.ok ? rad_pick_batch(R, (size_t)h->max_smem_optin) : 1;
   p->smem_bytes = rad_smem_bytes(R, R.nbatch);
   // small profiles on the squaring route: 128-thread CTAs, three per SM (a third of the SM's shared memory each,
@@ -785,7 +787,8 @@ int mcd_rad_problem_create(mcd_handle* h, const mcd_rad_problem_desc* d, void* s
 int mcd_rad_problem_destroy(mcd_rad_problem* p) {
   if (!p) return MCD_OK;
   cudaSetDevice(p->h->device);
-  cudaFree(p->blob);
+  cudaDeviceSynchronize();          // as cudaFree would: no kernel of any stream still reads the problem
+  cudaFreeAsync(p->blob, nullptr);  // back to the pool (no driver unmap)
   delete p;
   return MCD_OK;
 }

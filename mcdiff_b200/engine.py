@@ -69,6 +69,8 @@ class Engine:
         if t.dtype != dtype:
             t = t.to(dtype)
         TRAFFIC["h2d"] += t.numel() * t.element_size()
+        if t.numel() * t.element_size() < (1 << 20):
+            return t.to(self.device)          # small: page-locking a fresh buffer costs more (~2 ms) than the staged copy
         return t.pin_memory().to(self.device, non_blocking=True)
 
     def fp64_peak_tflops(self) -> float:

@@ -153,7 +153,7 @@ def run_lag_scan(files_by_lag, outdir, *, pbc=True, model="CosinusModel", ncosF=
             naccw_coeff=rows[:, o + 2 * nF + nD:].astype(np.int64)))
         with open(out, "w") as f:
             MC.print_laststate(f, final=True)
-        np.savez_compressed(out + ".chains.npz", log_like=MC.chain_log_like, v=MC.chain_v, w=MC.chain_w,
+        np.savez(out + ".chains.npz", log_like=MC.chain_log_like, v=MC.chain_v, w=MC.chain_w,
                             naccv=MC.chain_naccv, naccw=MC.chain_naccw, status=MC.chain_status)
     if world > 1:
         import torch.distributed as dist

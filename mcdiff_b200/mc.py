@@ -109,7 +109,7 @@ def _finish_radial(MC, logger, outfile, nmc, rank):
         return MC, logger
     _write_outputs(MC, pooled, outfile)
     n = MC.model.dim_wrad
-    np.savez_compressed((outfile or "mc") + ".chains.npz", log_like=allrows[:, 0], dwrad=allrows[:, 1],
+    np.savez((outfile or "mc") + ".chains.npz", log_like=allrows[:, 0], dwrad=allrows[:, 1],
                         naccwrad=allrows[:, 8], status=allrows[:, 11], scal=allrows[:, :8],
                         counters=allrows[:, 8:16].astype(np.int64), wrad=allrows[:, 16:16 + n],
                         wrad_coeff=allrows[:, 16 + n:16 + n + ncos],
@@ -185,7 +185,7 @@ def find_parameters(filenames, pbc, model, dv, dw, dwrad, D0, dtimezero, temp, t
     o += nv + nw
     vc, wc = allrows[:, o:o + nF], allrows[:, o + nF:o + nF + nD]
     o += nF + nD
-    np.savez_compressed((outfile or "mc") + ".chains.npz",
+    np.savez((outfile or "mc") + ".chains.npz",
                         log_like=allrows[:, K.S_LL], dv=allrows[:, K.S_DV], dw=allrows[:, K.S_DW],
                         naccv=allrows[:, 8 + K.C_NACCV], naccw=allrows[:, 8 + K.C_NACCW],
                         nacctimezero=allrows[:, 8 + K.C_NACCT0], status=allrows[:, 8 + K.C_STATUS],
