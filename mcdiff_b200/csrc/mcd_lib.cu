@@ -20,6 +20,9 @@ size_t mcd128_problem_bytes();
 size_t mcd128_smem_bytes(int np, int ld);
 int mcd128_launch_mc_run(const void* problem, const void* params, const void* io, int nchains, int nsteps, size_t smem,
                          double* gws, cudaStream_t st);
+#if defined(MCD_PHASE_CLOCK)
+int mcd128_debug_phase_clocks(long long* out32);
+#endif
 constexpr int kSmallBins = 56;   // 7 x 7 tiles: at most 4 symmetric warp tasks
 // mcd_pk.cu: 256-thread CTAs with packed symmetric work matrices, two chains per SM (kSmallBins < np <= 104)
 size_t mcdpk_problem_bytes();
@@ -859,10 +862,12 @@ int mcd_rad_mc_run(mcd_handle* h, const mcd_rad_problem* p, const mcd_rad_mc_par
 #if defined(MCD_PHASE_CLOCK)
 // debug build only (profiles/prof_phases.py): read and reset the phase clocks of CTA 0
 int mcd_debug_phase_clocks(long long* out32) {
-  long long z[32] = {0};
+  long long z[32] = {0}, small[32] = {0};
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out32, mcd::g_phase_clk, sizeof(z));
   cudaMemcpyToSymbol(mcd::g_phase_clk, z, sizeof(z));
+  mcd128_debug_phase_clocks(small);   // the 128-thread kernels of mcd_small.cu keep their own clocks
+  for (int i = 0; i < 32; ++i) out32[i] += small[i];
   return (int)cudaGetLastError();
 }
 #endif

@@ -33,9 +33,15 @@ struct RadProblem {
 constexpr int kMaxBessel = 64;
 constexpr int kMaxRadBatch = 6;   // Bessel terms advanced in lockstep by the squaring route
 
+// Squaring route: the kernels G_m(t_l) wait for the Bessel sums in a per-CTA global (L2) workspace.  Only the pairs
+// i <= j are kept, pair-major [nlag][lmax][rad_kernel_stride(n)]: 3.7 KB per kernel at n = 30 instead of the 9.2 KB of a
+// padded matrix, so that the workspaces of all resident CTAs (592 x 150 KB at config 5) stay inside L2 (the full
+// matrices did not: ncu r02d, 7.4 GB of DRAM traffic per launch, long_scoreboard the top stall), and the staging
+// loads of the Bessel sums are contiguous instead of one sector per element.
+MCD_HOSTDEV size_t rad_kernel_stride(int n) { return (((size_t)n * (n + 1) / 2) + 3) & ~(size_t)3; }
 MCD_HOSTDEV size_t rad_workspace_doubles(const RadProblem& R) {
   const size_t eig = (size_t)R.lmax * R.np * R.ld + (size_t)R.lmax * R.np;
-  const size_t sq = ((size_t)R.nlag * R.lmax + (size_t)kMaxSlots * kMaxRadBatch) * R.np * R.ld;
+  const size_t sq = (size_t)R.nlag * R.lmax * rad_kernel_stride(R.n) + (size_t)kMaxSlots * kMaxRadBatch * R.np * R.ld;
   return eig > sq ? eig : sq;
 }
 // shared memory: nbatch pairs of work matrices, the chain vectors, a0[np], elm[lmax][np] (only the eigen
@@ -98,7 +104,7 @@ struct RadCtx {
   Smem& s;
   double* a0;      // [np] diagonal of the 1-D generator
   double* elm;     // [lmax][np]
-  double* ws_x;    // squaring: [lmax][nlag][np][ld] kernels; eigen: [lmax][np][ld] eigenvectors (global, L2 resident)
+  double* ws_x;    // squaring: [nlag][lmax][rad_kernel_stride] packed kernels + slots; eigen: [lmax][np][ld] eigenvectors (global, L2 resident)
   double* ws_lam;  // [lmax][np]
   const unsigned char* ptab;  // (i, j) of the pairs i <= j, row-major
   double* ewr;     // [np] exp(wrad)
@@ -176,6 +182,18 @@ struct RadCtx {
     });
   }
 
+  // kernels of the nb terms of a batch -> packed pair-major rows of the workspace (dst: row of the first term)
+  __device__ __forceinline__ void batch_pack(double* dst, const double* src, int nb) {
+    const int npairs = R.n * (R.n + 1) / 2, ld = R.ld;
+    const size_t me = (size_t)R.np * ld, kst = rad_kernel_stride(R.n);
+    ex.par([&](int tid) {
+      for (int p = tid; p < npairs; p += kThreads) {
+        const int off = (int)ptab[2 * p] * ld + (int)ptab[2 * p + 1];
+        for (int b = 0; b < nb; ++b) dst[(size_t)b * kst + p] = src[(size_t)b * me + off];
+      }
+    });
+  }
+
   // exp(t S_b) for the nb terms of the batch: Taylor/Horner + squarings.  bank0 / bank1: NB matrices
   // each.  Returns the bank holding the results (*other: the second one), nullptr for an absurd scale.
   __device__ __forceinline__ double* batch_chain(double t, double gersh, int nb, int NB, int T1, double* bank0,
@@ -222,6 +240,7 @@ struct RadCtx {
         });
       }
     }
+    MCD_CLK(25);   // Taylor polynomials of the batch (23: the squarings that follow)
     double* src = bank0;
     double* dst = bank1;
     double* G = src;
@@ -250,6 +269,7 @@ struct RadCtx {
     const int lpad = (lmax + 3) & ~3, mt = (dim_rad + 7) / 8;
     if ((size_t)lpad * CHP > 2 * (size_t)NB * me) return false;
     const int npairs = n * (n + 1) / 2;
+    const size_t kst = rad_kernel_stride(n);
     double* gs = s.XT;   // [lpad][CHP]
     const double clip = R.clip, logclip = log(R.clip);
     for (int l = 0; l < R.nlag; ++l) {
@@ -265,8 +285,7 @@ struct RadCtx {
               const bool inr = e < CHT * lpad;
               const bool live = inr && m < lmax && c0 + p < npairs;
               const int pr = live ? c0 + p : 0;
-              const int i = ptab[2 * pr], j = ptab[2 * pr + 1];
-              const double x = ws_x[((size_t)l * lmax + (live ? m : 0)) * me + (size_t)i * ld + j];
+              const double x = ws_x[((size_t)l * lmax + (live ? m : 0)) * kst + pr];
               g[q] = live ? x : 0.0;
               dst[q] = inr ? m * CHP + p : -1;
             }
@@ -378,7 +397,8 @@ struct RadCtx {
     if (NB * T1 > kThreads / 32) NB = (kThreads / 32) / T1;
     double* bank0 = s.XT;
     double* bank1 = s.XT + (size_t)NB * me;
-    double* slots = ws_x + (size_t)R.nlag * lmax * me;
+    const size_t kst = rad_kernel_stride(n);
+    double* slots = ws_x + (size_t)R.nlag * lmax * kst;
     const bool fast = pl.fast != 0;
     int bad = 0;
     ex.par([&](int tid) {
@@ -418,7 +438,7 @@ struct RadCtx {
         O = other;
       }
       if (bad) break;
-      batch_copy(ws_x + ((size_t)pl.order[0] * lmax + m0) * me, Rk, nb);
+      batch_pack(ws_x + ((size_t)pl.order[0] * lmax + m0) * kst, Rk, nb);
       double* G0 = Rk;
       int in_O = -1;
       for (int i = 1; i < R.nlag; ++i) {
@@ -436,7 +456,7 @@ struct RadCtx {
             batch_product(Rk, O, Rk, nb, T1, 2);
           }
         }
-        batch_copy(ws_x + ((size_t)l * lmax + m0) * me, res, nb);
+        batch_pack(ws_x + ((size_t)l * lmax + m0) * kst, res, nb);
         if (!fast && pl.park[i] >= 0) batch_copy(slots + (size_t)pl.park[i] * NB * me, Rk, nb);
       }
     }
@@ -465,10 +485,7 @@ struct RadCtx {
         ex.par([&](int tid) {
           for (int e = tid; e < CH * lmax; e += kThreads) {
             const int m = e / CH, p = e - m * CH;
-            if (c0 + p < npairs) {
-              const int i = ptab[2 * (c0 + p)], j = ptab[2 * (c0 + p) + 1];
-              gs[e] = ws_x[((size_t)l * lmax + m) * me + (size_t)i * ld + j];
-            }
+            if (c0 + p < npairs) gs[e] = ws_x[((size_t)l * lmax + m) * kst + c0 + p];
           }
         });
         // thread (p, kg): four radial bins at a time -- four independent Bessel sums, their count loads

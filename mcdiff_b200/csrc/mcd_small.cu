@@ -87,3 +87,13 @@ int mcd128_launch_rad_loglike(const void* rproblem, int grid, int B, const doubl
   mcd_rad_loglike_kernel<<<grid, kThreads, smem, st>>>(R, B, wrad, out_ll, out_P, status, gws);
   return (int)cudaGetLastError();
 }
+
+#if defined(MCD_PHASE_CLOCK)
+// debug build only: the phase clocks of this translation unit's kernels (read and reset), added to mcd_debug_phase_clocks
+int mcd128_debug_phase_clocks(long long* out32) {
+  long long z[32] = {0};
+  cudaMemcpyFromSymbol(out32, mcd128::g_phase_clk, sizeof(z));
+  cudaMemcpyToSymbol(mcd128::g_phase_clk, z, sizeof(z));
+  return (int)cudaGetLastError();
+}
+#endif

@@ -76,6 +76,22 @@ class Logger:
         else:
             self.w[a:b] = pw
 
+    def fill_rows_all(self, first_row, samples, model):
+        """samples: [nchains][k][sample_dim] of ALL chains of this Logger at once (one strided copy per field instead
+        of a Python call per chain: 1024 chains cost 3 ms per chunk the slow way)."""
+        k = samples.shape[1]
+        if k == 0:
+            return
+        a, b = first_row, first_row + k
+
+        def view(arr):
+            return arr.reshape((self.nchains, self.nf_chain) + arr.shape[1:])
+        for j, name in enumerate(("log_like", "timezero", "dv", "dw", "dtimezero", "temp")):
+            view(getattr(self, name))[:, a:b] = samples[:, :, j]
+        nv = model.ncosF if model.ncosF > 0 else model.dim_v
+        view(self.v_coeff if model.ncosF > 0 else self.v)[:, a:b] = samples[:, :, 6:6 + nv]
+        view(self.w_coeff if model.ncosD > 0 else self.w)[:, a:b] = samples[:, :, 6 + nv:]
+
     def fill_rows_radial(self, chain, first_row, rows, MC):
         """rows: [k][3 + nw] = {log_like, dwrad, temp, wrad | wrad_coeff}; v, w are frozen in radial runs."""
         k = rows.shape[0]

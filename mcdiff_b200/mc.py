@@ -59,8 +59,7 @@ def do_mc_cycles(MC, logger, chunk=1000):
         samples = MC.advance(n)
         done += n
         if samples is not None and samples.shape[1] > 0:
-            for c in range(MC.nchains):
-                logger.fill_rows(c, next_row, samples[c], m)
+            logger.fill_rows_all(next_row, samples, m)
             next_row += samples.shape[1]
         MC.print_intermediate(done - 1)
     logger.dwrad[:] = MC.dwrad

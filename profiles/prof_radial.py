@@ -41,8 +41,10 @@ if hasattr(eng.lib, "mcd_debug_phase_clocks"):      # -DMCD_PHASE_CLOCK build (M
     ch.run(nsteps, num_mc_update=100, seed=1); torch.cuda.synchronize()
     eng.lib.mcd_debug_phase_clocks(out)
     names = {20: "lag products, copies to the workspace", 21: "Bessel sums + logarithms", 22: "batch diagonals, Gershgorin",
-             23: "Taylor/Horner + squarings of the batch", 24: "proposal, Metropolis, records"}
-    tot = float(sum(out))
+             23: "squarings of the batch", 24: "proposal, Metropolis, records", 25: "Taylor polynomials of the batch"}
+    tot = float(sum(out)) or 1.0
     print("cycles per MC step (CTA 0): %.0f" % (tot / nsteps))
-    for i in sorted(names):
-        print("%2d %-42s %9.0f cycles/step %5.1f %%" % (i, names[i], out[i] / nsteps, 100.0 * out[i] / tot))
+    for i in range(32):
+        if out[i]:
+            print("%2d %-42s %9.0f cycles/step %5.1f %%" % (i, names.get(i, "(chain-body phase %d)" % i), out[i] / nsteps,
+                                                          100.0 * out[i] / tot))

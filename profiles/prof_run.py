@@ -1,7 +1,7 @@
 """Small fixed workloads for ncu (one wave of CTAs, a few launches; capture the last one):
   python profiles/prof_run.py main   [method]   296 chains x 20 MC steps of the bench headline (100 bins x 4 lags)
   python profiles/prof_run.py c3                148 chains x 10 MC steps of config 3 (200 bins x 8 lags, blocked engine)
-  python profiles/prof_run.py radial            148 chains x 20 MC steps of config 5 (n=30, dim_rad=41, lmax=20)
+  python profiles/prof_run.py radial [chains]   592 chains (4 per SM) x 20 MC steps of config 5 (n=30, dim_rad=41, lmax=20)
 The workloads are the ones bench.py times (same generators, same models)."""
 import os
 import sys
@@ -91,7 +91,8 @@ else:
     rmodel = RadCosinusModel(rdata, 1.0, 0, 0, 0, 4)
     rr = np.arange(rmodel.dim_rad, dtype=np.float64) + 0.5
     bess = np.array([2 * rr * special.j0(rr / rmodel.dim_rad * z) / special.j1(z) ** 2 / rmodel.dim_rad ** 2 for z in zeros])
-    rch = RadialChains(eng, rmodel.v, rmodel.w, True, rdata.list_lt, rdata.list_trans, bess, zeros, 148,
+    rch = RadialChains(eng, rmodel.v, rmodel.w, True, rdata.list_lt, rdata.list_trans, bess, zeros,
+                       int(sys.argv[2]) if len(sys.argv) > 2 else 592,      # 592 = 148 SMs x 4 resident chains
                        wrad_basis=rmodel.wrad_basis)
     rch.set_state(rmodel.wrad, rmodel.wrad_coeff, dwrad=0.05)
     rch.init_log_like()
