@@ -134,12 +134,16 @@ def _replay_chain(args):
     cfg = O.ChainConfig(counts, lags, True, v_basis=vb, w_basis=wb, dv=dv, dw=dw, dtimezero=dt0, temp=1.0,
                         nmc=nsteps, num_mc_update=nupd, move_timezero=move_t0)
     tu, ti = philox.chain_tape(seed, gchain, 0, nsteps, n, n, ncf, ncd)
-    out = O.replay(cfg, np.zeros(n), wb @ wc0, tu, ti, v_coeff0=np.zeros(ncf), w_coeff0=wc0)
+    # one BLAS thread per worker: several replays run side by side, and 16 OpenBLAS threads each on a 16-core host
+    # make a 200 x 200 expm ten times slower than a single thread does
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):
+        out = O.replay(cfg, np.zeros(n), wb @ wc0, tu, ti, v_coeff0=np.zeros(ncf), w_coeff0=wc0)
     return out["accepted"], out["accepted_t0"], out["move"], out["ll"], out["timezero"], out["dv"], out["dw"]
 
 
 def _device_vs_replay(engine, counts, lags, ncf, ncd, wc00, dv, dw, dt0, nch, nsteps, nupd, move_t0, seed, off,
-                      chunks, method):
+                      chunks, method, replay=True):
     from mcdiff_b200 import _capi as K
     from mcdiff_b200.engine import ChainBatch, DeviceProblem
     from oracle import mcdiff_oracle as O
@@ -169,6 +173,8 @@ def _device_vs_replay(engine, counts, lags, ncf, ncd, wc00, dv, dw, dt0, nch, ns
     dec = np.concatenate(decs, axis=1)
     st = ch.host_state()
     assert not st["counters"][:, 6].any()
+    if not replay:                                   # device run only (compared with another device run by the caller)
+        return st["scal"].copy(), dec, prob
     jobs = [(counts, lags, ncf, ncd, wc0, dv, dw, dt0, nsteps, nupd, move_t0, seed, off + c) for c in range(nch)]
     with ProcessPoolExecutor(max_workers=min(nch, os.cpu_count() or 1)) as ex:
         refs = list(ex.map(_replay_chain, jobs))
@@ -189,32 +195,34 @@ def test_ten_thousand_decisions_equal_the_oracle_replay(engine):
     from oracle import mcdiff_oracle as O
     counts, lags, edges, F, w_true = O.synthetic_counts()
     ndec, dec, prob = _device_vs_replay(engine, counts, lags, 10, 6, float(np.mean(w_true)), 0.05, 0.05, 0.2,
-                                        nch=8, nsteps=700, nupd=100.0, move_t0=True, seed=4242, off=0,
-                                        chunks=(200, 200, 300), method=0)
+                                        nch=16, nsteps=1000, nupd=100.0, move_t0=True, seed=4242, off=0,
+                                        chunks=(200, 300, 500), method=0)
     assert prob.squaring_ok and prob.in_smem
-    assert ndec >= 10000
+    assert ndec >= 32000
     acc = int((dec & 1).sum())
     assert 0.05 * dec.size < acc < 0.95 * dec.size                       # both outcomes are exercised
     assert int(((dec >> 1) & 1).sum()) > 0
 
 
-@pytest.mark.parametrize("cluster", ["0", "auto"])
-def test_config3_shape_mc_replay(engine, monkeypatch, cluster):
-    """200 bins x 8 lags {5..40}, CosinusModel ncosF 12 / ncosD 8 (BASELINE.json config 3) on the blocked engine:
-    one SM per chain ("0") and the default, which puts a batch smaller than a wave on two-CTA clusters ("auto")."""
-    if cluster == "0":
-        monkeypatch.setenv("MCDIFF_B200_CLUSTER", "0")
-    else:
-        monkeypatch.delenv("MCDIFF_B200_CLUSTER", raising=False)
+def test_config3_shape_mc_replay(engine, monkeypatch):
+    """200 bins x 8 lags {5..40}, CosinusModel ncosF 12 / ncosD 8 (BASELINE.json config 3) on the blocked engine: one SM
+    per chain against the oracle replay, and the default launch -- which puts a batch smaller than a wave on two-CTA
+    clusters -- against that run (same decisions, same final state)."""
     from oracle import mcdiff_oracle as O
     lags = np.array([5.0, 10.0, 15.0, 20.0, 25.0, 30.0, 35.0, 40.0])
     counts = O.synthetic_counts(200, lags, seed=3, total=1.0e6, dz=0.5)[0]
-    ndec, dec, prob = _device_vs_replay(engine, counts, lags, 12, 8, -np.log(0.25), 0.05, 0.05, 0.1,
-                                        nch=4, nsteps=28, nupd=12.0, move_t0=False, seed=33, off=7,
-                                        chunks=(18, 10), method=0)
+    args = (engine, counts, lags, 12, 8, -np.log(0.25), 0.05, 0.05, 0.1)
+    kw = dict(nch=6, nsteps=80, nupd=12.0, move_t0=False, seed=33, off=7, chunks=(50, 30), method=0)
+    monkeypatch.setenv("MCDIFF_B200_CLUSTER", "0")
+    ndec, dec, prob = _device_vs_replay(*args, **kw)
     assert prob.squaring_ok and not prob.in_smem                          # the blocked engine ran it
-    assert ndec == 4 * 28
+    assert ndec == 6 * 80
     assert 0 < int((dec & 1).sum()) < dec.size
+    scal0, dec0, _ = _device_vs_replay(*args, replay=False, **kw)
+    monkeypatch.delenv("MCDIFF_B200_CLUSTER", raising=False)
+    scal1, dec1, _ = _device_vs_replay(*args, replay=False, **kw)
+    assert np.array_equal(dec0, dec) and np.array_equal(dec1, dec)
+    np.testing.assert_allclose(scal1, scal0, rtol=1e-12)
 
 
 def test_packed_engine_two_chains_per_sm(engine, monkeypatch):
