@@ -18,7 +18,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdlib>
 
 #include "../../include/mcdiff_b200.h"
 #include "mcd_handle.h"
@@ -81,11 +80,14 @@ struct Pack4<uint8_t> {
   static __device__ __forceinline__ word make(int a, int b, int c, int d) {
     return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
   }
-  static __device__ __forceinline__ int get(word w, int e) { return (int)((w >> (8 * e)) & 0xffu); }
+  static __device__ __forceinline__ int get(word w, int e) { return (int)__byte_perm(w, 0u, 0x4440u + (unsigned)e); }
   // four bins starting at element j (any alignment) of an array padded by one word
   static __device__ __forceinline__ word load(const uint8_t* bins, long long j) {
     const word* w = reinterpret_cast<const word*>(bins) + (j >> 2);
     return __funnelshift_r(__ldg(w), __ldg(w + 1), 8 * (int)(j & 3));
+  }
+  static __device__ __forceinline__ word load_aligned(const uint8_t* bins, long long pack) {
+    return __ldg(reinterpret_cast<const word*>(bins) + pack);
   }
 };
 template <>
@@ -101,15 +103,28 @@ struct Pack4<uint16_t> {
     const word w0 = __ldg(w), w1 = __ldg(w + 1);
     return r ? ((w0 >> r) | (w1 << (64 - r))) : w0;
   }
+  static __device__ __forceinline__ word load_aligned(const uint16_t* bins, long long pack) {
+    return __ldg(reinterpret_cast<const word*>(bins) + pack);
+  }
 };
 
 // ---- kernel 1: coordinates -> bin indices -------------------------------------------------------------
+// Four coordinates per thread and iteration on a STRAIGHT-LINE fast path: the four folds and the four guesses are
+// computed without a branch (edges staged with sentinels -inf / +inf around them, so the verification is the same two
+// comparisons for every bin), and only if one of them is unsafe does the thread redo that coordinate exactly.  The
+// branchy per-coordinate version ran 52 instructions per coordinate and was issue bound (ncu: 68 % issue slots, 4.1
+// TB/s); this one is bound by the 9 B per coordinate it moves.
 template <typename BinT, bool kVec>
 __global__ void __launch_bounds__(kDigThreads)
 mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double period, const double* __restrict__ edges,
                          int ne, BinT* __restrict__ bins) {
-  extern __shared__ double se[];
+  extern __shared__ double se_raw[];   // [ne + 2]: -inf, edges, +inf
+  double* se = se_raw + 1;
   for (int k = threadIdx.x; k < ne; k += blockDim.x) se[k] = edges[k];
+  if (threadIdx.x == 0) {
+    se[-1] = __longlong_as_double((long long)0xfff0000000000000ull);      // -inf
+    se[ne] = __longlong_as_double(0x7ff0000000000000ll);                  // +inf
+  }
   __syncthreads();
   const double e0 = se[0];
   const double inv_dx = (ne > 1 && se[ne - 1] > e0) ? (double)(ne - 1) / (se[ne - 1] - e0) : 0.0;
@@ -125,9 +140,36 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
       const double2 a = __ldcs(reinterpret_cast<const double2*>(x) + 2 * p);
       const double2 b = __ldcs(reinterpret_cast<const double2*>(x) + 2 * p + 1);
       double v[4] = {a.x, a.y, b.x, b.y};
-      int k[4];
+      if (do_fold) {
+        double f[4];
+        unsigned unsafe = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) k[e] = digitize(do_fold ? fold(v[e], period, inv_period) : v[e], se, ne, e0, inv_dx);
+        for (int e = 0; e < 4; ++e) {
+          const double t = __dadd_rn(__dmul_rn(v[e], inv_period), 0.5);
+          f[e] = floor(t);
+          const unsigned hf = (unsigned)__double2hiint(t - f[e]), ht = (unsigned)__double2hiint(t) & 0x7fffffffu;
+          unsafe |= (hf > 0x3e112e0bu && hf < 0x3feffffeu && ht < 0x41300000u) ? 0u : (1u << e);   // see fold()
+        }
+        if (unsafe) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (unsafe & (1u << e)) f[e] = floor(__dadd_rn(__ddiv_rn(v[e], period), 0.5));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = __dsub_rn(v[e], __dmul_rn(period, f[e]));
+      }
+      int k[4];
+      unsigned miss = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        k[e] = min(max(__double2int_rz((v[e] - e0) * inv_dx + 1.0), 0), ne);
+        miss |= (se[k[e] - 1] <= v[e] && v[e] < se[k[e]]) ? 0u : (1u << e);
+      }
+      if (miss) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (miss & (1u << e)) k[e] = digitize(v[e], se, ne, e0, inv_dx);
+      }
       out[p] = P::make(k[0], k[1], k[2], k[3]);
     }
     for (long long i = (npack << 2) + t0; i < N; i += stride)
@@ -143,42 +185,77 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
 // once; otherwise every pair is a 64-bit atomic on the output (L2).
 template <typename BinT, bool kSmem>
 __global__ void __launch_bounds__(kCntThreads, 1)
-mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int L, int gl, int nl2, int H,
+mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int L, int gl, int H,
                       unsigned long long* __restrict__ out) {
   using P = Pack4<BinT>;
+  using word = typename P::word;
   extern __shared__ unsigned hist[];
   const int l0 = blockIdx.y * gl;
   const int nl = min(gl, L - l0);
-  const int ns = kSmem ? max(nl - nl2, 0) : 0;   // shifts [0, ns) of the group: shared-memory cells, the rest: L2 atomics
   const int HH = H * H;
   if (kSmem) {
-    for (int c = threadIdx.x; c < ns * HH; c += blockDim.x) hist[c] = 0u;
+    for (int c = threadIdx.x; c < nl * HH; c += blockDim.x) hist[c] = 0u;
     __syncthreads();
   }
+  long long maxoff = 0;
+  for (int k = 0; k < nl; ++k) maxoff = max(maxoff, sh.off[l0 + k]);
+  unsigned long long* outg = out + (size_t)l0 * HH;
   const long long npack = (N + 3) >> 2;
+  const long long nfast = (N - 3 - maxoff) >> 2;   // packs p < nfast: all four partners of every shift exist
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npack; p += stride) {
     const long long i = p << 2;
-    const typename P::word s4 = P::load(bins, i);
-    for (int k = 0; k < nl; ++k) {
-      const long long j = i + sh.off[l0 + k];
-      if (j >= N) continue;
-      const typename P::word e4 = P::load(bins, j);
+    const word s4 = P::load_aligned(bins, p);
+    const int s0 = P::get(s4, 0), s1 = P::get(s4, 1), s2 = P::get(s4, 2), s3 = P::get(s4, 3);
+    if (p < nfast) {
+      // shifts four at a time: the partner loads of a group are issued together, then its 16 increments
+      for (int k0 = 0; k0 < nl; k0 += 4) {
+        word e4[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (j + e < N) {
-          const int cell = P::get(e4, e) * H + P::get(s4, e);   // A[end, start] += 1  (extract.py:86-87)
-          if (k < ns) atomicAdd(&hist[k * HH + cell], 1u);
-          else atomicAdd(&out[(size_t)(l0 + k) * HH + cell], 1ull);
+        for (int q = 0; q < 4; ++q) e4[q] = (k0 + q < nl) ? P::load(bins, i + sh.off[l0 + k0 + q]) : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (k0 + q < nl) {
+            const int c0 = P::get(e4[q], 0) * H + s0, c1 = P::get(e4[q], 1) * H + s1;   // A[end, start] += 1
+            const int c2 = P::get(e4[q], 2) * H + s2, c3 = P::get(e4[q], 3) * H + s3;   // (extract.py:86-87)
+            if (kSmem) {
+              // byte offsets end * 4H + 4 start against the (warp-uniform) base of this shift's histogram: three
+              // instructions per increment (byte extract, multiply-add, ATOMS [reg + uniform])
+              char* hk = reinterpret_cast<char*>(hist + (k0 + q) * HH);
+              const int H4 = 4 * H;
+              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 0) * H4 + 4 * s0)), 1u);
+              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 1) * H4 + 4 * s1)), 1u);
+              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 2) * H4 + 4 * s2)), 1u);
+              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 3) * H4 + 4 * s3)), 1u);
+            } else {
+              unsigned long long* ok = outg + (size_t)(k0 + q) * HH;
+              atomicAdd(ok + c0, 1ull); atomicAdd(ok + c1, 1ull); atomicAdd(ok + c2, 1ull); atomicAdd(ok + c3, 1ull);
+            }
+          }
+        }
+      }
+    } else {   // the last max(shift) frames: partner by partner
+      const int sv[4] = {s0, s1, s2, s3};
+      for (int k = 0; k < nl; ++k) {
+        const long long j = i + sh.off[l0 + k];
+        if (j >= N) continue;
+        const word e4 = P::load(bins, j);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (j + e < N) {
+            const int cell = P::get(e4, e) * H + sv[e];
+            if (kSmem) atomicAdd(&hist[k * HH + cell], 1u);
+            else atomicAdd(&outg[(size_t)k * HH + cell], 1ull);
+          }
         }
       }
     }
   }
   if (kSmem) {
     __syncthreads();
-    for (int c = threadIdx.x; c < ns * HH; c += blockDim.x) {
+    for (int c = threadIdx.x; c < nl * HH; c += blockDim.x) {
       const unsigned v = hist[c];
-      if (v) atomicAdd(&out[(size_t)l0 * HH + c], (unsigned long long)v);
+      if (v) atomicAdd(&outg[c], (unsigned long long)v);
     }
   }
 }
@@ -238,7 +315,7 @@ int digitize_launch(mcd_handle* h, const double* x, long long N, double period, 
   const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
   long long want = (N / 4 + kDigThreads - 1) / kDigThreads;
   const int grid = (int)(want < 1 ? 1 : (want > (long long)h->sm_count * 32 ? (long long)h->sm_count * 32 : want));
-  const size_t smem = (size_t)ne * sizeof(double);
+  const size_t smem = (size_t)(ne + 2) * sizeof(double);
   if (vec) mcd_traj_digitize_kernel<BinT, true><<<grid, kDigThreads, smem, st>>>(x, N, period, edges, ne, bins);
   else mcd_traj_digitize_kernel<BinT, false><<<grid, kDigThreads, smem, st>>>(x, N, period, edges, ne, bins);
   TRAJ_TRY(cudaGetLastError());
@@ -270,19 +347,14 @@ int counts_impl(mcd_handle* h, const double* x, long long nframes, long long nco
     if (S > need) S = need < 1 ? 1 : need;
     TRAJ_TRY(cudaFuncSetAttribute(mcd_traj_count_kernel<BinT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(gl * hist)));
-    // experiment knobs (profiles/prof_traj.py): shifts per group accumulated in L2 instead of shared memory, CTA size
-    const char* env2 = getenv("MCDIFF_B200_TRAJ_L2");
-    const char* envt = getenv("MCDIFF_B200_TRAJ_THREADS");
-    const int nl2 = env2 ? atoi(env2) : 0;
-    const int nthr = envt ? atoi(envt) : kCntThreads;
-    mcd_traj_count_kernel<BinT, true><<<dim3((unsigned)S, (unsigned)G), nthr, gl * hist, st>>>(
-        (const BinT*)bins.p, N, sh, L, gl, nl2, H, counts);
+    mcd_traj_count_kernel<BinT, true><<<dim3((unsigned)S, (unsigned)G), kCntThreads, gl * hist, st>>>(
+        (const BinT*)bins.p, N, sh, L, gl, H, counts);
   } else {
     long long S = (npack + kCntThreads - 1) / kCntThreads;
     if (S > 2LL * h->sm_count) S = 2LL * h->sm_count;
     if (S < 1) S = 1;
-    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, 1), kCntThreads, 0, st>>>((const BinT*)bins.p, N, sh, L, L, 0,
-                                                                                      H, counts);
+    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, 1), kCntThreads, 0, st>>>((const BinT*)bins.p, N, sh, L, L, H,
+                                                                                      counts);
   }
   TRAJ_TRY(cudaGetLastError());
   h->launches++;

@@ -1,6 +1,5 @@
 """Trajectory -> counts (mcd_traj_counts) on the bench workload: 2^28 coordinates, 100 bins, 4 shifts.
-  python profiles/prof_traj.py            CUDA-event time per call for the accumulation variants
-                                          (MCDIFF_B200_TRAJ_L2 = shifts per group sent to L2 atomics, CTA size)
+  python profiles/prof_traj.py            CUDA-event time per call for 4 / 1 / 2 / 11 shifts and one long trajectory
   python profiles/prof_traj.py once       three calls of the default configuration (for ncu)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -39,14 +38,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "once":
     sys.exit(0)
 
 nbytes = 8.0 * T * M
-for thr in (1024, 512):
-    for l2 in (0, 1, 2, 3, 4):
-        os.environ["MCDIFF_B200_TRAJ_L2"] = str(l2)
-        os.environ["MCDIFF_B200_TRAJ_THREADS"] = str(thr)
-        ms = timed()
-        print("threads=%4d shifts_in_L2=%d  %.3f ms/call  %.0f GB/s algorithmic" % (thr, l2, ms, nbytes / ms / 1e6))
-os.environ["MCDIFF_B200_TRAJ_L2"] = "0"
-os.environ["MCDIFF_B200_TRAJ_THREADS"] = "1024"
+ms = timed()
+print("shifts= 4  %.3f ms/call  %.0f GB/s algorithmic" % (ms, nbytes / ms / 1e6))
 for sh in ([10], [10, 20], [1, 2, 3, 4, 5, 10, 15, 20, 30, 40, 50]):
     ms = timed(sh=sh)
     print("shifts=%2d  %.3f ms/call  %.0f GB/s algorithmic" % (len(sh), ms, nbytes / ms / 1e6))
