@@ -203,50 +203,68 @@ mcd_traj_count_kernel(const BinT* __restrict__ bins, long long N, Shifts sh, int
   const long long npack = (N + 3) >> 2;
   const long long nfast = (N - 3 - maxoff) >> 2;   // packs p < nfast: all four partners of every shift exist
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npack; p += stride) {
-    const long long i = p << 2;
-    const word s4 = P::load_aligned(bins, p);
+  // fast packs (every partner exists): at most four shifts per CTA (mcd_traj_counts caps the group), software
+  // pipelined -- the nine word loads of the next pack are in flight while the 16 increments of this one issue
+  long long off[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) off[q] = sh.off[l0 + (q < nl ? q : 0)];
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  word s4 = 0, e4[4] = {0, 0, 0, 0};
+  if (p < nfast) {
+    s4 = P::load_aligned(bins, p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e4[q] = (q < nl) ? P::load(bins, (p << 2) + off[q]) : 0;
+  }
+  while (p < nfast) {
+    const long long pn = p + stride;
+    word s4n = 0, e4n[4] = {0, 0, 0, 0};
+    if (pn < nfast) {
+      s4n = P::load_aligned(bins, pn);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e4n[q] = (q < nl) ? P::load(bins, (pn << 2) + off[q]) : 0;
+    }
     const int s0 = P::get(s4, 0), s1 = P::get(s4, 1), s2 = P::get(s4, 2), s3 = P::get(s4, 3);
-    if (p < nfast) {
-      // shifts four at a time: the partner loads of a group are issued together, then its 16 increments
-      for (int k0 = 0; k0 < nl; k0 += 4) {
-        word e4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) e4[q] = (k0 + q < nl) ? P::load(bins, i + sh.off[l0 + k0 + q]) : 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (k0 + q < nl) {
-            const int c0 = P::get(e4[q], 0) * H + s0, c1 = P::get(e4[q], 1) * H + s1;   // A[end, start] += 1
-            const int c2 = P::get(e4[q], 2) * H + s2, c3 = P::get(e4[q], 3) * H + s3;   // (extract.py:86-87)
-            if (kSmem) {
-              // byte offsets end * 4H + 4 start against the (warp-uniform) base of this shift's histogram: three
-              // instructions per increment (byte extract, multiply-add, ATOMS [reg + uniform])
-              char* hk = reinterpret_cast<char*>(hist + (k0 + q) * HH);
-              const int H4 = 4 * H;
-              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 0) * H4 + 4 * s0)), 1u);
-              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 1) * H4 + 4 * s1)), 1u);
-              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 2) * H4 + 4 * s2)), 1u);
-              atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 3) * H4 + 4 * s3)), 1u);
-            } else {
-              unsigned long long* ok = outg + (size_t)(k0 + q) * HH;
-              atomicAdd(ok + c0, 1ull); atomicAdd(ok + c1, 1ull); atomicAdd(ok + c2, 1ull); atomicAdd(ok + c3, 1ull);
-            }
-          }
+    for (int q = 0; q < 4; ++q) {
+      if (q < nl) {
+        if (kSmem) {
+          // byte offsets end * 4H + 4 start against the (warp-uniform) base of this shift's histogram: three
+          // instructions per increment (byte extract, multiply-add, ATOMS [reg + uniform]); A[end, start] += 1
+          char* hk = reinterpret_cast<char*>(hist + q * HH);
+          const int H4 = 4 * H;
+          atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 0) * H4 + 4 * s0)), 1u);
+          atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 1) * H4 + 4 * s1)), 1u);
+          atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 2) * H4 + 4 * s2)), 1u);
+          atomicAdd(reinterpret_cast<unsigned*>(hk + (P::get(e4[q], 3) * H4 + 4 * s3)), 1u);
+        } else {
+          unsigned long long* ok = outg + (size_t)q * HH;
+          atomicAdd(ok + (P::get(e4[q], 0) * H + s0), 1ull);
+          atomicAdd(ok + (P::get(e4[q], 1) * H + s1), 1ull);
+          atomicAdd(ok + (P::get(e4[q], 2) * H + s2), 1ull);
+          atomicAdd(ok + (P::get(e4[q], 3) * H + s3), 1ull);
         }
       }
-    } else {   // the last max(shift) frames: partner by partner
-      const int sv[4] = {s0, s1, s2, s3};
-      for (int k = 0; k < nl; ++k) {
-        const long long j = i + sh.off[l0 + k];
-        if (j >= N) continue;
-        const word e4 = P::load(bins, j);
+    }
+    s4 = s4n;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (j + e < N) {
-            const int cell = P::get(e4, e) * H + sv[e];
-            if (kSmem) atomicAdd(&hist[k * HH + cell], 1u);
-            else atomicAdd(&outg[(size_t)k * HH + cell], 1ull);
-          }
+    for (int q = 0; q < 4; ++q) e4[q] = e4n[q];
+    p = pn;
+  }
+  // the last max(shift) frames: partner by partner
+  for (; p < npack; p += stride) {
+    const long long i = p << 2;
+    const word t4 = P::load_aligned(bins, p);
+    const int sv[4] = {P::get(t4, 0), P::get(t4, 1), P::get(t4, 2), P::get(t4, 3)};
+    for (int k = 0; k < nl; ++k) {
+      const long long j = i + sh.off[l0 + k];
+      if (j >= N) continue;
+      const word w4 = P::load(bins, j);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e < N) {
+          const int cell = P::get(w4, e) * H + sv[e];
+          if (kSmem) atomicAdd(&hist[k * HH + cell], 1u);
+          else atomicAdd(&outg[(size_t)k * HH + cell], 1ull);
         }
       }
     }
@@ -339,6 +357,7 @@ int counts_impl(mcd_handle* h, const double* x, long long nframes, long long nco
   const long long npack = (N + 3) / 4;
   if (gl >= 1) {
     if (gl > L) gl = L;
+    if (gl > 4) gl = 4;   // the count kernel pipelines one group of at most four shifts
     const int G = (L + gl - 1) / gl;
     gl = (L + G - 1) / G;   // balanced groups
     long long S = h->sm_count / G;
@@ -353,8 +372,8 @@ int counts_impl(mcd_handle* h, const double* x, long long nframes, long long nco
     long long S = (npack + kCntThreads - 1) / kCntThreads;
     if (S > 2LL * h->sm_count) S = 2LL * h->sm_count;
     if (S < 1) S = 1;
-    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, 1), kCntThreads, 0, st>>>((const BinT*)bins.p, N, sh, L, L, H,
-                                                                                      counts);
+    mcd_traj_count_kernel<BinT, false><<<dim3((unsigned)S, (unsigned)((L + 3) / 4)), kCntThreads, 0, st>>>(
+        (const BinT*)bins.p, N, sh, L, 4, H, counts);
   }
   TRAJ_TRY(cudaGetLastError());
   h->launches++;
