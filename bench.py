@@ -444,7 +444,8 @@ def run_gpu(args):
     st3 = ch3.host_state()
     secondary["config3_200bins_8lags"] = {
         "value": float(world) * 512 * C3_MC * sec_steps / (ms3 * 1e-3), "unit": UNIT, "chains_per_gpu": 512,
-        "mc_steps_per_launch": C3_MC, "launches": sec_steps, "kernel": "mcd_mc_run_blk_kernel",
+        "mc_steps_per_launch": C3_MC, "launches": sec_steps,
+        "kernel": "mcd_mc_run_blk_kernel (444 chains = 3 full waves) + mcd_mc_run_blk2_kernel (68 chains on two-CTA clusters)",
         "kernel_ms_per_launch": k3, "algorithmic_flops_per_mc_step": fl3,
         "achieved_tflops": 512 * C3_MC * fl3 / (k3 * 1e-3) / 1e12,
         "frac": 512 * C3_MC * fl3 / (k3 * 1e-3) / 1e12 / peak_tf,
@@ -612,7 +613,7 @@ def run_gpu(args):
     e2e_reps = max(2, min(args.steps, 3))
     E2E_NMC = 1000
     e2e_value, e2e_s, h2d, d2h = e2e_leg(world * nch, E2E_NMC, e2e_reps, "e2e")
-    strong_value, strong_s, _, _ = e2e_leg(STRONG_CHAINS, MC_PER_LAUNCH, 2, "strong")
+    strong_value, strong_s, _, _ = e2e_leg(STRONG_CHAINS, E2E_NMC, 2, "strong")
 
     if world > 1:
         dist.barrier()
@@ -674,7 +675,7 @@ def run_gpu(args):
                 "steps": e2e_reps, "seconds_per_step": e2e_s,
                 "api": "mcdiff_b200.mc.find_parameters (= run-mcdiff): %d transition files in, .dat/.pic/.pic.ave.dat/"
                        ".chains.npz out, %d chains x %d MC steps, gathers included" % (L, world * nch, E2E_NMC)},
-        "strong": {"value": strong_value, "unit": UNIT, "chains_total": STRONG_CHAINS, "mc_steps": MC_PER_LAUNCH,
+        "strong": {"value": strong_value, "unit": UNIT, "chains_total": STRONG_CHAINS, "mc_steps": E2E_NMC,
                    "seconds": strong_s, "api": "find_parameters, fixed total chains over %d GPU(s)" % world},
         "secondary": secondary,
         "gpu_launches": int(launches),

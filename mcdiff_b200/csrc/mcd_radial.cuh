@@ -261,7 +261,9 @@ struct RadCtx {
   // loads are issued before the MMAs and the logarithms are branch-free (one per pair and bin:
   // log P_ij = log p + (v_j - v_i)/2, log P_ji = log p - (v_j - v_i)/2, clip as lib/twod.py:29).
   // Returns false (nothing done) when the shapes do not fit; the vector-pipe version below then runs.
-  static constexpr int kBinGroup = 6;   // radial-bin tiles (8 bins each) accumulated at a time
+  // radial-bin tiles (8 bins each) accumulated at a time: 3 x 2 x kBinGroup doubles per lane.  The 128-thread build has 128
+  // registers per thread (four chains per SM) and spilled most of a group of 6 (ptxas: 960 bytes of stack)
+  static constexpr int kBinGroup = (kThreads <= 128) ? 3 : 6;
   __device__ __forceinline__ bool bessel_sums_mma(double* Pb, int NB) {
     const int n = R.n, np = R.np, ld = R.ld, lmax = R.lmax, dim_rad = R.dim_rad;
     const size_t me = (size_t)np * ld;
