@@ -50,7 +50,7 @@ STRONG_CHAINS = 4096
 METRIC = "MC steps/sec (all chains, 100 bins x 4 lags)"
 UNIT = "MC steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 chains x 200 steps), ncu --set full, see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {"mcd_mc_run_kernel<true>": 3954944 + 56320, "mcd_mc_run_sq_kernel": 3954944 + 56320}
+NCU_DRAM_BYTES_PER_LAUNCH = {"mcd_mc_run_kernel<true>": 3954944 + 56320, "mcd_mc_run_sq_kernel": 3990528 + 33280}
 
 
 def flops_per_mc_step(n, L):
@@ -575,7 +575,9 @@ def run_gpu(args):
         "frames": TR_T, "particles": TR_M, "bins": TR_BINS, "shifts": tr_shifts, "launches": sec_steps,
         "kernels": ["mcd_traj_digitize_kernel", "mcd_traj_count_kernel"], "ms_per_call": ktr,
         "roofline": {"bound": "hbm", "achieved": tr_bytes / (ktr * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": tr_bytes / (ktr * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "frac": tr_bytes / (ktr * 1e-3) / 1e9 / hbm_peak,
+                     # dram__bytes_read + write of the two kernels of one call (ncu --set full, profiles/r02_ncu_full_traj_*.csv)
+                     "traffic": 2147514000 + 214921000 + 268601000 + 4628000, "peak_source": hbm_src,
                      "algorithmic_bytes_per_coordinate": 8},
         "pairs_counted_ok": bool(tr_total == tr_expect),
         "workload": "synthetic random walks, periodic fold at zpbc=50, 100 bins (+2 outside), shifts = the headline's "

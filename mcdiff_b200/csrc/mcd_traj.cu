@@ -136,10 +136,18 @@ mcd_traj_digitize_kernel(const double* __restrict__ x, long long N, double perio
     using P = Pack4<BinT>;
     const long long npack = N >> 2;
     typename P::word* out = reinterpret_cast<typename P::word*>(bins);
+    // the 32 bytes of the next pack are requested before this one is digitized (ncu: long_scoreboard was the top stall)
+    double2 a = make_double2(0.0, 0.0), b = a;
+    if (t0 < npack) {
+      a = __ldcs(reinterpret_cast<const double2*>(x) + 2 * t0);
+      b = __ldcs(reinterpret_cast<const double2*>(x) + 2 * t0 + 1);
+    }
     for (long long p = t0; p < npack; p += stride) {
-      const double2 a = __ldcs(reinterpret_cast<const double2*>(x) + 2 * p);
-      const double2 b = __ldcs(reinterpret_cast<const double2*>(x) + 2 * p + 1);
       double v[4] = {a.x, a.y, b.x, b.y};
+      if (p + stride < npack) {
+        a = __ldcs(reinterpret_cast<const double2*>(x) + 2 * (p + stride));
+        b = __ldcs(reinterpret_cast<const double2*>(x) + 2 * (p + stride) + 1);
+      }
       if (do_fold) {
         double f[4];
         unsigned unsafe = 0;
