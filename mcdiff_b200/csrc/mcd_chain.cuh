@@ -2215,40 +2215,36 @@ struct Chain {
     const bool tr = K > I;
     const int bi = tr ? I : K, bj = tr ? K : I;
     const bool diag = (bi == bj);
-    // one item = one row (8 doubles = four 16-byte chunks) of one tile
-    const int nitems = t13 * t13 * 8;
-    for (int e = tid; e < nitems; e += Exec::nthr()) {
-      const int tile = e >> 3, r = e & 7;
-      const int ta = tile / t13, tb = tile - ta * t13;
-      if (diag && ta > tb) continue;
-      const double* src = G + (size_t)pk_tile(bi * t13 + ta, bj * t13 + tb, nb8) * 64 + r * 8;
-      double* drow = dst + (size_t)(ta * 8 + r) * lds + tb * 8;
-      const int sw = ((r >> 1) & 1) << 1;                       // stored chunk cs holds logical chunk cs ^ sw
+    // One warp instruction = one tile: the 32 lanes copy the 32 16-byte chunks of the 512 contiguous bytes of a stored
+    // tile (16 full sectors per request).  The first version gave a lane a tile ROW and issued its four chunks one after
+    // the other: every request touched 32 half-used sectors spread over four tiles, and issuing a panel took ~9 k cycles
+    // (phase clocks) -- the copies were bound by L2 -> SM transactions, not bytes.
+    const int warp = tid >> 5, lane = tid & 31, nwarp = Exec::nthr() / 32;
+    const int r = lane >> 2, cs = lane & 3;
+    const int sw = ((r >> 1) & 1) << 1;                         // stored chunk cs holds logical chunk cs ^ sw
+    const int c = (cs ^ sw) * 2;                                // first of the two logical columns of this lane's chunk
+    // tiles warp, warp + nwarp, ... in row-major order; (ta, tb) advance without a division
+    int ta = warp / t13, tb = warp - ta * t13;
+    for (int tile = warp; tile < t13 * t13; tile += nwarp, tb += nwarp) {
+      while (tb >= t13) { tb -= t13; ++ta; }
+      {
+        if (diag && ta > tb) continue;
+        const double* src = G + (size_t)pk_tile(bi * t13 + ta, bj * t13 + tb, nb8) * 64 + r * 8 + 2 * cs;
+        double* d = dst + (size_t)(ta * 8 + r) * lds + tb * 8 + c;
 #if defined(__CUDA_ARCH__)
-      const unsigned d0 = (unsigned)__cvta_generic_to_shared(drow);
-#pragma unroll
-      for (int cs = 0; cs < 4; ++cs)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (unsigned)(((cs ^ sw) * 2) * 8)), "l"(src + 2 * cs) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(src) : "memory");
 #else
-      for (int cs = 0; cs < 4; ++cs) { drow[(cs ^ sw) * 2] = src[2 * cs]; drow[(cs ^ sw) * 2 + 1] = src[2 * cs + 1]; }
+        d[0] = src[0]; d[1] = src[1];
 #endif
-      if (diag && ta < tb) {                                     // mirror image of the tile row: column r of tile (tb, ta)
-        // the four loads first (one L2 round trip per tile row), then the eight scattered stores
-        d2 x[4];
-#pragma unroll
-        for (int cs = 0; cs < 4; ++cs) {
+        if (diag && ta < tb) {                                   // mirror image: columns c, c + 1 of row r -> tile (tb, ta)
 #if defined(__CUDA_ARCH__)
-          const double2 xg = MCD_LD_PEER(reinterpret_cast<const double2*>(src + 2 * cs));
-          x[cs] = d2{xg.x, xg.y};
+          const double2 xg = MCD_LD_PEER(reinterpret_cast<const double2*>(src));
+          const d2 x = d2{xg.x, xg.y};
 #else
-          x[cs] = ld2(src + 2 * cs);
+          const d2 x = ld2(src);
 #endif
-        }
-#pragma unroll
-        for (int cs = 0; cs < 4; ++cs) {
-          const int c = (cs ^ sw) * 2;
-          dst[(size_t)(tb * 8 + c) * lds + ta * 8 + r] = x[cs].x;
-          dst[(size_t)(tb * 8 + c + 1) * lds + ta * 8 + r] = x[cs].y;
+          dst[(size_t)(tb * 8 + c) * lds + ta * 8 + r] = x.x;
+          dst[(size_t)(tb * 8 + c + 1) * lds + ta * 8 + r] = x.y;
         }
       }
     }

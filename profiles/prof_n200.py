@@ -39,5 +39,6 @@ if hasattr(eng.lib, "mcd_debug_phase_clocks"):      # -DMCD_PHASE_CLOCK build (M
              12: "Metropolis", 13: "commit, records"}
     tot = float(sum(out))
     print("cycles per MC step (CTA 0): %.0f" % (tot / nsteps))
-    for i in sorted(names):
-        print("%2d %-50s %9.0f cycles/step %5.1f %%" % (i, names[i], out[i] / nsteps, 100.0 * out[i] / tot))
+    for i in range(32):
+        if out[i]:
+            print("%2d %-50s %9.0f cycles/step %5.1f %%" % (i, names.get(i, "(phase %d)" % i), out[i] / nsteps, 100.0 * out[i] / tot))
