@@ -45,13 +45,13 @@ def do_mc_cycles(MC, logger, chunk=1000):
     nw = m.ncosD if m.ncosD > 0 else m.dim_w
     pv = MC.chain_v_coeff if m.ncosF > 0 else MC.chain_v
     pw = MC.chain_w_coeff if m.ncosD > 0 else MC.chain_w
-    row0 = np.zeros((1, 6 + nv + nw))
-    for c in range(MC.nchains):
-        row0[0, :6] = (MC.chain_log_like[c], MC.chain_timezero[c], MC.chain_dv[c], MC.chain_dw[c], MC.dtimezero,
-                       MC.chain_temp[c])
-        row0[0, 6:6 + nv] = pv[c]
-        row0[0, 6 + nv:] = pw[c]
-        logger.fill_rows(c, 0, row0, m)
+    row0 = np.zeros((MC.nchains, 1, 6 + nv + nw))
+    row0[:, 0, 0], row0[:, 0, 1] = MC.chain_log_like, MC.chain_timezero
+    row0[:, 0, 2], row0[:, 0, 3] = MC.chain_dv, MC.chain_dw
+    row0[:, 0, 4], row0[:, 0, 5] = MC.dtimezero, MC.chain_temp
+    row0[:, 0, 6:6 + nv] = pv
+    row0[:, 0, 6 + nv:] = pw
+    logger.fill_rows_all(0, row0, m)
     done = 0
     next_row = 1
     while done < MC.nmc:

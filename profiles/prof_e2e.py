@@ -6,6 +6,8 @@ import torch
 import bench
 from mcdiff_b200.mc import find_parameters
 
+NCH = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+NMC = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 tmp = tempfile.mkdtemp(prefix="mcd_e2e_")
 bench.headline_files(tmp)
 files = [os.path.join(tmp, "transitions.nbins%d.%d.pbc.dat" % (bench.N_BINS, int(l))) for l in bench.LAGS]
@@ -14,9 +16,9 @@ sink = io.StringIO()
 
 def call():
     with contextlib.redirect_stdout(sink):
-        find_parameters(files, True, "CosinusModel", bench.DV, bench.DW, 0.5, 1.0, 0.1, 1.0, 1.0, 1000, bench.NMC_UPDATE, 1,
+        find_parameters(files, True, "CosinusModel", bench.DV, bench.DW, 0.5, 1.0, 0.1, 1.0, 1.0, NMC, bench.NMC_UPDATE, 1,
                         os.path.join(tmp, "e2e.dat"), bench.NCOS_F, bench.NCOS_D, 0, False, None, -1, -1, False, None,
-                        nchains=1024, device=0, chunk=bench.MC_PER_LAUNCH)
+                        nchains=NCH, device=0)
     torch.cuda.synchronize()
 
 
