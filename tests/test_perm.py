@@ -147,3 +147,15 @@ def test_device_propagator_batch_mixed_items(engine, n):
     vbad[2, 5] = np.nan
     _, status = prob.propagators(vbad, w, times, sink=sink)
     assert status[2] != 0 and not np.delete(status, 2).any()
+
+
+def test_host_cut_argument_checks():
+    from mcdiff_b200.permeability import absorbing_cut
+    v, w = np.zeros(10), np.zeros(10)
+    for st, end in ((-2, 5), (3, 11), (4, 5), (9, 10)):          # the asserts of lib/utils.py:66-68
+        with pytest.raises(AssertionError):
+            absorbing_cut(v, w, st, end, "both")
+    with pytest.raises(AssertionError):
+        absorbing_cut(v, np.zeros(9), 2, 8, "both")              # the cut is taken from the periodic matrix
+    vs, ws, sink = absorbing_cut(v, w, None, None, None)         # st = -1, end = n, both ends reflective
+    assert len(vs) == 10 and len(ws) == 9 and not sink.any()

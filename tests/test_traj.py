@@ -142,3 +142,23 @@ def test_device_counts_argument_errors(engine):
     assert call(100, 0) < 0 and call(1, 1) < 0 and call(100, 1, 65) < 0 and call(100, 99) == 0
     torch.cuda.synchronize()
     assert int(out.sum()) == 1
+
+
+# ---------------------------------------------------------------- CPU: host-side argument handling (no device call is reached)
+def test_host_argument_checks():
+    from mcdiff_b200 import extract as X
+    with pytest.raises(ValueError):
+        X._check_edges([0.0, 2.0, 1.0])                         # np.digitize's other numbering is never used by the reference
+    with pytest.raises(ValueError):
+        X._check_edges([[0.0, 1.0]])
+    assert X._check_edges(np.arange(5)).dtype == np.float64
+    with pytest.raises(AssertionError):
+        X._shifts([5], 5)                                       # lib/tools/extract.py:73: shift < len(x)
+    with pytest.raises(AssertionError):
+        X._shifts([0], 5)
+    assert X._shifts(3, 10).tolist() == [3]
+    A = np.zeros((4, 4), int)
+    with pytest.raises(AssertionError):
+        X.transition_matrix_add1(A, np.zeros(10), np.arange(5.0), shift=1)      # len(A) == len(edges) + 1
+    with pytest.raises(AssertionError):
+        X.count_2D(np.zeros((3, 4, 4)), None, None, None, np.arange(3.0), np.arange(4.0))   # B.shape[0] == len(redges)
