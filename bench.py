@@ -631,7 +631,7 @@ def run_gpu(args):
                    else ("squaring_dfma" if args.method == "squaring_dfma" else "squaring_dmma"))
     # executed tensor-core flops: (squarings + L - 1) symmetric products of 12 warp tasks x 8 tiles x (np / 4) m8n8k4
     # (512 flop each); squarings per step is counted by the kernel.  ncu's DMMA instruction count agrees (profiles/).
-    executed = (squarings + L - 1) * 96 * (prob.np // 4) * 512.0 if engine_name == "squaring_dmma" else None
+    executed = (squarings + L - 1) * 96 * ((N_BINS + 3) // 4) * 512.0 if engine_name == "squaring_dmma" else None
     cpu = None
     if world == 1:
         for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS"):

@@ -1001,7 +1001,9 @@ struct Chain {
         for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = task.jb[t] * 64;
         const unsigned ax = (unsigned)__cvta_generic_to_shared(X) + (unsigned)(fk * ld + fr) * 8u;
         const unsigned ay = (unsigned)__cvta_generic_to_shared(Y) + (unsigned)(fk * ld + fr) * 8u;
-        const int pitch4 = 4 * ld * 8, nk4 = np / 4;
+        // rows k >= n of both operands are padding (zero): the k loop stops at the last group of four that holds a
+        // real row -- 25 instead of 26 steps at 100 bins
+        const int pitch4 = 4 * ld * 8, nk4 = (n + 3) >> 2;
         switch (na) {
           case 1: mma_loop<1>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
           case 2: mma_loop<2>(ax, ay, pitch4, nk4, rowA * 64, rowB * 64, offB, c); break;
@@ -1708,7 +1710,7 @@ struct Chain {
           int offB[kTilesPerWarp];
 #pragma unroll
           for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = (jb0 + ((t < nt) ? t : 0)) * 64;
-          const int pitch4 = 4 * ld * 8, nk4 = np / 4;
+          const int pitch4 = 4 * ld * 8, nk4 = (P.n + 3) >> 2;   // columns k >= n of X / rows k >= n of Y are zero padding
 #pragma unroll 2
           for (int it = 0; it < nk4; ++it) {
             const double a0 = lds64(ax);
@@ -2357,7 +2359,8 @@ struct Chain {
           int offB[kTilesPerWarp];
 #pragma unroll
           for (int t = 0; t < kTilesPerWarp; ++t) offB[t] = jbs[t] * tileB;
-          const int nk4 = nbk / 4;
+          // the last K block ends with padding rows (zero in both operands): stop at the last group of four real rows
+          const int nk4 = fin ? ((n - (P.nblk - 1) * nbk + 3) >> 2) : nbk / 4;
           switch (na) {
             case 1: mma_loop2<1>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
             case 2: mma_loop2<2>(pa, pb, stepA, stepB, nk4, rowA * tileA, rowB * tileA, offB, c); break;
