@@ -262,7 +262,7 @@ struct Smem {
   unsigned char* wtab;     // 16 bytes per warp task of the tensor-core product (see build_tables)
   unsigned char* hrow;     // Horner passes: band row owned by thread tid (tid / tpr) ...
   unsigned char* hrem;     // ... and its slot inside the row (tid % tpr); 255 = no row
-  unsigned char* tord;     // Taylor order for s = 0..31 squarings
+  unsigned char* tord;     // Taylor order for s = 0..31 squarings at argument bound kTheta; [32 + s]: at kThetaHi (255: none)
   Scalars* sc;
   int ntiles, nblk;
 };
@@ -275,7 +275,7 @@ MCD_HOSTDEV size_t smem_vectors_bytes(int np, bool panels = false) {
   size_t nb = np / 4, h = np / 2;
   size_t bytes = d * 8 + (panels ? 0 : (size_t)np * 4) /*rp,rq*/ + 64 * kMaxTasks /*wti*/ +
                  (panels ? 0 : nb * (nb + 1) + h * (h - 1)) + 16 * kMaxTasks + sizeof(Scalars) + 64 +
-                 2 * kThreads + 32 /*hrow, hrem, tord*/;
+                 2 * kThreads + 64 /*hrow, hrem, tord (two tables of 32)*/;
   return (bytes + 15) & ~(size_t)15;
 }
 MCD_HOSTDEV size_t smem_matrix_bytes(int np, int ld) { return (size_t)2 * np * ld * 8; }
@@ -384,7 +384,10 @@ struct Chain {
       const int row = tid / tpr;
       s.hrow[tid] = (unsigned char)((row < P.n && row < 255) ? row : 255);
       s.hrem[tid] = (unsigned char)(tid - row * tpr);
-      if (tid < 32) s.tord[tid] = (unsigned char)taylor_order(tid, 0);
+      if (tid < 32) {
+        s.tord[tid] = (unsigned char)taylor_order(tid, 0);
+        s.tord[32 + tid] = (unsigned char)taylor_order_hi(tid);
+      }
     });
     ex.single([&]() {
       // 4x4 tile table: DFMA products, and buffer_loglike of every full-storage engine (the tensor-only kernel needs it for
@@ -1120,6 +1123,21 @@ struct Chain {
     return m < 6 ? 6 : m;
   }
 
+  // One squaring less when the argument allows it: with s - 1 squarings the argument is twice as large, in (2, 4]; up to
+  // kThetaHi = 2.8 the Taylor order that keeps 2^s theta^(m+1)/(m+1)! <= 1e-17 still fits the register window (m <= 30
+  // for s <= 10), i.e. four more Taylor passes (~1 % of a step) instead of a dense product (~7 %) for the 48 % of the
+  // arguments that fall in (2, 2.8].  255: the bound is not reached with m <= 30 (no stretch).
+  static constexpr double kThetaHi = 2.8;
+  static MCD_HD int taylor_order_hi(int nsq) {
+    double term = ldexp(kThetaHi, nsq);
+    int m = 1;
+    while (m < 30 && !(term * kThetaHi / (double)(m + 1) <= 1.0e-17)) {
+      term = term * kThetaHi / (double)(m + 1);
+      ++m;
+    }
+    return (term * kThetaHi / (double)(m + 1) <= 1.0e-17) ? (m < 6 ? 6 : m) : 255;
+  }
+
   // How exp(tS) is reached: T = e^{-hc} T_m(h(S + cI)), then nsq squarings.
   struct TaylorPlan {
     int nsq, m, ring;
@@ -1136,9 +1154,14 @@ struct Chain {
       const double fr2 = frexp(y, &ex2);               // y = fr2 2^ex2, fr2 in [0.5, 1)
       nsq = (fr2 == 0.5) ? ex2 - 1 : ex2;
     }
+    int m_auto = s.tord[nsq];
+    if (taylor_m <= 0 && nsq >= 1 && ldexp(y, 1 - nsq) * kTheta <= kThetaHi && s.tord[32 + nsq - 1] != 255) {
+      --nsq;                                            // argument (rho/2) / 2^nsq in (kTheta, kThetaHi]
+      m_auto = s.tord[32 + nsq];
+    }
     tp.nsq = nsq;
     tp.h = ldexp(t, -nsq);
-    tp.m = (taylor_m > 0) ? (taylor_m < 30 ? taylor_m : 30) : s.tord[nsq];
+    tp.m = (taylor_m > 0) ? (taylor_m < 30 ? taylor_m : 30) : m_auto;
     tp.m += tp.m & 1;                                   // the passes are done in pairs (taylor_lane): a higher order only helps
     tp.shift = 0.5 * gersh;
     tp.scale = exp(-tp.h * tp.shift);
