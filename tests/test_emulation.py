@@ -472,3 +472,26 @@ def test_tensor_only_engine_mc_replay():
             assert abs(ch.scal[c][0] - out["ll"]) <= 1e-9 * abs(out["ll"])
     finally:
         H.use_threads(None)
+
+
+@pytest.mark.parametrize("n,pbc,lag", [(31, True, 11.0), (64, False, 7.0), (100, True, 53.0)])
+def test_rough_profiles_on_the_production_build(n, pbc, lag):
+    """Rough profiles (v ~ N(0, 1.5), w ~ N(-1, 0.8): rates spread over three decades, 4..9 squarings, arguments in the
+    stretched Taylor range (2, 2.83]) on the production build of the squaring engine: log L to 1e-12 relative and
+    every propagator entry >= 1e-10 to 1e-9 relative (measured 8e-15 and 3e-13, scipy's own error included)."""
+    from oracle import mcdiff_oracle as O
+    rng = np.random.default_rng(n)
+    lags = np.array([lag, 2 * lag])
+    counts = (rng.poisson(2.0, size=(2, n, n)) * 5).astype(np.int64)
+    v = rng.normal(0.0, 1.5, (3, n))
+    w = rng.normal(-1.0, 0.8, (3, n if pbc else n - 1))
+    prob = H.HostProblem(counts, lags, pbc)
+    ll, P, st, _ = H.loglike_batch(prob, v, w, want_P=True, method=TENSOR_ONLY)
+    assert not st.any()
+    ref = np.array([O.log_like_lag(v[b], w[b], lags, counts, pbc) for b in range(3)])
+    np.testing.assert_allclose(ll, ref, rtol=1e-12)
+    for l in range(2):
+        Pref = O.propagator(v[0], w[0], lags[l], pbc)
+        big = Pref >= 1e-10
+        np.testing.assert_allclose(P[0, l][big], Pref[big], rtol=1e-9)
+        assert np.max(np.abs(P[0, l][~big] - Pref[~big]), initial=0.0) < 1e-14
