@@ -495,3 +495,27 @@ def test_rough_profiles_on_the_production_build(n, pbc, lag):
         big = Pref >= 1e-10
         np.testing.assert_allclose(P[0, l][big], Pref[big], rtol=1e-9)
         assert np.max(np.abs(P[0, l][~big] - Pref[~big]), initial=0.0) < 1e-14
+
+
+@pytest.mark.parametrize("L", [4, 5, 6, 7, 8])
+def test_blocked_engine_multiples_of_the_first_lag(L):
+    """Multiples t0 .. L t0 on the blocked engine (the fast plan: every lag product takes G(t0) as its operand), every
+    lag's likelihood terms and propagator against the oracle -- n = 110 (2 x 2 blocks of 56), non-periodic for odd L."""
+    from oracle import mcdiff_oracle as O
+    n, pbc = 110, (L % 2 == 0)
+    lags = 5.0 * np.arange(1, L + 1)
+    counts = O.synthetic_counts(n, lags, seed=L, total=2.0e5, dz=0.6)[0]
+    if not pbc:
+        counts = counts.copy()
+        counts[:, 0, n - 1] = 0
+        counts[:, n - 1, 0] = 0
+    rng = np.random.default_rng(L)
+    v = rng.normal(0.0, 0.5, (2, n))
+    w = -0.8 + rng.normal(0.0, 0.3, (2, n if pbc else n - 1))
+    prob = H.HostProblem(counts, lags, pbc)
+    ll, P, st, _ = H.loglike_batch(prob, v, w, want_P=True, method=SQUARING)
+    assert not st.any()
+    ref = np.array([O.log_like_lag(v[b], w[b], lags, counts, pbc) for b in range(2)])
+    np.testing.assert_allclose(ll, ref, rtol=1e-11)
+    for l, lag in enumerate(lags):
+        assert np.max(np.abs(P[1, l] - O.propagator(v[1], w[1], lag, pbc))) < 1e-12
