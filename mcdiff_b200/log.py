@@ -164,13 +164,20 @@ class Logger:
         a = self._profiles(self.v_coeff, self.model.v_basis)
         return np.mean(a, 0), np.std(a, 0)
 
-    def average_profile_w_from_coeff(self):
+    def average_profile_w_from_coeff(self, want_log=True):
+        """(mean w, std w, mean e^w, std e^w) over all stored rows; want_log=False skips the first two (None, None):
+        the result files only need the statistics of D = e^w, and every reduction is a pass over 9 M values at 8192
+        chains."""
         a = self._profiles(self.w_coeff, self.model.w_basis)
-        return np.mean(a, 0), np.std(a, 0), np.mean(np.exp(a), 0), np.std(np.exp(a), 0)
+        ea = np.exp(a)
+        lm, ls = (np.mean(a, 0), np.std(a, 0)) if want_log else (None, None)
+        return lm, ls, np.mean(ea, 0), np.std(ea, 0)
 
-    def average_profile_wrad_from_coeff(self):
+    def average_profile_wrad_from_coeff(self, want_log=True):
         a = self._profiles(self.wrad_coeff, self.model.wrad_basis)
-        return np.mean(a, 0), np.std(a, 0), np.mean(np.exp(a), 0), np.std(np.exp(a), 0)
+        ea = np.exp(a)
+        lm, ls = (np.mean(a, 0), np.std(a, 0)) if want_log else (None, None)
+        return lm, ls, np.mean(ea, 0), np.std(ea, 0)
 
     def print_MC_params(self, f=None, final=False):
         f = f or sys.stdout

@@ -134,7 +134,7 @@ def read_F_D_edges_logger(logger):
     if m.ncosD <= 0:
         d, dst = average_profile(np.exp(logger.w))
     else:
-        _, _, d, dst = logger.average_profile_w_from_coeff()
+        _, _, d, dst = logger.average_profile_w_from_coeff(want_log=False)
     unit = np.exp(m.wunit)
     return v * m.vunit, d * unit, m.edges, vst * m.vunit, dst * unit
 
@@ -146,6 +146,6 @@ def read_Drad_logger(logger):
     if getattr(m, "ncosDrad", 0) <= 0:
         drad, dradst = average_profile(np.exp(logger.wrad))
     else:
-        _, _, drad, dradst = logger.average_profile_wrad_from_coeff()
+        _, _, drad, dradst = logger.average_profile_wrad_from_coeff(want_log=False)
     unit = np.exp(m.wradunit)
     return drad * unit, m.redges, dradst * unit
