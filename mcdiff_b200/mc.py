@@ -92,7 +92,10 @@ def _write_outputs(MC, pooled, outfile):
         picfile = outfile + ".pic"
     pooled.model = MC.model
     pooled.dump(picfile)
-    write_average_from_pic(picfile, picfile + ".ave.dat")
+    # the reference re-reads the pickle it has just written (write_average_from_pic, lib/log.py:380-387); the Logger in
+    # memory holds the same rows, and un-pickling 8192 chains costs more than the statistics themselves
+    with open(picfile + ".ave.dat", "w") as f:
+        pooled.print_average(pooled.model, f=f)
 
 
 def _finish_radial(MC, logger, outfile, nmc, rank):

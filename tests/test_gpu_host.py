@@ -263,3 +263,21 @@ def test_other_model_families_on_device(engine, gold_ll, tmp_path, capsys, model
     assert (MC.naccv, MC.naccw) == (ref["naccv"], ref["naccw"])
     np.testing.assert_allclose(MC.log_like, ref["ll"], rtol=1e-9)
     np.testing.assert_allclose(MC.model.v_coeff, ref["v_coeff"], atol=1e-13)
+
+
+def test_posterior_statistics_on_the_device_equal_numpy(engine):
+    """Many chains: the Logger forms profile rows, exponentials and their mean / std on the GPU
+    (Logger._device_stats); same numbers as the numpy formulas of lib/log.py:90-106 to rounding."""
+    from mcdiff_b200.log import Logger
+    rng = np.random.default_rng(1)
+    rows, ncos, n = 20000, 6, 100
+    coeff = rng.normal(0, 0.3, size=(rows, ncos))
+    basis = rng.normal(0, 1.0, size=(n, ncos))
+    lg = Logger()
+    d = lg._device_stats(coeff, basis, True, True)
+    assert d is not None
+    a = coeff @ basis.T
+    ea = np.exp(a)
+    for got, want in zip(d, (np.mean(a, 0), np.std(a, 0), np.mean(ea, 0), np.std(ea, 0))):
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
+    assert lg._device_stats(coeff[:100], basis, True, True) is None          # few rows stay on the host
